@@ -1,0 +1,90 @@
+"""ctypes binding of libcldrd.so (include/cldrd.h).  No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcldrd.so")
+
+SCAN_SIMT_F32, SCAN_TC_TF32, SCAN_TC_F16, SCAN_TC_BF16 = 0, 1, 2, 3
+SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "fp16": SCAN_TC_F16,
+              "bf16": SCAN_TC_BF16}
+MAX_K = 2048
+
+E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
+
+
+class CldrdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libcldrd error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_c_i64p = C.POINTER(C.c_int64)
+_c_i32p = C.POINTER(C.c_int32)
+_c_f32p = C.POINTER(C.c_float)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "cldrd_last_error": (C.c_char_p, []),
+    "cldrd_abi_version": (C.c_int, []),
+    "cldrd_index_probe": (C.c_int, [C.c_char_p, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_i32p, _c_i64p, _c_i64p]),
+    "cldrd_index_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "cldrd_index_writer_begin": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "cldrd_index_writer_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "cldrd_index_writer_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cldrd_index_read_rows": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cldrd_index_read_ids": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cldrd_shard_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "cldrd_shard_destroy": (None, [C.c_void_p]),
+    "cldrd_shard_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "cldrd_shard_load_file": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cldrd_shard_adopt": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cldrd_shard_set_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cldrd_shard_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cldrd_shard_nrows": (C.c_int64, [C.c_void_p]),
+    "cldrd_shard_dim": (C.c_int32, [C.c_void_p]),
+    "cldrd_shard_scan": (C.c_int32, [C.c_void_p]),
+    "cldrd_shard_scan_bytes": (C.c_int64, [C.c_void_p]),
+    "cldrd_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),
+    "cldrd_shard_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cldrd_shard_last_scan_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _c_i64p]),
+    "cldrd_scan_dense_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cldrd_write_run": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _c_i64p]),
+    "cldrd_format_score": (C.c_int, [C.c_float, C.c_char_p]),
+}
+
+
+def lib():
+    """Load libcldrd.so.  There is no fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CldrdError(E_STATE, f"{LIB_PATH} is missing: build it with `make -C cl-drd_b200` "
+                                  f"(or `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU or "
+                                  f"PyTorch fallback for the search path")
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().cldrd_last_error()
+        raise CldrdError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def ptr(a) -> C.c_void_p:
+    """void* of a numpy array (host) — caller keeps the array alive."""
+    return C.c_void_p(a.ctypes.data)

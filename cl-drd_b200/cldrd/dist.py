@@ -1,0 +1,118 @@
+"""Row-sharded search with one process per GPU (torchrun), the B200-native form of the
+reference's `index_cpu_to_gpu_multiple(..., shard=True)` (retriever/retrieval_utils.py:174-182).
+
+rank r keeps passage rows shard_ranges(N, G)[r] resident in its HBM; queries are replicated;
+every rank runs the same fused search over its shard and emits [nq, k] (score, GLOBAL row);
+one NCCL gather over NVLink brings the candidate lists to rank 0, where the merge kernel
+(same u64 key order as the single-GPU search, so results are bit-identical) and the id_map
+gather finish the job.  torch.distributed is plumbing only; no collective touches the index.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib
+from .index import GpuIndexFlat, _Shard, shard_ranges
+
+
+def gather_candidates(D_local: torch.Tensor, I_local: torch.Tensor, dst: int = 0, group=None
+                      ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Gather per-rank [nq,k] candidate lists to `dst` as [world, nq, k].  Works for CUDA tensors
+    over NCCL and for CPU tensors over gloo (used by the CPU tests of this plumbing)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return D_local.unsqueeze(0), I_local.unsqueeze(0)
+    if rank == dst:
+        allD = torch.empty((world,) + tuple(D_local.shape), dtype=D_local.dtype, device=D_local.device)
+        allI = torch.empty((world,) + tuple(I_local.shape), dtype=I_local.dtype, device=I_local.device)
+        dist.gather(D_local.contiguous(), list(allD.unbind(0)), dst=dst, group=group)
+        dist.gather(I_local.contiguous(), list(allI.unbind(0)), dst=dst, group=group)
+        return allD, allI
+    dist.gather(D_local.contiguous(), None, dst=dst, group=group)
+    dist.gather(I_local.contiguous(), None, dst=dst, group=group)
+    return None, None
+
+
+def merge_candidates(allD: torch.Tensor, allI: torch.Tensor, id_map: Optional[torch.Tensor] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[P,nq,k] scores + global rows (CUDA) -> merged [nq,k] via the libcldrd merge kernel."""
+    assert allD.is_cuda and allD.dim() == 3 and allI.shape == allD.shape
+    P, n, k = allD.shape
+    allD, allI = allD.contiguous(), allI.contiguous()
+    outD = torch.empty((n, k), dtype=torch.float32, device=allD.device)
+    outI = torch.empty((n, k), dtype=torch.int64, device=allD.device)
+    st = torch.cuda.current_stream(allD.device).cuda_stream
+    check(lib().cldrd_merge(allD.device.index, C.c_void_p(allD.data_ptr()), C.c_void_p(allI.data_ptr()), P, n, k,
+                            C.c_void_p(id_map.data_ptr()) if id_map is not None else None,
+                            C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()), C.c_void_p(st)))
+    return outD, outI
+
+
+class ShardedSearcher:
+    """rank-local shard + the gather/merge step.  Build with `from_rows` (device rows already in
+    HBM, zero copy) or `from_file` (each rank preads only its own row range)."""
+
+    def __init__(self, shard: _Shard, ntotal: int, d: int, id_map: Optional[torch.Tensor], group=None):
+        self.shard = shard
+        self.local = GpuIndexFlat(shard, shard.nrows, d)
+        self.ntotal, self.d = ntotal, d
+        self.id_map = id_map  # int64 [ntotal] on rank 0's device, or None
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    @classmethod
+    def from_rows(cls, rows: torch.Tensor, row0: int, ntotal: int, scan: str = "auto",
+                  id_map: Optional[torch.Tensor] = None, group=None) -> "ShardedSearcher":
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous()
+        n, d = rows.shape
+        sh = _Shard(rows.device.index, row0, n, d, scan)
+
+        def filler(s: _Shard):
+            check(lib().cldrd_shard_adopt(s.handle, C.c_void_p(rows.data_ptr())))
+
+        sh.fill(filler)
+        sh._keepalive = rows
+        return cls(sh, ntotal, d, id_map, group)
+
+    @classmethod
+    def from_file(cls, path: str, device: int, scan: str = "auto", group=None) -> "ShardedSearcher":
+        n, d = C.c_int64(), C.c_int32()
+        has_ids = C.c_int32()
+        check(lib().cldrd_index_probe(str(path).encode(), C.byref(n), C.byref(d), None, C.byref(has_ids), None,
+                                      None, None))
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rr = shard_ranges(n.value, world)[rank]
+        sh = _Shard(device, rr.start, len(rr), d.value, scan)
+
+        def filler(s: _Shard):
+            check(lib().cldrd_shard_load_file(s.handle, str(path).encode()))
+            check(lib().cldrd_shard_set_ids(s.handle, None))  # ids are applied after the merge
+
+        sh.fill(filler)
+        id_map = None
+        if has_ids.value and rank == 0:
+            import numpy as np
+            ids = np.empty((n.value,), dtype=np.int64)
+            check(lib().cldrd_index_read_ids(str(path).encode(), 0, n.value, _lib.ptr(ids)))
+            id_map = torch.from_numpy(ids).to(f"cuda:{device}")
+        return cls(sh, n.value, d.value, id_map, group)
+
+    def search(self, q: torch.Tensor, k: int):
+        """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
+        D, I = self.local.search_device(q, k, translate_ids=False)
+        if self.world == 1:
+            if self.id_map is not None:
+                return merge_candidates(D.unsqueeze(0), I.unsqueeze(0), self.id_map)
+            return D, I
+        allD, allI = gather_candidates(D, I, dst=0, group=self.group)
+        if self.rank != 0:
+            return None, None
+        return merge_candidates(allD, allI, self.id_map)

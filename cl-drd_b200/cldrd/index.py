@@ -1,0 +1,527 @@
+"""The subset of the `faiss` Python API that CL-DRD's retriever scripts touch, backed by
+libcldrd.so.  Same names, argument meaning and error behaviour:
+
+    IndexFlatIP(d), IndexIDMap(index), IndexIDMap2(index), index_factory(d, "Flat", METRIC_INNER_PRODUCT)
+        retriever/index_text.py:91-97, retriever/retrieval_utils.py:119-128
+    write_index / read_index
+        retriever/index_text.py:105, retriever/retrieve_top_passages.py:85
+    StandardGpuResources, GpuClonerOptions, index_cpu_to_gpu,
+    GpuResourcesVector, IntVector, GpuMultipleClonerOptions, index_cpu_to_gpu_multiple
+        retriever/retrieval_utils.py:155-184
+    index.search(x, k) -> (D float32 [n,k], I int64 [n,k])
+        retriever/retrieval_utils.py:135,143
+
+There is no CPU search: a host-side index that is asked to search places itself on the current
+CUDA device first.  Without the CUDA library / a B200 every search raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import CldrdError, check, lib, ptr
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+
+def default_scan() -> str:
+    """Scan mode used when the caller does not pick one: CLDRD_SCAN env var, else "auto"
+    (fp16 scan when the values fit fp16, else tf32).  Every mode returns exact fp32 results."""
+    return os.environ.get("CLDRD_SCAN", "auto").lower()
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side index objects
+# ---------------------------------------------------------------------------------------------
+
+
+class _RowStore:
+    """fp32 rows either in host memory (blocks appended by add) or still in an index file."""
+
+    def __init__(self, d: int):
+        self.d = int(d)
+        self.blocks: List[np.ndarray] = []
+        self.n = 0
+        self.file: Optional[str] = None  # lazily loaded file-backed rows
+        self.file_n = 0
+
+    def add(self, x: np.ndarray) -> None:
+        if self.file is not None:
+            self.materialize()
+        self.blocks.append(np.ascontiguousarray(x, dtype=np.float32))
+        self.n += x.shape[0]
+
+    def materialize(self) -> np.ndarray:
+        if self.file is not None:
+            out = np.empty((self.file_n, self.d), dtype=np.float32)
+            check(lib().cldrd_index_read_rows(self.file.encode(), 0, self.file_n, ptr(out)))
+            self.blocks = [out]
+            self.file = None
+        if len(self.blocks) != 1:
+            self.blocks = [np.concatenate(self.blocks, axis=0) if self.blocks else
+                           np.empty((0, self.d), dtype=np.float32)]
+        return self.blocks[0]
+
+
+def _check_x(x, d: int, what: str) -> np.ndarray:
+    # faiss' SWIG wrapper asserts on shape and raises TypeError on dtype; same here
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what}: expected a numpy.ndarray, got {type(x).__name__}")
+    if x.dtype != np.float32:
+        raise TypeError(f"{what}: array must be float32, got {x.dtype}")
+    assert x.ndim == 2, f"{what}: expected a 2-D array"
+    assert x.shape[1] == d, f"{what}: dimension {x.shape[1]} != index dimension {d}"
+    return np.ascontiguousarray(x)
+
+
+class Index:
+    """Common behaviour of the host-side flat / id-map objects."""
+
+    d: int
+    metric_type = METRIC_INNER_PRODUCT
+    is_trained = True
+
+    def __init__(self):
+        self._gpu: Optional["GpuIndexFlat"] = None
+
+    def _invalidate(self):
+        if self._gpu is not None:
+            self._gpu.close()
+            self._gpu = None
+
+    def search(self, x, k):
+        """No CPU search exists: clone to the current CUDA device on first use, then search there."""
+        if self._gpu is None:
+            import torch  # device plumbing only
+            if not torch.cuda.is_available():
+                raise CldrdError(_lib.E_CUDA, "no CUDA device: this index has no CPU search path")
+            self._gpu = index_cpu_to_gpu(StandardGpuResources(), torch.cuda.current_device(), self)
+        return self._gpu.search(x, k)
+
+
+class IndexFlatIP(Index):
+    def __init__(self, d: int):
+        super().__init__()
+        self.d = int(d)
+        self._rows = _RowStore(d)
+
+    @property
+    def ntotal(self) -> int:
+        return self._rows.n
+
+    def add(self, x):
+        x = _check_x(x, self.d, "add")
+        self._invalidate()
+        self._rows.add(x)
+
+    def reset(self):
+        self._invalidate()
+        self._rows = _RowStore(self.d)
+
+    # helpers for the cloner / writer
+    def _ids(self) -> Optional[np.ndarray]:
+        return None
+
+
+class IndexIDMap(Index):
+    _fourcc2 = False
+
+    def __init__(self, index: IndexFlatIP):
+        super().__init__()
+        if not isinstance(index, IndexFlatIP):
+            raise TypeError("IndexIDMap wraps an IndexFlatIP here (the only case the retriever uses)")
+        assert index.ntotal == 0, "index must be empty on input"
+        self.index = index
+        self.d = index.d
+        self._id_blocks: List[np.ndarray] = []
+        self._ids_file: Optional[str] = None
+
+    @property
+    def ntotal(self) -> int:
+        return self.index.ntotal
+
+    @property
+    def _rows(self) -> _RowStore:
+        return self.index._rows
+
+    def add_with_ids(self, x, ids):
+        x = _check_x(x, self.d, "add_with_ids")
+        if not isinstance(ids, np.ndarray):
+            raise TypeError("add_with_ids: ids must be a numpy.ndarray")
+        if ids.dtype != np.int64:
+            raise TypeError(f"add_with_ids: ids must be int64, got {ids.dtype}")
+        assert ids.shape == (x.shape[0],), "add_with_ids: not same nb of vectors as ids"
+        self._invalidate()
+        self._load_ids()
+        self.index._rows.add(x)
+        self._id_blocks.append(np.ascontiguousarray(ids))
+
+    def add(self, x):
+        raise RuntimeError("add not implemented for this type of index (use add_with_ids)")
+
+    def _load_ids(self):
+        if self._ids_file is not None:
+            n = self.index._rows.file_n if self.index._rows.file is not None else self.index.ntotal
+            out = np.empty((n,), dtype=np.int64)
+            check(lib().cldrd_index_read_ids(self._ids_file.encode(), 0, n, ptr(out)))
+            self._id_blocks = [out]
+            self._ids_file = None
+
+    def _ids(self) -> np.ndarray:
+        self._load_ids()
+        if len(self._id_blocks) != 1:
+            self._id_blocks = [np.concatenate(self._id_blocks) if self._id_blocks else
+                               np.empty((0,), dtype=np.int64)]
+        return self._id_blocks[0]
+
+    @property
+    def id_map(self) -> np.ndarray:
+        return self._ids()
+
+
+class IndexIDMap2(IndexIDMap):
+    _fourcc2 = True
+
+
+def index_factory(d: int, description: str, metric: int = METRIC_L2):
+    """Only what retriever/retrieval_utils.py:119 asks for: a flat inner-product index."""
+    if description != "Flat":
+        raise RuntimeError(f"index_factory: only 'Flat' is supported here, got {description!r}")
+    if metric != METRIC_INNER_PRODUCT:
+        raise RuntimeError("index_factory: only METRIC_INNER_PRODUCT is supported here")
+    return IndexFlatIP(d)
+
+
+# ---------------------------------------------------------------------------------------------
+# index files
+# ---------------------------------------------------------------------------------------------
+
+
+def write_index(index, path: str) -> None:
+    if isinstance(index, (GpuIndexFlat, GpuIndexShards)):
+        raise RuntimeError("write_index: clone the index to CPU first (faiss behaves the same)")
+    rows = index._rows.materialize()
+    ids = index._ids()
+    check(lib().cldrd_index_write(str(path).encode(), ptr(rows), ptr(ids) if ids is not None else None,
+                                  rows.shape[0], index.d, 1 if getattr(index, "_fourcc2", False) else 0))
+
+
+def read_index(path: str):
+    """Parse the headers only; rows stay in the file until they are cloned to a GPU (straight
+    from the file into HBM) or until a host-side operation needs them."""
+    path = str(path)
+    n, d, metric = C.c_int64(), C.c_int32(), C.c_int32()
+    has_ids, idmap2 = C.c_int32(), C.c_int32()
+    doff, ioff = C.c_int64(), C.c_int64()
+    check(lib().cldrd_index_probe(path.encode(), C.byref(n), C.byref(d), C.byref(metric), C.byref(has_ids),
+                                  C.byref(idmap2), C.byref(doff), C.byref(ioff)))
+    flat = IndexFlatIP(d.value)
+    wrapped = (IndexIDMap2 if idmap2.value else IndexIDMap)(flat) if has_ids.value else None
+    flat._rows.file = path
+    flat._rows.file_n = n.value
+    flat._rows.n = n.value
+    if wrapped is None:
+        return flat
+    wrapped._ids_file = path
+    return wrapped
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------
+
+
+class StandardGpuResources:
+    """Kept for signature compatibility; libcldrd sizes its own workspace (about 1 GiB per shard)."""
+
+    def __init__(self):
+        self.temp_memory = None
+
+    def setTempMemory(self, nbytes: int):
+        self.temp_memory = int(nbytes)
+
+    def noTempMemory(self):
+        self.temp_memory = 0
+
+
+class GpuClonerOptions:
+    def __init__(self):
+        self.useFloat16 = False  # True: fp16 scan copy.  Results are exact fp32 either way.
+        self.scan = None         # extension: "simt" | "tf32" | "f16" | "bf16" | "auto"
+
+
+class GpuMultipleClonerOptions(GpuClonerOptions):
+    def __init__(self):
+        super().__init__()
+        self.shard = False
+
+
+class _Vector(list):
+    def push_back(self, v):
+        self.append(v)
+
+    def size(self):
+        return len(self)
+
+    def at(self, i):
+        return self[i]
+
+
+class GpuResourcesVector(_Vector):
+    pass
+
+
+class IntVector(_Vector):
+    pass
+
+
+def _resolve_scan(co) -> str:
+    scan = getattr(co, "scan", None) if co is not None else None
+    if scan is None:
+        scan = "f16" if (co is not None and getattr(co, "useFloat16", False)) else default_scan()
+    return scan
+
+
+class _Shard:
+    """Owns one cldrd_shard handle."""
+
+    def __init__(self, device: int, row0: int, nrows: int, d: int, scan: str):
+        self.handle = C.c_void_p()
+        self.device, self.row0, self.nrows, self.d = int(device), int(row0), int(nrows), int(d)
+        self.scan_request = scan
+        self._create("f16" if scan == "auto" else scan)
+        self._keepalive = None
+
+    def _create(self, scan: str):
+        if scan not in _lib.SCAN_NAMES:
+            raise ValueError(f"unknown scan mode {scan!r}")
+        check(lib().cldrd_shard_create(C.byref(self.handle), self.device, self.row0, self.nrows, self.d,
+                                       _lib.SCAN_NAMES[scan]))
+
+    def close(self):
+        if self.handle:
+            lib().cldrd_shard_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fill(self, filler) -> None:
+        """filler(shard) populates rows/ids; finalize, retrying with tf32 when "auto" picked fp16
+        for values that do not fit fp16."""
+        filler(self)
+        try:
+            check(lib().cldrd_shard_finalize(self.handle, None))
+        except CldrdError as e:
+            if self.scan_request != "auto" or e.code != _lib.E_INVAL:
+                raise
+            self.close()
+            self._create("tf32")
+            filler(self)
+            check(lib().cldrd_shard_finalize(self.handle, None))
+
+    def stats(self) -> dict:
+        arr = (C.c_int64 * 8)()
+        check(lib().cldrd_shard_last_stats(self.handle, arr))
+        names = ["launches", "chunks", "fallback_queries", "rescored", "survivors", "max_list", "tc_tiles",
+                 "exact_compactions"]
+        return dict(zip(names, list(arr)))
+
+    def set_profiling(self, on: bool) -> None:
+        check(lib().cldrd_shard_set_profiling(self.handle, 1 if on else 0))
+
+    def scan_time(self):
+        """(summed device ms of the scan kernels of the last search, number of scan launches)."""
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().cldrd_shard_last_scan_time(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def scan(self) -> str:
+        code = lib().cldrd_shard_scan(self.handle)
+        return {0: "simt", 1: "tf32", 2: "f16", 3: "bf16"}[code]
+
+    @property
+    def scan_bytes(self) -> int:
+        return int(lib().cldrd_shard_scan_bytes(self.handle))
+
+
+def _fill_from_index(index, row0: int, nrows: int, with_ids: bool):
+    """Returns a filler that moves rows [row0,row0+nrows) of a host-side index into a shard."""
+    store = index._rows
+
+    def filler(sh: _Shard):
+        if store.file is not None:
+            check(lib().cldrd_shard_load_file(sh.handle, store.file.encode()))  # loads ids too
+            if not with_ids:
+                check(lib().cldrd_shard_set_ids(sh.handle, None))
+            return
+        rows = store.materialize()
+        part = rows[row0:row0 + nrows]
+        check(lib().cldrd_shard_upload(sh.handle, ptr(part), 0, nrows))
+        ids = index._ids() if with_ids else None
+        if ids is not None:
+            part_ids = np.ascontiguousarray(ids[row0:row0 + nrows])
+            check(lib().cldrd_shard_set_ids(sh.handle, ptr(part_ids)))
+
+    return filler
+
+
+class GpuIndexFlat:
+    """What index_cpu_to_gpu returns: the whole index resident on one GPU."""
+
+    def __init__(self, shard: _Shard, ntotal: int, d: int):
+        self._shard = shard
+        self.ntotal = ntotal
+        self.d = d
+        self.metric_type = METRIC_INNER_PRODUCT
+        self.is_trained = True
+        self._lock = threading.Lock()
+
+    def close(self):
+        self._shard.close()
+
+    def search(self, x, k):
+        k = int(k)
+        x = _check_x(x, self.d, "search")
+        assert k > 0, "search: k must be positive"
+        if k > _lib.MAX_K:
+            raise RuntimeError(f"search: k={k} above the GPU limit {_lib.MAX_K} (same limit as faiss GpuIndexFlat)")
+        n = x.shape[0]
+        D = np.empty((n, k), dtype=np.float32)
+        I = np.empty((n, k), dtype=np.int64)
+        if n:
+            with self._lock:
+                check(lib().cldrd_search_host(self._shard.handle, ptr(x), n, k, ptr(D), ptr(I)))
+        return D, I
+
+    def search_device(self, q, k: int, translate_ids: bool = True):
+        """Extension: torch CUDA tensor in, torch CUDA tensors out (no host copies)."""
+        import torch
+        assert q.is_cuda and q.dtype == torch.float32 and q.dim() == 2 and q.shape[1] == self.d
+        q = q.contiguous()
+        n = q.shape[0]
+        D = torch.empty((n, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=q.device)
+        if n:
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            with self._lock:
+                check(lib().cldrd_search_dev(self._shard.handle, C.c_void_p(q.data_ptr()), n, int(k),
+                                             1 if translate_ids else 0, C.c_void_p(D.data_ptr()),
+                                             C.c_void_p(I.data_ptr()), C.c_void_p(stream)))
+        return D, I
+
+    def last_stats(self) -> dict:
+        return self._shard.stats()
+
+    @property
+    def scan(self) -> str:
+        return self._shard.scan
+
+
+def index_cpu_to_gpu(res, device: int, index, co: Optional[GpuClonerOptions] = None) -> GpuIndexFlat:
+    """retriever/retrieval_utils.py:163.  File-backed indexes stream straight into HBM."""
+    n, d = index.ntotal, index.d
+    sh = _Shard(device, 0, n, d, _resolve_scan(co))
+    sh.fill(_fill_from_index(index, 0, n, with_ids=isinstance(index, IndexIDMap)))
+    return GpuIndexFlat(sh, n, d)
+
+
+def shard_ranges(ntotal: int, parts: int) -> List[range]:
+    """Contiguous passage-row ranges, rows_r = [floor(r*N/G), floor((r+1)*N/G))  (SURVEY §8e)."""
+    return [range((r * ntotal) // parts, ((r + 1) * ntotal) // parts) for r in range(parts)]
+
+
+class GpuIndexShards:
+    """What index_cpu_to_gpu_multiple(..., shard=True) returns inside ONE process: the index
+    row-sharded over several GPUs; per-shard candidates are copied to the first device over
+    NVLink and merged there by the same kernel the NCCL path uses."""
+
+    def __init__(self, shards: List[_Shard], ids: Optional[np.ndarray], ntotal: int, d: int):
+        import torch
+        self._shards = shards
+        self.ntotal, self.d = ntotal, d
+        self._torch = torch
+        self._dev0 = shards[0].device
+        self._id_map = None
+        if ids is not None:
+            self._id_map = torch.from_numpy(ids).to(f"cuda:{self._dev0}")
+
+    def close(self):
+        for s in self._shards:
+            s.close()
+
+    def search(self, x, k):
+        torch = self._torch
+        k = int(k)
+        x = _check_x(x, self.d, "search")
+        if k > _lib.MAX_K:
+            raise RuntimeError(f"search: k={k} above the GPU limit {_lib.MAX_K}")
+        n = x.shape[0]
+        xt = torch.from_numpy(x)
+        Ds, Is = [], []
+        threads = []
+
+        def work(sh: _Shard, slot: int):
+            dev = torch.device("cuda", sh.device)
+            with torch.cuda.device(dev):
+                q = xt.to(dev, non_blocking=False)
+                D = torch.empty((n, k), dtype=torch.float32, device=dev)
+                I = torch.empty((n, k), dtype=torch.int64, device=dev)
+                st = torch.cuda.current_stream(dev)
+                check(lib().cldrd_search_dev(sh.handle, C.c_void_p(q.data_ptr()), n, k, 0, C.c_void_p(D.data_ptr()),
+                                             C.c_void_p(I.data_ptr()), C.c_void_p(st.cuda_stream)))
+                st.synchronize()
+                Ds[slot], Is[slot] = D, I
+
+        Ds = [None] * len(self._shards)
+        Is = [None] * len(self._shards)
+        for i, sh in enumerate(self._shards):
+            t = threading.Thread(target=work, args=(sh, i))
+            t.start()
+            threads.append(t)
+        for t in threads:
+            t.join()
+        dev0 = torch.device("cuda", self._dev0)
+        with torch.cuda.device(dev0):
+            allD = torch.stack([d_.to(dev0) for d_ in Ds]).contiguous()
+            allI = torch.stack([i_.to(dev0) for i_ in Is]).contiguous()
+            outD = torch.empty((n, k), dtype=torch.float32, device=dev0)
+            outI = torch.empty((n, k), dtype=torch.int64, device=dev0)
+            st = torch.cuda.current_stream(dev0)
+            check(lib().cldrd_merge(self._dev0, C.c_void_p(allD.data_ptr()), C.c_void_p(allI.data_ptr()),
+                                    len(self._shards), n, k,
+                                    C.c_void_p(self._id_map.data_ptr()) if self._id_map is not None else None,
+                                    C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()),
+                                    C.c_void_p(st.cuda_stream)))
+            return outD.cpu().numpy(), outI.cpu().numpy()
+
+
+def index_cpu_to_gpu_multiple(vres, vdev: Sequence[int], index, co: Optional[GpuMultipleClonerOptions] = None):
+    """retriever/retrieval_utils.py:182.  shard=True: rows split over the devices; shard=False
+    (replicas) would only waste HBM bandwidth for this workload, so it is served by the same
+    sharded layout."""
+    devs = list(vdev)
+    assert len(devs) >= 1
+    n, d = index.ntotal, index.d
+    scan = _resolve_scan(co)
+    shards = []
+    for dev, rr in zip(devs, shard_ranges(n, len(devs))):
+        sh = _Shard(dev, rr.start, len(rr), d, scan)
+        sh.fill(_fill_from_index(index, rr.start, len(rr), with_ids=False))
+        shards.append(sh)
+    ids = index._ids() if isinstance(index, IndexIDMap) else None
+    return GpuIndexShards(shards, ids, n, d)
+
+
+def index_gpu_to_cpu(index):
+    raise RuntimeError("index_gpu_to_cpu: keep the host-side index you cloned from")

@@ -1,0 +1,45 @@
+"""Run-file writer: the regroup + write loops of retriever/retrieve_top_passages.py:90-109
+(and retrieve_top_queries.py:65-82) as one native call, byte-identical output."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from ._lib import check, lib, ptr
+
+
+def format_score(s: float) -> str:
+    """Text the reference writes for one fp32 score: repr(float(np.float32(s)))."""
+    buf = C.create_string_buffer(40)
+    n = lib().cldrd_format_score(C.c_float(float(s)), buf)
+    return buf.raw[:n].decode()
+
+
+def write_run_file(path, query_ids, nn_ids, nn_scores, append: bool = False) -> float:
+    """query_ids [n], nn_ids [n,k] int64, nn_scores [n,k] float32 -> "qid\\tdocid\\trank\\tscore\\n".
+
+    Mirrors the reference: creates the parent directory if missing (:99-100); a query id that
+    occurs more than once keeps its first position and its later hits continue the same rank
+    sequence (the dict regroup of :90-96).  Returns the average ranks per query it prints (:109).
+    """
+    qids = np.ascontiguousarray(np.asarray(query_ids, dtype=np.int64))
+    I = np.ascontiguousarray(np.asarray(nn_ids, dtype=np.int64))
+    D = np.ascontiguousarray(np.asarray(nn_scores, dtype=np.float32))
+    assert I.ndim == 2 and D.shape == I.shape and qids.shape == (I.shape[0],)
+    n, k = I.shape
+    parent = Path(path).parent
+    if not os.path.exists(parent):
+        os.mkdir(parent)
+    uniq, first = np.unique(qids, return_index=True)
+    if uniq.shape[0] != n:
+        # group duplicates behind their first occurrence, stable within a group
+        first_of = dict(zip(uniq.tolist(), first.tolist()))
+        order = np.argsort(np.array([first_of[q] for q in qids.tolist()], dtype=np.int64), kind="stable")
+        qids, I, D = qids[order], np.ascontiguousarray(I[order]), np.ascontiguousarray(D[order])
+    lines = C.c_int64()
+    check(lib().cldrd_write_run(str(path).encode(), ptr(qids), ptr(D), ptr(I), n, k, 1 if append else 0,
+                                C.byref(lines)))
+    return lines.value / max(uniq.shape[0], 1)

@@ -1,0 +1,865 @@
+// libcldrd.so — shard lifecycle, search orchestration and the CUDA entry points of the C ABI
+// (include/cldrd.h).  Replaces, for CL-DRD's retrieval path, what the reference gets from faiss:
+//   index_cpu_to_gpu(...)            retriever/retrieval_utils.py:159-163
+//   index.search(x, k)               retriever/retrieval_utils.py:135,143
+//   IndexShards merge                retriever/retrieval_utils.py:176-182
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
+#include <vector>
+
+#include "common_host.h"
+#include "scan_simt.cuh"
+#include "scan_tc.cuh"
+#include "select.cuh"
+
+using namespace cldrd;
+
+namespace {
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(CLDRD_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+constexpr int kQueryBatch = 8192;   // queries processed per pass over the index
+constexpr int kDensePiece = 8192;   // rows per dense piece (first chunk and fallback)
+constexpr int kSurvCap = 8192;      // survivor slots per query per chunk
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2D row-major [rows][d] tensor, box = [box_rows][128 bytes of K], 128B swizzle, zero OOB fill.
+int make_tensor_map(CUtensorMap* tm, int scan, const void* base, int64_t rows, int d, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(CLDRD_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMapDataType dt;
+    int esz;
+    if (scan == CLDRD_SCAN_TC_TF32) {
+        dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        esz = 4;
+    } else if (scan == CLDRD_SCAN_TC_F16) {
+        dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        esz = 2;
+    } else {
+        dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        esz = 2;
+    }
+    cuuint64_t gdim[2] = {cuuint64_t(d), cuuint64_t(rows)};
+    cuuint64_t gstride[1] = {cuuint64_t(d) * esz};
+    cuuint32_t box[2] = {cuuint32_t(TC_KB_BYTES / esz), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CLDRD_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return CLDRD_OK;
+}
+
+bool is_tc(int scan) { return scan == CLDRD_SCAN_TC_TF32 || scan == CLDRD_SCAN_TC_F16 || scan == CLDRD_SCAN_TC_BF16; }
+int lp_kind_of(int scan) { return scan == CLDRD_SCAN_TC_F16 ? 1 : scan == CLDRD_SCAN_TC_BF16 ? 2 : 0; }
+
+}  // namespace
+
+struct cldrd_shard {
+    int device = 0;
+    int64_t row0 = 0;
+    int64_t nrows = 0;
+    int d = 0;
+    int scan = 0;
+    int scan_eff = 0;        // scan actually used (SIMT when TMA cannot describe the shape)
+    bool finalized = false;
+
+    float* xb = nullptr;     // fp32 rows (owned unless adopted)
+    bool xb_owned = false;
+    void* xlp = nullptr;     // fp16 / bf16 copy
+    int64_t* ids = nullptr;  // external ids (device), optional
+    float bmax_norm = 0.f, bmax_abs = 0.f;
+    int vec4 = 0;
+    int num_sms = 0;
+    CUtensorMap tmB;
+
+    // workspace for one query batch
+    int ws_keep_cap = 0;
+    size_t ws_d = 0;
+    float* w_thr = nullptr;
+    float* w_band = nullptr;
+    int* w_list_len = nullptr;
+    int* w_surv_cnt = nullptr;
+    int* w_fail = nullptr;
+    int* w_fail_index = nullptr;
+    uint64_t* w_list = nullptr;
+    uint64_t* w_surv = nullptr;
+    float* w_dense = nullptr;
+    void* w_qlp = nullptr;
+    float* w_qfail = nullptr;     // compacted queries for the dense fallback
+    unsigned long long* w_stats = nullptr;   // device [ST_COUNT]
+    unsigned long long* h_stats = nullptr;   // pinned   [ST_COUNT]
+    int* h_fail = nullptr;                   // pinned   [kQueryBatch]
+
+    // pinned staging for cldrd_search_host
+    float* h_q = nullptr;
+    size_t h_q_bytes = 0;
+    float* h_D = nullptr;
+    int64_t* h_I = nullptr;
+    size_t h_out_elems = 0;
+    float* d_q = nullptr;
+    size_t d_q_bytes = 0;
+    float* d_D = nullptr;
+    int64_t* d_I = nullptr;
+    size_t d_out_elems = 0;
+
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // optional per-kernel timing of the scan launches (bench roofline): event pairs on the
+    // launching stream, summed after the search's final synchronisation
+    bool profile = false;
+    std::vector<cudaEvent_t> ev;   // 2 per scan launch
+    size_t ev_used = 0;
+    double scan_ms = 0.0;
+    int64_t scan_launches = 0;
+};
+
+namespace {
+
+void free_workspace(cldrd_shard* s) {
+    cudaFree(s->w_thr);
+    cudaFree(s->w_band);
+    cudaFree(s->w_list_len);
+    cudaFree(s->w_surv_cnt);
+    cudaFree(s->w_fail);
+    cudaFree(s->w_fail_index);
+    cudaFree(s->w_list);
+    cudaFree(s->w_surv);
+    cudaFree(s->w_dense);
+    cudaFree(s->w_qlp);
+    cudaFree(s->w_qfail);
+    cudaFree(s->w_stats);
+    if (s->h_stats) cudaFreeHost(s->h_stats);
+    if (s->h_fail) cudaFreeHost(s->h_fail);
+    s->w_thr = s->w_band = nullptr;
+    s->w_list_len = s->w_surv_cnt = s->w_fail = s->w_fail_index = nullptr;
+    s->w_list = s->w_surv = nullptr;
+    s->w_dense = nullptr;
+    s->w_qlp = nullptr;
+    s->w_qfail = nullptr;
+    s->w_stats = nullptr;
+    s->h_stats = nullptr;
+    s->h_fail = nullptr;
+    s->ws_keep_cap = 0;
+}
+
+int ensure_workspace(cldrd_shard* s) {
+    if (s->w_thr) return CLDRD_OK;
+    const int keep_cap = (s->scan_eff == CLDRD_SCAN_TC_BF16) ? 8192 : 4096;
+    const size_t Q = kQueryBatch;
+    CU_TRY(cudaMalloc(&s->w_thr, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_band, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_list_len, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_surv_cnt, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
+    CU_TRY(cudaMalloc(&s->w_surv, Q * kSurvCap * sizeof(uint64_t)));
+    CU_TRY(cudaMalloc(&s->w_dense, Q * kDensePiece * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_qfail, Q * size_t(s->d) * sizeof(float)));
+    if (lp_kind_of(s->scan_eff)) CU_TRY(cudaMalloc(&s->w_qlp, Q * size_t(s->d) * 2));
+    CU_TRY(cudaMalloc(&s->w_stats, ST_COUNT * sizeof(unsigned long long)));
+    CU_TRY(cudaHostAlloc(&s->h_stats, ST_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&s->h_fail, Q * sizeof(int), cudaHostAllocDefault));
+    s->ws_keep_cap = keep_cap;
+    return CLDRD_OK;
+}
+
+// error-bound coefficients: eps = coef * |q| * max|b| + abs_coef * (|q| + max|b|)   
+void eps_coefs(int scan, int d, float* coef, float* abs_coef) {
+    const double u24 = std::ldexp(1.0, -24);
+    const double rescore = (d + 16) * u24;          // fp32 re-score vs the real dot product
+    const double accum = 2.2 * d * std::ldexp(1.0, -23);  // tensor-core accumulation slack
+    double c = 0.0, a = 0.0;
+    switch (scan) {
+        case CLDRD_SCAN_SIMT_F32: c = (d + 16) * u24; break;
+        case CLDRD_SCAN_TC_TF32: c = std::ldexp(1.0, -9) * 1.002 + accum; break;   // operands truncated to 10+1 bits
+        case CLDRD_SCAN_TC_F16:
+            c = std::ldexp(1.0, -10) * 1.002 + accum;
+            a = std::ldexp(1.0, -24) * std::sqrt(double(d));                    // fp16 subnormal inputs
+            break;
+        case CLDRD_SCAN_TC_BF16: c = std::ldexp(1.0, -7) * 1.01 + accum; break;
+    }
+    *coef = float((c + rescore) * 1.01);
+    *abs_coef = float(a);
+}
+
+struct BatchCtx {
+    cldrd_shard* s;
+    cudaStream_t st;
+    const float* q;    // fp32 queries of this batch (device)
+    int nq;
+    int k;
+    CUtensorMap tmA;
+    bool have_tmA = false;
+    int64_t launches = 0;
+    int64_t chunks = 0;
+};
+
+cudaEvent_t next_event(cldrd_shard* s) {
+    if (s->ev_used == s->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->ev.push_back(e);
+    }
+    return s->ev[s->ev_used++];
+}
+
+int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
+    cldrd_shard* s = c.s;
+    if (s->profile) cudaEventRecord(next_event(s), c.st);
+    ScanParams p{};
+    p.xb = s->xb;
+    p.q = c.q;
+    p.d = s->d;
+    p.nq = c.nq;
+    p.row_begin = row_begin;
+    p.nrows = nrows;
+    p.thr = s->w_thr;
+    p.surv = s->w_surv;
+    p.surv_cnt = s->w_surv_cnt;
+    p.surv_cap = kSurvCap;
+    p.dense = s->w_dense;
+    p.dense_ld = kDensePiece;
+    p.stats = s->w_stats;
+    if (is_tc(s->scan_eff)) {
+        const int esz = (s->scan_eff == CLDRD_SCAN_TC_TF32) ? 4 : 2;
+        p.kb_elems = TC_KB_BYTES / esz;
+        p.num_kb = (s->d * esz + TC_KB_BYTES - 1) / TC_KB_BYTES;
+        const long long tiles = (long long)((c.nq + TC_BM - 1) / TC_BM) * ((nrows + TC_BN - 1) / TC_BN);
+        const int grid = int(std::min<long long>(tiles, s->num_sms));
+        if (grid <= 0) {
+            if (s->profile) cudaEventRecord(next_event(s), c.st);
+            return CLDRD_OK;
+        }
+#define LAUNCH_TC(KIND)                                                                               \
+    do {                                                                                              \
+        if (dense)                                                                                    \
+            scan_tc_kernel<KIND, true><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p);  \
+        else                                                                                          \
+            scan_tc_kernel<KIND, false><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p); \
+    } while (0)
+        if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC(0);
+        else if (s->scan_eff == CLDRD_SCAN_TC_BF16) LAUNCH_TC(1);
+        else LAUNCH_TC(2);
+#undef LAUNCH_TC
+    } else {
+        dim3 grid((nrows + SIMT_BN - 1) / SIMT_BN, (c.nq + SIMT_BM - 1) / SIMT_BM);
+        if (grid.x == 0 || grid.y == 0) {
+            if (s->profile) cudaEventRecord(next_event(s), c.st);
+            return CLDRD_OK;
+        }
+        const bool vec = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
+        if (dense) {
+            if (vec) scan_simt_kernel<true, true><<<grid, 256, 0, c.st>>>(p);
+            else scan_simt_kernel<true, false><<<grid, 256, 0, c.st>>>(p);
+        } else {
+            if (vec) scan_simt_kernel<false, true><<<grid, 256, 0, c.st>>>(p);
+            else scan_simt_kernel<false, false><<<grid, 256, 0, c.st>>>(p);
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    if (s->profile) cudaEventRecord(next_event(s), c.st);
+    c.launches++;
+    c.chunks++;
+    return CLDRD_OK;
+}
+
+size_t select_smem(const cldrd_shard* s) { return size_t(s->ws_keep_cap + kSurvCap) * 8 + size_t(s->d) * 4 + 16; }
+
+int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
+    cldrd_shard* s = c.s;
+    SelectParams p{};
+    p.list = s->w_list;
+    p.list_len = s->w_list_len;
+    p.keep_cap = s->ws_keep_cap;
+    p.surv = s->w_surv;
+    p.surv_cnt = s->w_surv_cnt;
+    p.surv_cap = kSurvCap;
+    p.dense = dense ? s->w_dense : nullptr;
+    p.dense_ld = kDensePiece;
+    p.dense_n = nrows;
+    p.dense_row0 = uint32_t(row_begin);
+    p.thr = s->w_thr;
+    p.band = s->w_band;
+    p.k = c.k;
+    p.fail = s->w_fail;
+    p.stats = s->w_stats;
+    p.xb = s->xb;
+    p.q = c.q;
+    p.d = s->d;
+    p.vec4 = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
+    select_merge_kernel<<<c.nq, 512, select_smem(s), c.st>>>(p);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return CLDRD_OK;
+}
+
+int launch_prep(BatchCtx& c) {
+    cldrd_shard* s = c.s;
+    QueryPrepParams p{};
+    p.q = c.q;
+    p.nq = c.nq;
+    p.d = s->d;
+    p.lp_kind = lp_kind_of(s->scan_eff);
+    p.q_lp = s->w_qlp;
+    eps_coefs(s->scan_eff, s->d, &p.coef, &p.abs_coef);
+    p.bmax_norm = s->bmax_norm;
+    p.band = s->w_band;
+    p.thr = s->w_thr;
+    p.list_len = s->w_list_len;
+    p.surv_cnt = s->w_surv_cnt;
+    p.fail = s->w_fail;
+    p.stats = s->w_stats;
+    const int threads = 256;
+    const int blocks = (c.nq * 32 + threads - 1) / threads;
+    query_prep_kernel<<<blocks, threads, 0, c.st>>>(p);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    if (is_tc(s->scan_eff)) {
+        const void* base = lp_kind_of(s->scan_eff) ? static_cast<const void*>(s->w_qlp) : static_cast<const void*>(c.q);
+        int rc = make_tensor_map(&c.tmA, s->scan_eff, base, c.nq, s->d, TC_BM);
+        if (rc) return rc;
+        c.have_tmA = true;
+    }
+    return CLDRD_OK;
+}
+
+int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool translate, const int* out_index,
+                   const int* fail_flags) {
+    cldrd_shard* s = c.s;
+    RescoreParams p{};
+    p.xb = s->xb;
+    p.q = c.q;
+    p.d = s->d;
+    p.vec4 = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
+    p.list = s->w_list;
+    p.list_len = s->w_list_len;
+    p.keep_cap = s->ws_keep_cap;
+    p.n_pad = s->ws_keep_cap;
+    p.k = c.k;
+    p.row0 = s->row0;
+    p.ids = (translate && s->ids) ? s->ids : nullptr;
+    p.out_scores = out_scores;
+    p.out_ids = out_ids;
+    p.out_index = out_index;
+    p.fail = fail_flags;
+    p.stats = s->w_stats;
+    const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
+    rescore_sort_kernel<<<c.nq, 512, smem, c.st>>>(p);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return CLDRD_OK;
+}
+
+int read_stats(cldrd_shard* s, cudaStream_t st) {
+    CU_TRY(cudaMemcpyAsync(s->h_stats, s->w_stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (s->h_stats[ST_KERNEL_ERR])
+        return fail(CLDRD_ECUDA, "scan kernel watchdog fired (code %llu)", s->h_stats[ST_KERNEL_ERR]);
+    return CLDRD_OK;
+}
+
+// One pass of `c.nq` (<= kQueryBatch) queries over the whole shard.
+//   dense_only: every chunk is a dense piece (the fallback for queries whose survivor buffer
+//   overflowed; it cannot overflow itself).
+int run_pass(BatchCtx& c, bool dense_only) {
+    cldrd_shard* s = c.s;
+    const int64_t N = s->nrows;
+    int rc = launch_prep(c);
+    if (rc) return rc;
+    int64_t done = 0;
+    const int first = int(std::min<int64_t>(N, kDensePiece));
+    if (first > 0) {
+        if ((rc = launch_scan(c, true, 0, first))) return rc;
+        if ((rc = launch_select(c, true, 0, first))) return rc;
+        done = first;
+    }
+    if (done >= N) return CLDRD_OK;
+    if (dense_only) {
+        while (done < N) {
+            const int m = int(std::min<int64_t>(N - done, kDensePiece));
+            if ((rc = launch_scan(c, true, done, m))) return rc;
+            if ((rc = launch_select(c, true, done, m))) return rc;
+            done += m;
+        }
+        return CLDRD_OK;
+    }
+    // Size the growing chunks from the candidate-list length after the first piece: a chunk of
+    // m rows after `done` rows is expected to push about len * m / done survivors per query;
+    // keep that at a quarter of the survivor buffer.
+    if ((rc = read_stats(s, c.st))) return rc;
+    const double k_eff = std::max<double>(c.k, double(s->h_stats[ST_MAX_LIST])) * 1.1;
+    const double growth = double(kSurvCap) / (4.0 * k_eff);
+    while (done < N) {
+        int64_t m = int64_t(double(done) * growth);
+        m = std::max<int64_t>(m, TC_BN);
+        m = (m / TC_BN) * TC_BN;
+        m = std::min<int64_t>(m, int64_t(1) << 30);
+        if (m > N - done) m = N - done;
+        if ((rc = launch_scan(c, false, done, int(m)))) return rc;
+        if ((rc = launch_select(c, false, done, int(m)))) return rc;
+        done += m;
+    }
+    return CLDRD_OK;
+}
+
+int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool translate, float* out_scores,
+                 int64_t* out_ids, cudaStream_t st, int64_t* launches, int64_t* chunks, int64_t* nfailed) {
+    BatchCtx c{};
+    c.s = s;
+    c.st = st;
+    c.q = q_dev;
+    c.nq = nq;
+    c.k = k;
+    int rc = run_pass(c, false);
+    if (rc) return rc;
+    if ((rc = launch_rescore(c, out_scores, out_ids, translate, nullptr, s->w_fail))) return rc;
+    // any query whose survivors overflowed?  (one small D2H; also surfaces watchdog / range errors)
+    if ((rc = read_stats(s, st))) return rc;
+    *launches += c.launches;
+    *chunks += c.chunks;
+    if (s->h_stats[ST_RANGE_ERR])
+        return fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
+    const unsigned long long nfail = s->h_stats[ST_FAILED];
+    if (nfail == 0) return CLDRD_OK;
+    *nfailed += int64_t(nfail);
+    // dense fallback for the failed queries only
+    CU_TRY(cudaMemcpyAsync(s->h_fail, s->w_fail, size_t(nq) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<int> idx;
+    for (int i = 0; i < nq; ++i)
+        if (s->h_fail[i]) idx.push_back(i);
+    CU_TRY(cudaMemcpyAsync(s->w_fail_index, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    gather_failed_kernel<<<int(idx.size()), 128, 0, st>>>(q_dev, s->d, s->w_fail_index, int(idx.size()), s->w_qfail);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));  // idx goes out of scope after this function
+    BatchCtx f{};
+    f.s = s;
+    f.st = st;
+    f.q = s->w_qfail;
+    f.nq = int(idx.size());
+    f.k = k;
+    const unsigned long long keep_failed = nfail;
+    if ((rc = run_pass(f, true))) return rc;
+    if ((rc = launch_rescore(f, out_scores, out_ids, translate, s->w_fail_index, nullptr))) return rc;
+    if ((rc = read_stats(s, st))) return rc;
+    s->h_stats[ST_FAILED] = keep_failed;
+    *launches += f.launches + 1;
+    *chunks += f.chunks;
+    return CLDRD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrows, int32_t d, int32_t scan) {
+    if (!out || nrows < 0 || d <= 0 || row0 < 0 || scan < 0 || scan > 3)
+        return fail(CLDRD_EINVAL, "shard_create: bad argument (nrows=%lld d=%d scan=%d)", (long long)nrows, d, scan);
+    if (row0 + nrows >= (int64_t(1) << 32) - 1)
+        return fail(CLDRD_EINVAL, "shard_create: rows beyond 2^32-2 are not addressable by the candidate keys");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CLDRD_ECUDA, "no CUDA device: libcldrd has no CPU search path");
+    if (device < 0 || device >= ndev) return fail(CLDRD_EINVAL, "shard_create: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CLDRD_ECUDA, "device %d is sm_%d%d; libcldrd is built for sm_100a only", device, prop.major, prop.minor);
+    auto* s = new cldrd_shard();
+    s->device = device;
+    s->row0 = row0;
+    s->nrows = nrows;
+    s->d = d;
+    s->scan = scan;
+    s->num_sms = prop.multiProcessorCount;
+    *out = s;
+    return CLDRD_OK;
+}
+
+void cldrd_shard_destroy(cldrd_shard* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    free_workspace(s);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    if (s->xb_owned) cudaFree(s->xb);
+    cudaFree(s->xlp);
+    cudaFree(s->ids);
+    if (s->h_q) cudaFreeHost(s->h_q);
+    if (s->h_D) cudaFreeHost(s->h_D);
+    if (s->h_I) cudaFreeHost(s->h_I);
+    cudaFree(s->d_q);
+    cudaFree(s->d_D);
+    cudaFree(s->d_I);
+    delete s;
+}
+
+static int ensure_rows(cldrd_shard* s) {
+    if (s->xb) return CLDRD_OK;
+    CU_TRY(cudaMalloc(&s->xb, std::max<size_t>(size_t(s->nrows) * s->d * sizeof(float), 16)));
+    s->xb_owned = true;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_upload(cldrd_shard* s, const float* rows_host, int64_t row_off, int64_t n) {
+    if (!s || (!rows_host && n) || row_off < 0 || n < 0 || row_off + n > s->nrows)
+        return fail(CLDRD_EINVAL, "shard_upload: bad range");
+    if (s->xb && !s->xb_owned) return fail(CLDRD_ESTATE, "shard_upload: rows were adopted");
+    DeviceGuard g(s->device);
+    int rc = ensure_rows(s);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(s->xb + size_t(row_off) * s->d, rows_host, size_t(n) * s->d * sizeof(float), cudaMemcpyHostToDevice));
+    s->finalized = false;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_adopt(cldrd_shard* s, const float* rows_dev) {
+    if (!s || (!rows_dev && s->nrows)) return fail(CLDRD_EINVAL, "shard_adopt: NULL");
+    if (s->xb && s->xb_owned) return fail(CLDRD_ESTATE, "shard_adopt: rows already uploaded");
+    if (reinterpret_cast<uintptr_t>(rows_dev) % 16) return fail(CLDRD_EINVAL, "shard_adopt: buffer must be 16-byte aligned");
+    s->xb = const_cast<float*>(rows_dev);
+    s->xb_owned = false;
+    s->finalized = false;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_load_file(cldrd_shard* s, const char* path) {
+    if (!s || !path) return fail(CLDRD_EINVAL, "shard_load_file: NULL");
+    IndexFileInfo info;
+    int rc = probe_index_file(path, &info);
+    if (rc) return rc;
+    if (info.d != s->d) return fail(CLDRD_EINVAL, "shard_load_file: file d=%d, shard d=%d", info.d, s->d);
+    if (s->row0 + s->nrows > info.ntotal)
+        return fail(CLDRD_EINVAL, "shard_load_file: rows [%lld,+%lld) outside ntotal=%lld", (long long)s->row0,
+                    (long long)s->nrows, (long long)info.ntotal);
+    if (s->xb && !s->xb_owned) return fail(CLDRD_ESTATE, "shard_load_file: rows were adopted");
+    DeviceGuard g(s->device);
+    if ((rc = ensure_rows(s))) return rc;
+    // pread -> pinned double buffer -> cudaMemcpyAsync; the payload starts at an odd byte offset
+    // (82), so it is staged rather than mapped.
+    const size_t row_bytes = size_t(s->d) * 4;
+    const size_t piece_rows = std::max<size_t>(1, (size_t(64) << 20) / row_bytes);
+    char* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    cudaStream_t st;
+    CU_TRY(cudaStreamCreate(&st));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaHostAlloc(&pin[i], piece_rows * row_bytes, cudaHostAllocDefault));
+        CU_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) rc = fail(CLDRD_EIO, "cannot open '%s'", path);
+    int b = 0;
+    for (int64_t r = 0; r < s->nrows && !rc; r += int64_t(piece_rows), b ^= 1) {
+        const size_t n = size_t(std::min<int64_t>(int64_t(piece_rows), s->nrows - r));
+        cudaEventSynchronize(ev[b]);
+        size_t want = n * row_bytes, got = 0;
+        off_t off = off_t(info.data_off) + off_t(s->row0 + r) * off_t(row_bytes);
+        while (got < want) {
+            ssize_t x = pread(fd, pin[b] + got, want - got, off + off_t(got));
+            if (x <= 0) {
+                rc = fail(CLDRD_EIO, "short read from '%s'", path);
+                break;
+            }
+            got += size_t(x);
+        }
+        if (rc) break;
+        if (cudaMemcpyAsync(reinterpret_cast<char*>(s->xb) + size_t(r) * row_bytes, pin[b], want, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            rc = fail(CLDRD_ECUDA, "H2D copy failed");
+        cudaEventRecord(ev[b], st);
+    }
+    if (fd >= 0) close(fd);
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(pin[i]);
+        cudaEventDestroy(ev[i]);
+    }
+    cudaStreamDestroy(st);
+    if (rc) return rc;
+    if (info.has_ids) {
+        std::vector<int64_t> ids(size_t(s->nrows));
+        if ((rc = cldrd_index_read_ids(path, s->row0, s->nrows, ids.data()))) return rc;
+        if ((rc = cldrd_shard_set_ids(s, ids.data()))) return rc;
+    }
+    s->finalized = false;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_set_ids(cldrd_shard* s, const int64_t* ids_host) {
+    if (!s) return fail(CLDRD_EINVAL, "shard_set_ids: NULL");
+    DeviceGuard g(s->device);
+    cudaFree(s->ids);
+    s->ids = nullptr;
+    if (!ids_host || s->nrows == 0) return CLDRD_OK;
+    CU_TRY(cudaMalloc(&s->ids, size_t(s->nrows) * sizeof(int64_t)));
+    CU_TRY(cudaMemcpy(s->ids, ids_host, size_t(s->nrows) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    return CLDRD_OK;
+}
+
+int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
+    if (!s) return fail(CLDRD_EINVAL, "shard_finalize: NULL");
+    if (s->nrows > 0 && !s->xb) return fail(CLDRD_ESTATE, "shard_finalize: no rows uploaded / loaded / adopted");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // can TMA describe this shape?  (row pitch multiple of 16 bytes, 16-byte aligned base)
+    s->scan_eff = s->scan;
+    s->vec4 = (s->d % 4 == 0) && (reinterpret_cast<uintptr_t>(s->xb) % 16 == 0);
+    if (is_tc(s->scan)) {
+        const int esz = (s->scan == CLDRD_SCAN_TC_TF32) ? 4 : 2;
+        if ((s->d * esz) % 16 != 0 || !s->vec4) s->scan_eff = CLDRD_SCAN_SIMT_F32;
+    }
+    free_workspace(s);
+    cudaFree(s->xlp);
+    s->xlp = nullptr;
+    const int lp = lp_kind_of(s->scan_eff);
+    if (lp && s->nrows) CU_TRY(cudaMalloc(&s->xlp, size_t(s->nrows) * s->d * 2));
+    unsigned int* d_max = nullptr;
+    CU_TRY(cudaMalloc(&d_max, 2 * sizeof(unsigned int)));
+    CU_TRY(cudaMemsetAsync(d_max, 0, 2 * sizeof(unsigned int), st));
+    if (s->nrows) {
+        const int threads = 256;
+        const int blocks = int(std::min<int64_t>((s->nrows * 32 + threads - 1) / threads, int64_t(s->num_sms) * 16));
+        index_prep_kernel<<<blocks, threads, 0, st>>>(s->xb, s->nrows, s->d, lp, s->xlp, d_max, d_max + 1);
+        CU_TRY(cudaGetLastError());
+    }
+    unsigned int h_max[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_max);
+    float n2, mx;
+    memcpy(&n2, &h_max[0], 4);
+    memcpy(&mx, &h_max[1], 4);
+    s->bmax_norm = std::sqrt(n2) * 1.0001f;
+    s->bmax_abs = mx;
+    if (s->scan_eff == CLDRD_SCAN_TC_F16 && !(mx < 65504.f))
+        return fail(CLDRD_EINVAL, "index values (max |x| = %g) exceed the fp16 range; use the bf16 or tf32 scan", double(mx));
+    if (is_tc(s->scan_eff) && s->nrows) {
+        const void* base = lp ? s->xlp : static_cast<const void*>(s->xb);
+        int rc = make_tensor_map(&s->tmB, s->scan_eff, base, s->nrows, s->d, TC_BN);
+        if (rc) return rc;
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+    }
+    int rc = ensure_workspace(s);
+    if (rc) return rc;
+    CU_TRY(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(select_smem(s))));
+    CU_TRY(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(size_t(s->ws_keep_cap) * 8 + size_t(s->d) * 4 + 16)));
+    s->finalized = true;
+    return CLDRD_OK;
+}
+
+int64_t cldrd_shard_nrows(const cldrd_shard* s) { return s ? s->nrows : 0; }
+int32_t cldrd_shard_dim(const cldrd_shard* s) { return s ? s->d : 0; }
+int32_t cldrd_shard_scan(const cldrd_shard* s) { return s ? s->scan_eff : -1; }
+int64_t cldrd_shard_scan_bytes(const cldrd_shard* s) {
+    if (!s) return 0;
+    const int esz = lp_kind_of(s->scan_eff) ? 2 : 4;
+    return s->nrows * int64_t(s->d) * esz;
+}
+
+int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
+                     float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    if (!s || nq < 0 || (nq && (!q_dev || !out_scores_dev || !out_ids_dev)))
+        return fail(CLDRD_EINVAL, "search: NULL argument");
+    if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "search: k=%d outside [1,%d]", k, CLDRD_MAX_K);
+    if (!s->finalized) return fail(CLDRD_ESTATE, "search: shard not finalized");
+    if (reinterpret_cast<uintptr_t>(q_dev) % 16 && is_tc(s->scan_eff))
+        return fail(CLDRD_EINVAL, "search: query buffer must be 16-byte aligned");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int64_t launches = 0, chunks = 0, nfailed = 0;
+    unsigned long long tot[ST_COUNT] = {0};
+    s->ev_used = 0;
+    s->scan_ms = 0.0;
+    s->scan_launches = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
+        const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
+        CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+        int rc = search_batch(s, q_dev + size_t(q0) * s->d, nb, k, translate_ids != 0,
+                              out_scores_dev + size_t(q0) * k, out_ids_dev + size_t(q0) * k, st, &launches,
+                              &chunks, &nfailed);
+        if (rc) return rc;
+        for (int i = 0; i < ST_COUNT; ++i) {
+            if (i == ST_MAX_LIST) tot[i] = std::max(tot[i], s->h_stats[i]);
+            else tot[i] += s->h_stats[i];
+        }
+    }
+    if (s->profile) {  // every batch ended with a stream synchronisation: the events are complete
+        for (size_t i = 0; i + 1 < s->ev_used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->scan_ms += ms;
+            s->scan_launches++;
+        }
+    }
+    s->stats[0] = launches;
+    s->stats[1] = chunks;
+    s->stats[2] = nfailed;
+    s->stats[3] = int64_t(tot[ST_RESCORED]);
+    s->stats[4] = int64_t(tot[ST_SURVIVORS]);
+    s->stats[5] = int64_t(tot[ST_MAX_LIST]);
+    s->stats[6] = int64_t(tot[ST_TILES]);
+    s->stats[7] = int64_t(tot[ST_EXACT_COMPACT]);
+    return CLDRD_OK;
+}
+
+int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k, float* out_scores_host,
+                      int64_t* out_ids_host) {
+    if (!s || nq < 0 || (nq && (!q_host || !out_scores_host || !out_ids_host)))
+        return fail(CLDRD_EINVAL, "search_host: NULL argument");
+    if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "search: k=%d outside [1,%d]", k, CLDRD_MAX_K);
+    if (nq == 0) return CLDRD_OK;
+    DeviceGuard g(s->device);
+    const size_t qbytes = size_t(nq) * s->d * sizeof(float);
+    const size_t oelems = size_t(nq) * k;
+    if (qbytes > s->h_q_bytes) {
+        if (s->h_q) cudaFreeHost(s->h_q);
+        s->h_q = nullptr;
+        s->h_q_bytes = 0;
+        CU_TRY(cudaHostAlloc(&s->h_q, qbytes, cudaHostAllocDefault));
+        s->h_q_bytes = qbytes;
+    }
+    if (qbytes > s->d_q_bytes) {
+        cudaFree(s->d_q);
+        s->d_q = nullptr;
+        s->d_q_bytes = 0;
+        CU_TRY(cudaMalloc(&s->d_q, qbytes));
+        s->d_q_bytes = qbytes;
+    }
+    if (oelems > s->h_out_elems) {
+        if (s->h_D) cudaFreeHost(s->h_D);
+        if (s->h_I) cudaFreeHost(s->h_I);
+        s->h_D = nullptr;
+        s->h_I = nullptr;
+        s->h_out_elems = 0;
+        CU_TRY(cudaHostAlloc(&s->h_D, oelems * sizeof(float), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&s->h_I, oelems * sizeof(int64_t), cudaHostAllocDefault));
+        s->h_out_elems = oelems;
+    }
+    if (oelems > s->d_out_elems) {
+        cudaFree(s->d_D);
+        cudaFree(s->d_I);
+        s->d_D = nullptr;
+        s->d_I = nullptr;
+        s->d_out_elems = 0;
+        CU_TRY(cudaMalloc(&s->d_D, oelems * sizeof(float)));
+        CU_TRY(cudaMalloc(&s->d_I, oelems * sizeof(int64_t)));
+        s->d_out_elems = oelems;
+    }
+    cudaStream_t st = cudaStreamPerThread;
+    memcpy(s->h_q, q_host, qbytes);
+    CU_TRY(cudaMemcpyAsync(s->d_q, s->h_q, qbytes, cudaMemcpyHostToDevice, st));
+    int rc = cldrd_search_dev(s, s->d_q, nq, k, 1, s->d_D, s->d_I, st);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(s->h_D, s->d_D, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(s->h_I, s->d_I, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(out_scores_host, s->h_D, oelems * sizeof(float));
+    memcpy(out_ids_host, s->h_I, oelems * sizeof(int64_t));
+    return CLDRD_OK;
+}
+
+int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t k,
+                const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    if (parts < 1 || nq < 0 || k < 1 || k > CLDRD_MAX_K || (nq && (!scores_dev || !rows_dev || !out_scores_dev || !out_ids_dev)))
+        return fail(CLDRD_EINVAL, "merge: bad argument");
+    if (nq == 0) return CLDRD_OK;
+    int n_pad = 2;
+    while (n_pad < parts * k) n_pad <<= 1;
+    const size_t smem = size_t(n_pad) * 8;
+    if (smem > 200 * 1024) return fail(CLDRD_EINVAL, "merge: parts*k=%d too large", parts * k);
+    DeviceGuard g(device);
+    CU_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    merge_kernel<<<unsigned(nq), 512, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
+        scores_dev, rows_dev, parts, nq, k, n_pad, id_map_dev, out_scores_dev, out_ids_dev);
+    CU_TRY(cudaGetLastError());
+    return CLDRD_OK;
+}
+
+int cldrd_shard_set_profiling(cldrd_shard* s, int32_t on) {
+    if (!s) return fail(CLDRD_EINVAL, "set_profiling: NULL");
+    s->profile = on != 0;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_last_scan_time(const cldrd_shard* s, double* scan_ms, int64_t* scan_launches) {
+    if (!s) return fail(CLDRD_EINVAL, "last_scan_time: NULL");
+    if (scan_ms) *scan_ms = s->scan_ms;
+    if (scan_launches) *scan_launches = s->scan_launches;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_last_stats(const cldrd_shard* s, int64_t stats[8]) {
+    if (!s || !stats) return fail(CLDRD_EINVAL, "last_stats: NULL");
+    memcpy(stats, s->stats, sizeof(s->stats));
+    return CLDRD_OK;
+}
+
+int cldrd_scan_dense_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int64_t row_begin, int64_t nrows,
+                         float* out_dev, void* cuda_stream) {
+    if (!s || !q_dev || !out_dev || nq < 1 || nq > kQueryBatch || nrows < 1 || nrows > kDensePiece || row_begin < 0 ||
+        row_begin + nrows > s->nrows)
+        return fail(CLDRD_EINVAL, "scan_dense: bad argument");
+    if (!s->finalized) return fail(CLDRD_ESTATE, "scan_dense: shard not finalized");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    BatchCtx c{};
+    c.s = s;
+    c.st = st;
+    c.q = q_dev;
+    c.nq = int(nq);
+    c.k = 1;
+    CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+    int rc = launch_prep(c);
+    if (rc) return rc;
+    if ((rc = launch_scan(c, true, row_begin, int(nrows)))) return rc;
+    CU_TRY(cudaMemcpy2DAsync(out_dev, size_t(nrows) * 4, s->w_dense, size_t(kDensePiece) * 4, size_t(nrows) * 4, size_t(nq),
+                             cudaMemcpyDeviceToDevice, st));
+    return read_stats(s, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// fp32 FFMA scan: 128 queries x 128 rows per CTA, fused threshold filter or dense dump.
+// This is the correctness anchor and the path for shapes TMA cannot describe (d*4 not a
+// multiple of 16 bytes, unaligned buffers).  It is NOT the fast path: see scan_tc.cuh.
+#pragma once
+#include "device_common.cuh"
+
+namespace cldrd {
+
+struct ScanParams {
+    // operands
+    const float* xb;      // fp32 rows of the shard (SIMT scan)
+    const float* q;       // [nq][d] fp32 (SIMT scan)
+    int d;
+    int nq;
+    int64_t row_begin;    // first local row of the chunk
+    int nrows;            // rows in the chunk
+    // fused filter
+    const float* thr;     // [nq]
+    uint64_t* surv;       // [nq][surv_cap]
+    int* surv_cnt;        // [nq]
+    int surv_cap;
+    // dense dump
+    float* dense;         // [nq][dense_ld]
+    int dense_ld;
+    unsigned long long* stats;
+    // tensor-core scan only
+    int num_kb;           // K blocks of 128 bytes
+    int kb_elems;         // elements per K block (64 half, 32 tf32)
+};
+
+constexpr int SIMT_BM = 128, SIMT_BN = 128, SIMT_BK = 16, SIMT_LD = 132;
+
+template <bool DENSE, bool VEC>
+__global__ void __launch_bounds__(256) scan_simt_kernel(ScanParams p) {
+    __shared__ __align__(16) float As[SIMT_BK][SIMT_LD];
+    __shared__ __align__(16) float Bs[SIMT_BK][SIMT_LD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * SIMT_BM;
+    const int n0 = blockIdx.x * SIMT_BN;
+    const float* __restrict__ A = p.q;
+    const float* __restrict__ B = p.xb + size_t(p.row_begin) * p.d;
+    const int d = p.d;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // each thread stages 2 x (1 row, 4 consecutive k) of A and of B per K block
+    float4 ra[2], rb[2];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int r = idx >> 2, kq = (idx & 3) * 4;
+            const int k = k0 + kq;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            const int qa = m0 + r, rbw = n0 + r;
+            if (VEC) {
+                if (qa < p.nq && k < d) va = *reinterpret_cast<const float4*>(A + size_t(qa) * d + k);
+                if (rbw < p.nrows && k < d) vb = __ldg(reinterpret_cast<const float4*>(B + size_t(rbw) * d + k));
+            } else {
+                if (qa < p.nq) {
+                    const float* s = A + size_t(qa) * d;
+                    if (k + 0 < d) va.x = s[k + 0];
+                    if (k + 1 < d) va.y = s[k + 1];
+                    if (k + 2 < d) va.z = s[k + 2];
+                    if (k + 3 < d) va.w = s[k + 3];
+                }
+                if (rbw < p.nrows) {
+                    const float* s = B + size_t(rbw) * d;
+                    if (k + 0 < d) vb.x = __ldg(s + k + 0);
+                    if (k + 1 < d) vb.y = __ldg(s + k + 1);
+                    if (k + 2 < d) vb.z = __ldg(s + k + 2);
+                    if (k + 3 < d) vb.w = __ldg(s + k + 3);
+                }
+            }
+            ra[i] = va;
+            rb[i] = vb;
+        }
+    };
+    auto store_tile = [&]() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int r = idx >> 2, kq = (idx & 3) * 4;
+            As[kq + 0][r] = ra[i].x;
+            As[kq + 1][r] = ra[i].y;
+            As[kq + 2][r] = ra[i].z;
+            As[kq + 3][r] = ra[i].w;
+            Bs[kq + 0][r] = rb[i].x;
+            Bs[kq + 1][r] = rb[i].y;
+            Bs[kq + 2][r] = rb[i].z;
+            Bs[kq + 3][r] = rb[i].w;
+        }
+    };
+
+    load_tile(0);
+    for (int k0 = 0; k0 < d; k0 += SIMT_BK) {
+        __syncthreads();
+        store_tile();
+        __syncthreads();
+        if (k0 + SIMT_BK < d) load_tile(k0 + SIMT_BK);
+#pragma unroll
+        for (int k = 0; k < SIMT_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int qi = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (qi >= p.nq) continue;
+        float t = 0.f;
+        if (!DENSE) t = p.thr[qi];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (col >= p.nrows) continue;
+            const float v = acc[i][j];
+            if (DENSE) {
+                p.dense[size_t(qi) * p.dense_ld + col] = v;
+            } else if (v >= t) {
+                const int slot = atomicAdd(&p.surv_cnt[qi], 1);
+                if (slot < p.surv_cap)
+                    p.surv[size_t(qi) * p.surv_cap + slot] = make_key(v, uint32_t(p.row_begin + col));
+            }
+        }
+    }
+}
+
+}  // namespace cldrd

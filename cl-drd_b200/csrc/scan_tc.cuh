@@ -1,0 +1,245 @@
+// Tensor-core scan for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma -> TMEM -> fused
+// per-query threshold filter (or dense dump).  The score tile never reaches HBM.
+//
+//   CTA tile      128 queries (TMEM lanes) x 256 index rows (TMEM columns), K streamed in
+//                 128-byte blocks (64 fp16/bf16 or 32 tf32 elements), 4-stage mbarrier ring
+//   accumulators  2 x 256 fp32 columns = all 512 TMEM columns: the epilogue of tile i overlaps
+//                 the MMAs of tile i+1
+//   warps         0: TMA producer   1: MMA issuer + TMEM owner   2..5: epilogue (one per TMEM
+//                 lane quadrant; thread = one query, its threshold lives in a register)
+//   schedule      persistent CTAs; tile t -> (query tile t % num_m, row tile t / num_m) so the
+//                 CTAs in flight share a handful of row tiles through L2 while HBM sees each
+//                 index row once per pass
+#pragma once
+#include "device_common.cuh"
+#include "scan_simt.cuh"  // ScanParams
+
+namespace cldrd {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_KB_BYTES = 128;
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_STAGE = TC_BM * TC_KB_BYTES;  // 16 KiB
+constexpr int TC_B_STAGE = TC_BN * TC_KB_BYTES;  // 32 KiB
+constexpr int TC_STAGE_BYTES = TC_A_STAGE + TC_B_STAGE;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;
+constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// kind: 0 = fp16, 1 = bf16, 2 = tf32.  Instruction descriptor (cute::UMMA::InstrDescriptor):
+// c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | K-major A and B (bits 15,16 = 0)
+// | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t tc_idesc(int kind) {
+    return (1u << 4) | (uint32_t(kind) << 7) | (uint32_t(kind) << 10) | (uint32_t(TC_BN >> 3) << 17) |
+           (uint32_t(TC_BM >> 4) << 24);
+}
+
+template <int KIND, bool DENSE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               ScanParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // 128B-swizzled operand tiles need 1024-byte alignment
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smemA = smem;
+    unsigned char* smemB = smem + size_t(TC_STAGES) * TC_A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(TC_STAGES) * TC_STAGE_BYTES);
+    uint64_t* full_bar = bars;                     // [STAGES] TMA -> MMA
+    uint64_t* empty_bar = bars + TC_STAGES;        // [STAGES] MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * TC_STAGES;    // [2] MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;  // [2] epilogue -> MMA
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    unsigned long long* err = p.stats ? &p.stats[ST_KERNEL_ERR] : nullptr;
+
+    const int num_m = (p.nq + TC_BM - 1) / TC_BM;
+    const int num_n = (p.nrows + TC_BN - 1) / TC_BN;
+    const long long num_tiles = (long long)num_m * num_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_base_slot, TC_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m = int(t % num_m), n = int(t / num_m);
+            const int crd_q = m * TC_BM;
+            const int crd_r = int(p.row_begin) + n * TC_BN;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                    // queries are re-read by every row tile: keep them in L2; index rows stream
+                    tma_load_2d(smemA + size_t(stage) * TC_A_STAGE, &tmA, &full_bar[stage],
+                                kb * p.kb_elems, crd_q, kEvictLast);
+                    tma_load_2d(smemB + size_t(stage) * TC_B_STAGE, &tmB, &full_bar[stage],
+                                kb * p.kb_elems, crd_r, kEvictNormal);
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = tc_idesc(KIND);
+        int stage = 0;
+        uint32_t phase = 0;
+        long long it = 0;
+        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int as = int(it & 1);
+            const uint32_t aphase = uint32_t((it >> 1) & 1);
+            mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + uint32_t(as * TC_BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase, err, 300 + stage);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t a_desc = umma_desc_sw128(smem_u32(smemA + size_t(stage) * TC_A_STAGE));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(smemB + size_t(stage) * TC_B_STAGE));
+#pragma unroll
+                    for (int kk = 0; kk < TC_KB_BYTES / 32; ++kk) {
+                        // one MMA consumes 32 bytes of K: +2 in the 16-byte start-address field
+                        tc_mma_ss<KIND == 2>(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2),
+                                             idesc, uint32_t((kb | kk) != 0));
+                    }
+                    tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> filter =====================
+        const int qd = warp & 3;  // the TMEM lane quadrant this warp may read
+        long long it = 0;
+        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int m = int(t % num_m), n = int(t / num_m);
+            const int as = int(it & 1);
+            const uint32_t aphase = uint32_t((it >> 1) & 1);
+            const int qrow = m * TC_BM + qd * 32 + lane;
+            const bool qvalid = qrow < p.nq;
+            const int valid_n = min(TC_BN, p.nrows - n * TC_BN);
+            const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + uint32_t(as * TC_BN);
+            float thr = INFINITY;
+            if (!DENSE && qvalid) thr = p.thr[qrow];
+            mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
+            tc_fence_after();
+            float v[32];
+            if (DENSE) {
+#pragma unroll 1
+                for (int b = 0; b < TC_BN / 32; ++b) {
+                    tmem_ld32(taddr + uint32_t(b * 32), v);
+                    if (qvalid) {
+                        float* dst = p.dense + size_t(qrow) * p.dense_ld + size_t(n) * TC_BN + b * 32;
+                        if (b * 32 + 32 <= valid_n && (p.dense_ld & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (b * 32 + j < valid_n) dst[j] = v[j];
+                        }
+                    }
+                }
+            } else {
+                // pass 1: which 32-column groups hold anything >= thr for this query?
+                uint32_t flags = 0;
+#pragma unroll
+                for (int b = 0; b < TC_BN / 32; ++b) {
+                    tmem_ld32(taddr + uint32_t(b * 32), v);
+                    float mx = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    flags |= (mx >= thr) ? (1u << b) : 0u;
+                }
+                const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
+                if (wflags) {
+                    // pass 2 (rare): exact survivor masks, one slot reservation per query per tile
+                    uint32_t masks[TC_BN / 32];
+                    int cnt = 0;
+#pragma unroll
+                    for (int b = 0; b < TC_BN / 32; ++b) {
+                        masks[b] = 0;
+                        if ((wflags >> b) & 1u) {
+                            tmem_ld32(taddr + uint32_t(b * 32), v);
+                            uint32_t mk = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                mk |= (v[j] >= thr && (b * 32 + j) < valid_n) ? (1u << j) : 0u;
+                            masks[b] = mk;
+                            cnt += __popc(mk);
+                        }
+                    }
+                    int base = 0;
+                    if (cnt) base = atomicAdd(&p.surv_cnt[qrow], cnt);
+                    uint64_t* dst = p.surv + size_t(qvalid ? qrow : 0) * p.surv_cap;
+                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n * TC_BN);
+#pragma unroll
+                    for (int b = 0; b < TC_BN / 32; ++b) {
+                        if (__any_sync(0xffffffffu, masks[b] != 0)) {
+                            tmem_ld32(taddr + uint32_t(b * 32), v);
+                            const uint32_t mk = masks[b];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if ((mk >> j) & 1u) {
+                                    if (base < p.surv_cap) dst[base] = make_key(v[j], row0 + uint32_t(b * 32 + j));
+                                    ++base;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (warp == 2 && lane == 0 && p.stats && blockIdx.x < num_tiles) {
+            long long mine = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+            atomicAdd(&p.stats[ST_TILES], (unsigned long long)mine);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+}  // namespace cldrd

@@ -1,0 +1,425 @@
+// Candidate bookkeeping kernels: per-query streaming select, exact fp32 re-score + final sort,
+// multi-shard merge, and the query / index preparation passes.
+//
+// Streaming invariant.  For query q let eps be the proven bound on
+// |scan score - exact fp32 score|.  After every chunk the list holds every row seen so far whose
+// scan score is >= v_k - 2*eps, where v_k is the k-th best scan score seen so far, and
+// thr[q] = v_k - 2*eps is what the fused filter of the next chunk compares against.  Any row of
+// the exact top-k satisfies that inequality, so the final exact re-score of the list returns
+// the exact result.
+#pragma once
+#include <cfloat>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "device_common.cuh"
+
+namespace cldrd {
+
+// ------------------------------------------------------------------------------------------
+// block-wide radix select of the k-th largest value among keys[0..n) (shared memory)
+// BITS = 32: on the score half only.  BITS = 64: on the full key (unique -> exactly k kept).
+// Returns the selected value (same in all threads).
+// ------------------------------------------------------------------------------------------
+template <int BITS>
+__device__ uint64_t block_radix_select(const uint64_t* keys, int n, int k, uint32_t* hist /*256*/,
+                                       uint64_t* bcast /*2*/) {
+    uint64_t prefix = 0, mask = 0;
+    int remaining = k;
+    constexpr int kLow = (BITS == 32) ? 32 : 0;  // 32: only the score half takes part
+    for (int shift = 56; shift >= kLow; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            uint64_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[uint32_t(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, b = 255;
+            for (; b > 0; --b) {
+                int h = int(hist[b]);
+                if (cum + h >= remaining) break;
+                cum += h;
+            }
+            bcast[0] = uint64_t(b);
+            bcast[1] = uint64_t(remaining - cum);
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= uint64_t(255) << shift;
+        remaining = int(bcast[1]);
+        __syncthreads();
+    }
+    return prefix;
+}
+
+struct SelectParams {
+    uint64_t* list;        // [nq][keep_cap]
+    int* list_len;         // [nq]
+    int keep_cap;
+    uint64_t* surv;        // [nq][surv_cap]   (filter mode)
+    int* surv_cnt;         // [nq]
+    int surv_cap;
+    const float* dense;    // [nq][dense_ld]   (dense mode, else nullptr)
+    int dense_ld;
+    int dense_n;           // valid columns
+    uint32_t dense_row0;   // local row of dense column 0
+    float* thr;            // [nq]
+    const float* band;     // [nq]  2*eps
+    int k;
+    int* fail;             // [nq]
+    unsigned long long* stats;
+    // exact compaction (tie floods)
+    const float* xb;       // fp32 rows of the shard
+    const float* q;        // [nq][d]
+    int d;
+    int vec4;
+};
+
+// One CTA per query.  dyn smem: keys[keep_cap + surv_cap] u64 | q_s[d] f32 (16B aligned)
+__global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    float* q_s = reinterpret_cast<float*>(sm_raw + size_t(p.keep_cap + p.surv_cap) * 8);
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t bcast[2];
+    __shared__ int s_n, s_out;
+
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (p.fail[q]) {
+        if (tid == 0 && p.surv_cnt) p.surv_cnt[q] = 0;
+        return;
+    }
+    const int L = p.list_len[q];
+    uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
+    for (int i = tid; i < L; i += blockDim.x) keys[i] = my_list[i];
+    if (tid == 0) {
+        s_n = L;
+        s_out = 0;
+    }
+    __syncthreads();
+    int n;
+    if (p.dense) {
+        const float t = p.thr[q];
+        const float* row = p.dense + size_t(q) * p.dense_ld;
+        for (int j = tid; j < p.dense_n; j += blockDim.x) {
+            float v = row[j];
+            if (v >= t) {
+                int slot = atomicAdd(&s_n, 1);
+                keys[slot] = make_key(v, p.dense_row0 + uint32_t(j));
+            }
+        }
+        __syncthreads();
+        n = s_n;
+    } else {
+        const int S = p.surv_cnt[q];
+        if (S > p.surv_cap) {  // survivors were dropped: this query goes to the dense fallback
+            if (tid == 0) {
+                p.fail[q] = 1;
+                p.surv_cnt[q] = 0;
+                atomicAdd(&p.stats[ST_FAILED], 1ull);
+            }
+            return;
+        }
+        const uint64_t* sv = p.surv + size_t(q) * p.surv_cap;
+        for (int i = tid; i < S; i += blockDim.x) keys[L + i] = sv[i];
+        __syncthreads();
+        if (tid == 0) {
+            p.surv_cnt[q] = 0;
+            atomicAdd(&p.stats[ST_SURVIVORS], (unsigned long long)S);
+        }
+        n = L + S;
+    }
+    if (n == L) return;  // nothing new: list and threshold stay as they are
+    if (n < p.k) {  // fewer than k rows seen: keep everything, threshold stays -inf
+        for (int i = L + tid; i < n; i += blockDim.x) my_list[i] = keys[i];
+        if (tid == 0) {
+            p.list_len[q] = n;
+            atomicMax(&p.stats[ST_MAX_LIST], (unsigned long long)n);
+        }
+        return;
+    }
+    // k-th best scan score, then the band below it
+    const uint32_t vk = uint32_t(block_radix_select<32>(keys, n, p.k, hist, bcast) >> 32);
+    const float cutf = ord2f(vk) - p.band[q];
+    const uint32_t cut = f2ord(cutf);
+    // count the band first: if it does not fit, trim by exact score instead
+    int cnt = 0;
+    for (int i = tid; i < n; i += blockDim.x) cnt += (key_ord(keys[i]) >= cut);
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_out, cnt);
+    __syncthreads();
+    cnt = s_out;
+    __syncthreads();
+    if (cnt <= p.keep_cap) {
+        if (tid == 0) s_out = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {
+            uint64_t key = keys[i];
+            if (key_ord(key) >= cut) {
+                int slot = atomicAdd(&s_out, 1);
+                my_list[slot] = key;
+            }
+        }
+        if (tid == 0) {
+            p.list_len[q] = cnt;
+            p.thr[q] = cutf;
+            atomicMax(&p.stats[ST_MAX_LIST], (unsigned long long)cnt);
+        }
+        return;
+    }
+    // Tie flood: more than keep_cap rows inside the band.  Re-score every candidate exactly
+    // (same routine as the final re-score) and keep exactly the k best by full key; exact
+    // scores have zero error, so the invariant still holds with the same band.
+    for (int i = tid; i < p.d; i += blockDim.x) q_s[i] = p.q[size_t(q) * p.d + i];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const uint32_t row = key_row(keys[i]);
+        float s = exact_dot_warp(q_s, p.xb + size_t(row) * p.d, p.d, p.vec4 != 0, lane);
+        if (lane == 0) keys[i] = make_key(s, row);
+    }
+    __syncthreads();
+    const uint64_t kth = block_radix_select<64>(keys, n, p.k, hist, bcast);
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        uint64_t key = keys[i];
+        if (key >= kth) {
+            int slot = atomicAdd(&s_out, 1);
+            my_list[slot] = key;
+        }
+    }
+    if (tid == 0) {
+        p.list_len[q] = p.k;
+        p.thr[q] = ord2f(uint32_t(kth >> 32)) - p.band[q];
+        atomicAdd(&p.stats[ST_EXACT_COMPACT], 1ull);
+        atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)n);
+        atomicMax(&p.stats[ST_MAX_LIST], (unsigned long long)p.k);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide bitonic sort, descending, n_pad a power of two (shared memory)
+// ------------------------------------------------------------------------------------------
+__device__ void block_bitonic_desc(uint64_t* keys, int n_pad) {
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                int hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+struct RescoreParams {
+    const float* xb;      // fp32 rows of the shard
+    const float* q;       // [nq][d]
+    int d;
+    int vec4;
+    const uint64_t* list; // [nq][keep_cap]
+    const int* list_len;
+    int keep_cap;
+    int n_pad;            // pow2 >= keep_cap
+    int k;
+    int64_t row0;         // global row of local row 0
+    const int64_t* ids;   // external ids of this shard's rows, or nullptr
+    float* out_scores;    // [*][k]
+    int64_t* out_ids;     // [*][k]
+    const int* out_index; // optional: output row of query q (dense fallback scatter), or nullptr
+    const int* fail;      // skip failed queries (nullptr = none)
+    unsigned long long* stats;
+};
+
+// One CTA per query: exact fp32 score of every listed row, sort, emit the k best.
+// dyn smem: keys[n_pad] u64 | q_s[d] f32
+__global__ void __launch_bounds__(512) rescore_sort_kernel(RescoreParams p) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    float* q_s = reinterpret_cast<float*>(sm_raw + size_t(p.n_pad) * 8);
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (p.fail && p.fail[q]) return;
+    const int L = p.list_len[q];
+    for (int i = tid; i < p.d; i += blockDim.x) q_s[i] = p.q[size_t(q) * p.d + i];
+    int n_pad = 2;
+    while (n_pad < L) n_pad <<= 1;
+    for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
+    __syncthreads();
+    const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < L; i += nwarps) {
+        const uint32_t row = key_row(my_list[i]);
+        float s = exact_dot_warp(q_s, p.xb + size_t(row) * p.d, p.d, p.vec4 != 0, lane);
+        if (lane == 0) keys[i] = make_key(s, row);
+    }
+    if (tid == 0) atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)L);
+    block_bitonic_desc(keys, n_pad);
+    const size_t orow = p.out_index ? size_t(p.out_index[q]) : size_t(q);
+    float* os = p.out_scores + orow * p.k;
+    int64_t* oi = p.out_ids + orow * p.k;
+    for (int i = tid; i < p.k; i += blockDim.x) {
+        if (i < L) {
+            uint64_t key = keys[i];
+            uint32_t row = key_row(key);
+            os[i] = ord2f(key_ord(key));
+            oi[i] = p.ids ? p.ids[row] : (p.row0 + int64_t(row));
+        } else {
+            os[i] = -FLT_MAX;
+            oi[i] = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-shard merge: [parts][nq][k] (score, global row) -> [nq][k], same key order, so the
+// result is bit-identical to a single-shard search.  One CTA per query.
+// dyn smem: keys[n_pad] u64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) merge_kernel(const float* scores, const int64_t* rows,
+                                                    int parts, int64_t nq, int k, int n_pad,
+                                                    const int64_t* id_map, float* out_scores,
+                                                    int64_t* out_ids) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = parts * k;
+    for (int i = tid; i < n_pad; i += blockDim.x) {
+        uint64_t key = 0;
+        if (i < n) {
+            int part = i / k, j = i - part * k;
+            size_t off = (size_t(part) * nq + q) * k + j;
+            int64_t r = rows[off];
+            if (r >= 0) key = make_key(scores[off], uint32_t(r));
+        }
+        keys[i] = key;
+    }
+    block_bitonic_desc(keys, n_pad);
+    for (int i = tid; i < k; i += blockDim.x) {
+        uint64_t key = keys[i];
+        if (key != 0) {
+            uint32_t row = key_row(key);
+            out_scores[q * k + i] = ord2f(key_ord(key));
+            out_ids[q * k + i] = id_map ? id_map[row] : int64_t(row);
+        } else {
+            out_scores[q * k + i] = -FLT_MAX;
+            out_ids[q * k + i] = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Query preparation: norms -> error band, reset per-query state, low-precision copy.
+// One warp per query.
+// ------------------------------------------------------------------------------------------
+struct QueryPrepParams {
+    const float* q;    // [nq][d]
+    int nq, d;
+    int lp_kind;       // 0 none, 1 f16, 2 bf16
+    void* q_lp;        // [nq][d] half / bf16
+    float coef;        // eps = coef * |q| * bmax_norm + abs_coef * (|q| + bmax_norm)
+    float abs_coef;
+    float bmax_norm;
+    float* band;       // 2*eps (slightly inflated)
+    float* thr;
+    int* list_len;
+    int* surv_cnt;
+    int* fail;
+    unsigned long long* stats;
+};
+
+__global__ void query_prep_kernel(QueryPrepParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.nq) return;
+    const float* row = p.q + size_t(warp) * p.d;
+    float ss = 0.f, mx = 0.f;
+    for (int c = lane; c < p.d; c += 32) {
+        float v = row[c];
+        ss = fmaf(v, v, ss);
+        mx = fmaxf(mx, fabsf(v));
+        if (p.lp_kind == 1)
+            reinterpret_cast<__half*>(p.q_lp)[size_t(warp) * p.d + c] = __float2half_rn(v);
+        else if (p.lp_kind == 2)
+            reinterpret_cast<__nv_bfloat16*>(p.q_lp)[size_t(warp) * p.d + c] = __float2bfloat16_rn(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        const float qn = sqrtf(ss) * 1.0001f;
+        const float eps = p.coef * qn * p.bmax_norm + p.abs_coef * (qn + p.bmax_norm);
+        p.band[warp] = 2.0f * eps * 1.0001f;
+        p.thr[warp] = -INFINITY;
+        p.list_len[warp] = 0;
+        p.surv_cnt[warp] = 0;
+        p.fail[warp] = 0;
+        if (p.lp_kind == 1 && !(mx < 65504.f)) atomicAdd(&p.stats[ST_RANGE_ERR], 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Index preparation (shard finalize): max row norm, max |x|, optional fp16/bf16 copy.
+// One warp per row, grid-stride.
+// ------------------------------------------------------------------------------------------
+__global__ void index_prep_kernel(const float* xb, int64_t nrows, int d, int lp_kind, void* lp,
+                                  unsigned int* max_norm2_bits, unsigned int* max_abs_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    float best_ss = 0.f, best_mx = 0.f;
+    for (int64_t r = warp0; r < nrows; r += nwarps) {
+        const float* row = xb + r * d;
+        float ss = 0.f, mx = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            float v = row[c];
+            ss = fmaf(v, v, ss);
+            mx = fmaxf(mx, fabsf(v));
+            if (lp_kind == 1)
+                reinterpret_cast<__half*>(lp)[r * d + c] = __float2half_rn(v);
+            else if (lp_kind == 2)
+                reinterpret_cast<__nv_bfloat16*>(lp)[r * d + c] = __float2bfloat16_rn(v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        // NaN/inf rows poison the bound on purpose: (ss != ss) -> +inf
+        if (!(ss == ss)) ss = INFINITY;
+        if (!(mx == mx)) mx = INFINITY;
+        best_ss = fmaxf(best_ss, ss);
+        best_mx = fmaxf(best_mx, mx);
+    }
+    if (lane == 0) {
+        atomicMax(max_norm2_bits, __float_as_uint(best_ss));  // non-negative floats order as uints
+        atomicMax(max_abs_bits, __float_as_uint(best_mx));
+    }
+}
+
+// gather failed queries into a compact matrix + remember where their results go
+__global__ void gather_failed_kernel(const float* q, int d, const int* fail_index, int nfail,
+                                     float* q_out) {
+    const int f = blockIdx.x;
+    if (f >= nfail) return;
+    const float* src = q + size_t(fail_index[f]) * d;
+    float* dst = q_out + size_t(f) * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) dst[c] = src[c];
+}
+
+}  // namespace cldrd

@@ -1,0 +1,183 @@
+/* cldrd.h — C ABI of libcldrd.so: B200-native exhaustive inner-product top-k search.
+ *
+ * This is the drop-in boundary for CL-DRD's dense-retrieval search path.  The reference has no
+ * FFI of its own: its seam is the subset of the `faiss` Python API that the retriever scripts
+ * touch.  Every entry point below names the reference interface it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding that a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function returns 0 on success
+ * or a negative CLDRD_E* code; cldrd_last_error() returns a thread-local message for the last
+ * failure on the calling thread.  Pointers named *_host are host memory, *_dev are device
+ * memory on the shard's device.  Handles are opaque and not thread-safe per handle (the
+ * reference issues one search at a time: retriever/retrieval_utils.py:141-147).
+ * There is NO CPU search path: without a CUDA device the compute entry points fail with
+ * CLDRD_ECUDA.
+ */
+#ifndef CLDRD_H_
+#define CLDRD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLDRD_ABI_VERSION 1
+
+/* error codes */
+#define CLDRD_OK        0
+#define CLDRD_EINVAL   -1   /* bad argument (shape, dtype, k out of range, NULL) */
+#define CLDRD_EIO      -2   /* file could not be opened / read / written */
+#define CLDRD_EFORMAT  -3   /* not an IxMp/IxM2/IxFI index file, or metric != inner product */
+#define CLDRD_ECUDA    -4   /* CUDA runtime / driver failure, or no device */
+#define CLDRD_ENOMEM   -5   /* host or device allocation failed */
+#define CLDRD_ESTATE   -6   /* call order violated (e.g. search before finalize) */
+
+/* scan precision of a shard.  All modes return exact fp32 scores: the tensor-core scan is a
+ * filter with a proven error band and every surviving candidate is re-scored in fp32 from the
+ * fp32 rows.  They differ in what the scan streams from HBM. */
+#define CLDRD_SCAN_SIMT_F32 0  /* fp32 FFMA tiles, no tensor cores; any d.  Correctness anchor.   */
+#define CLDRD_SCAN_TC_TF32  1  /* tcgen05 kind::tf32 straight off the fp32 rows (no second copy). */
+#define CLDRD_SCAN_TC_F16   2  /* tcgen05 kind::f16 over an fp16 copy of the rows.                */
+#define CLDRD_SCAN_TC_BF16  3  /* tcgen05 kind::f16 over a bf16 copy of the rows.                 */
+
+#define CLDRD_MAX_K 2048       /* same limit as faiss' GPU flat index */
+
+typedef struct cldrd_shard cldrd_shard;
+
+const char* cldrd_last_error(void);
+int         cldrd_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index file  (replaces faiss.write_index / faiss.read_index:
+ *   retriever/index_text.py:105, retriever/retrieve_top_passages.py:85,
+ *   retriever/retrieve_top_queries.py:60).  Layout: SURVEY.md §8 a-2.  Host only, no CUDA.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Parse the headers.  has_ids: 1 for IxMp / IxM2 wrappers, 0 for a bare IxFI.  idmap2: 1 for IxM2.
+ * data_off / ids_off: byte offsets of the float32 payload and of the int64 id array. */
+int cldrd_index_probe(const char* path, int64_t* ntotal, int32_t* d, int32_t* metric,
+                      int32_t* has_ids, int32_t* idmap2, int64_t* data_off, int64_t* ids_off);
+
+/* Write IxMp{IxFI} (ids != NULL; IxM2 when idmap2 != 0) or bare IxFI (ids == NULL). */
+int cldrd_index_write(const char* path, const float* xb_host, const int64_t* ids_host,
+                      int64_t n, int32_t d, int32_t idmap2);
+
+/* Streaming writer used by the index builder (replaces the hold-everything-in-RAM flow of
+ * retriever/index_text.py:86-105): begin reserves the layout for n rows, append writes rows at
+ * their final offset, finish writes the id array and closes. */
+typedef struct cldrd_index_writer cldrd_index_writer;
+int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t n, int32_t d,
+                             int32_t with_ids, int32_t idmap2);
+int cldrd_index_writer_append(cldrd_index_writer* w, const float* rows_host, int64_t nrows);
+int cldrd_index_writer_finish(cldrd_index_writer* w, const int64_t* ids_host /* n or NULL */);
+
+/* pread a row range / id range of an index file into host memory. */
+int cldrd_index_read_rows(const char* path, int64_t row0, int64_t nrows, float* out_host);
+int cldrd_index_read_ids(const char* path, int64_t row0, int64_t nrows, int64_t* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Shard = a contiguous range of passage rows resident in one GPU's HBM
+ * (replaces faiss.index_cpu_to_gpu / index_cpu_to_gpu_multiple(shard=True):
+ *   retriever/retrieval_utils.py:155-184).
+ * ------------------------------------------------------------------------------------------- */
+
+/* row0: global row of the shard's first row (added to local rows in the results).
+ * scan: one of CLDRD_SCAN_*.  Allocates nothing large until rows arrive. */
+int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrows, int32_t d,
+                       int32_t scan);
+void cldrd_shard_destroy(cldrd_shard* s);
+
+/* Three ways to populate the fp32 rows (exactly one must cover [0, nrows)):
+ *  - upload: copy n rows from host memory into local rows [row_off, row_off+n)
+ *  - load_file: pread this shard's rows [row0, row0+nrows) of an index file through a pinned
+ *    double buffer (the payload starts at byte 82, never aligned, so it cannot be mapped in place)
+ *  - adopt: borrow a device buffer of nrows*d floats that the caller keeps alive (zero copy). */
+int cldrd_shard_upload(cldrd_shard* s, const float* rows_host, int64_t row_off, int64_t n);
+int cldrd_shard_load_file(cldrd_shard* s, const char* path);
+int cldrd_shard_adopt(cldrd_shard* s, const float* rows_dev);
+
+/* External ids (faiss IndexIDMap::id_map; retriever/index_text.py:97).  ids_host: nrows int64
+ * for this shard's rows, or NULL -> results carry global row numbers. */
+int cldrd_shard_set_ids(cldrd_shard* s, const int64_t* ids_host);
+
+/* Build the scan-side state: fp16/bf16 copy (if the scan mode needs one), row-norm bound,
+ * TMA descriptors.  Must be called once after the rows are in place and before any search. */
+int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream);
+
+/* Properties. */
+int64_t cldrd_shard_nrows(const cldrd_shard* s);
+int32_t cldrd_shard_dim(const cldrd_shard* s);
+int32_t cldrd_shard_scan(const cldrd_shard* s);
+/* Bytes one full scan streams from HBM (the roofline's algorithmic bytes per index pass). */
+int64_t cldrd_shard_scan_bytes(const cldrd_shard* s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Search  (replaces index.search(x, k): retriever/retrieval_utils.py:135,143;
+ *          duplicate call sites evaluation/utils.py:110,117).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Device-resident search over one shard.
+ *   q_dev         [nq, d] float32, C-contiguous, 16-byte aligned
+ *   out_scores_dev[nq, k] float32, best first; -FLT_MAX padding when the shard has < k rows
+ *   out_ids_dev   [nq, k] int64: external ids if translate_ids != 0 and ids were set, else
+ *                 global rows (row0 + local row); -1 padding
+ * Order: descending score, ties -> lower row.  Work is issued on `cuda_stream`; the call
+ * synchronises that stream before returning (it reads back the overflow / watchdog flags), so
+ * results are complete on return. */
+int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
+                     int32_t translate_ids, float* out_scores_dev, int64_t* out_ids_dev,
+                     void* cuda_stream);
+
+/* Host-buffer search: the call the faiss-shaped wrapper makes.  Copies q in through pinned
+ * staging, searches, copies D and I out; synchronous on return like faiss. */
+int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k,
+                      float* out_scores_host, int64_t* out_ids_host);
+
+/* Merge per-shard candidate lists (replaces faiss IndexShards' CPU merge_knn_results behind
+ * retriever/retrieval_utils.py:176-182).  Inputs are [parts][nq][k] device arrays of scores and
+ * GLOBAL rows as produced by cldrd_search_dev(translate_ids=0) on each shard and gathered to
+ * one device (NCCL all_gather / gather by the caller).  id_map_dev: optional int64[ntotal]
+ * global-row -> external-id table applied to the merged rows (NULL = keep rows). */
+int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
+                int64_t nq, int32_t k, const int64_t* id_map_dev, float* out_scores_dev,
+                int64_t* out_ids_dev, void* cuda_stream);
+
+/* Per-search statistics of the last cldrd_search_* call on this shard (for tests / bench):
+ * stats[0] kernel launches, [1] index chunks scanned, [2] queries sent to the dense fallback,
+ * [3] total candidates re-scored, [4] total survivors pushed by the fused filter,
+ * [5] max candidate-list length, [6] tcgen05 tiles executed, [7] in-kernel exact compactions. */
+int cldrd_shard_last_stats(const cldrd_shard* s, int64_t stats[8]);
+
+/* Scan-kernel timing for the roofline line of bench.py: when on, every scan launch is bracketed
+ * by CUDA events on the launching stream; after a search, last_scan_time returns the summed
+ * device time of the scan kernels of that search and how many launches it covers. */
+int cldrd_shard_set_profiling(cldrd_shard* s, int32_t on);
+int cldrd_shard_last_scan_time(const cldrd_shard* s, double* scan_ms, int64_t* scan_launches);
+
+/* Debug / test hook: run only the scan kernel in dense mode and return the raw scan scores
+ * (approximate for the tensor-core modes) of queries [0,nq) against local rows
+ * [row_begin, row_begin+nrows), nrows <= 8192.  out_dev: [nq, nrows] float32. */
+int cldrd_scan_dense_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int64_t row_begin,
+                         int64_t nrows, float* out_dev, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Run file  (replaces the regroup + writer loops: retriever/retrieve_top_passages.py:90-109,
+ *            retriever/retrieve_top_queries.py:65-82).  Host only.
+ * Writes "qid\tdocid\trank\tscore\n" per hit; score text is Python's repr(float(np.float32)).
+ * Consecutive equal qids continue one rank sequence (the reference's dict regroup); hits with
+ * id -1 are written as the reference would write them.  append != 0 opens with "a".
+ * lines_written (optional) receives the number of lines. */
+int cldrd_write_run(const char* path, const int64_t* qids, const float* scores,
+                    const int64_t* ids, int64_t nq, int32_t k, int32_t append,
+                    int64_t* lines_written);
+
+/* Format one float exactly as the reference's f-string does; returns the length written
+ * (buf must hold >= 32 bytes). */
+int cldrd_format_score(float s, char* buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLDRD_H_ */

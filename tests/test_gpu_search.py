@@ -1,0 +1,358 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): fp32 scores within 1e-5 relative; ids bit-exact except
+inside near-tie bands of that width (oracle.compare_topk).  Integer outputs (ids, padding) are
+compared exactly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SCANS = ["simt", "tf32", "f16", "bf16"]
+
+
+def _gpu_index(xb, ids, scan, device=0):
+    import cldrd
+    host = cldrd.IndexIDMap(cldrd.IndexFlatIP(xb.shape[1])) if ids is not None else cldrd.IndexFlatIP(xb.shape[1])
+    if ids is not None:
+        host.add_with_ids(xb, ids)
+    else:
+        host.add(xb)
+    co = cldrd.GpuClonerOptions()
+    co.scan = scan
+    return cldrd.index_cpu_to_gpu(cldrd.StandardGpuResources(), device, host, co)
+
+
+def _check(gpu, xb, ids, xq, k, margin=16):
+    D, I = gpu.search(xq, k)
+    D_ref, I_ref = O.search(xb, ids, xq, k)
+    D_ext, I_ext = O.search(xb, ids, xq, k + margin, dtype=np.float64)
+    r = O.compare_topk(D, I, D_ref, I_ref, D_ext, I_ext)
+    assert r["ok"], (gpu.scan, k, r, gpu.last_stats())
+    assert r["overlap"] == 1.0
+    # sortedness: descending scores within every row
+    valid = I >= 0
+    d = np.where(valid, D, -np.inf)
+    assert (np.diff(d, axis=1) <= 0).all()
+    return D, I
+
+
+# ------------------------------------------------------------------------------------------
+# the scan kernels alone: raw scan scores against the fp64 product, inside the proven band
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_scan_dense_within_error_bound(cldrd_lib, scan):
+    import torch
+    import cldrd
+    from cldrd._lib import check
+    xb, xq = O.synth(3000, 768, 10), O.synth(200, 768, 11)
+    gpu = _gpu_index(xb, None, scan)
+    assert gpu.scan == scan
+    q = torch.from_numpy(xq).cuda()
+    nrows, row_begin = 1500, 700   # unaligned begin, partial last tile
+    out = torch.empty((xq.shape[0], nrows), dtype=torch.float32, device="cuda")
+    check(cldrd_lib.cldrd_scan_dense_dev(gpu._shard.handle, C.c_void_p(q.data_ptr()), xq.shape[0], row_begin, nrows,
+                                         C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    ref = xq.astype(np.float64) @ xb[row_begin:row_begin + nrows].astype(np.float64).T
+    scale = np.linalg.norm(xq, axis=1)[:, None] * np.linalg.norm(xb[row_begin:row_begin + nrows], axis=1)[None, :]
+    rel = np.abs(got - ref) / scale
+    coef = {"simt": 2.0 ** -24 * 784, "tf32": 2.0 ** -9, "f16": 2.0 ** -10, "bf16": 2.0 ** -7}[scan]
+    assert rel.max() <= coef, (scan, rel.max(), coef)
+    # and it is a real product, not zeros: typical error far below the bound, result correlated
+    assert np.corrcoef(got.ravel(), ref.ravel())[0, 1] > 0.9999
+    gpu.close()
+
+
+# ------------------------------------------------------------------------------------------
+# search parity
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_golden_seeded_1000x64(cldrd_lib, scan):
+    g = np.load(os.path.join(GOLD, "seeded_1000x64.npz"))
+    xb, xq, ids = O.synth(1000, 64, 0), O.synth(16, 64, 1), O.synth_ids(1000, 7)
+    gpu = _gpu_index(xb, ids, scan)
+    for k in (10, 100):
+        D, I = gpu.search(xq, k)
+        r = O.compare_topk(D, I, g[f"D{k}"], g[f"I{k}"])
+        assert r["ok"], (scan, k, r)
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_golden_20000x768_k1000(cldrd_lib, scan):
+    g = np.load(os.path.join(GOLD, "seeded_20000x768_k1000.npz"))
+    xb, xq = O.synth(20000, 768, 0), O.synth(8, 768, 1)
+    gpu = _gpu_index(xb, None, scan)
+    D, I = gpu.search(xq, 1000)
+    D_ext, I_ext = O.search_rows(xb, xq, 1016, dtype=np.float64)
+    r = O.compare_topk(D, I, g["D"], g["R"].astype(np.int64), D_ext, I_ext)
+    assert r["ok"], (scan, r, gpu.last_stats())
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+@pytest.mark.parametrize("k", [1, 10, 1000, 2048])
+def test_parity_medium(cldrd_lib, scan, k):
+    xb, xq, ids = O.synth(30000, 128, 20), O.synth(129, 128, 21), O.synth_ids(30000, 22)
+    gpu = _gpu_index(xb, ids, scan)
+    _check(gpu, xb, ids, xq, k)
+    st = gpu.last_stats()
+    assert st["launches"] > 0 and st["chunks"] >= 2
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", ["f16", "tf32"])
+def test_parity_config1_shape(cldrd_lib, scan):
+    """BASELINE.json configs[0] shape (100k x 768, k=1000) on a query subset the oracle finishes fast."""
+    xb, xq, ids = O.synth(100_000, 768, 0), O.synth(1000, 768, 1)[:200], O.synth_ids(100_000, 7)
+    gpu = _gpu_index(xb, ids, scan)
+    _check(gpu, xb, ids, xq, 1000)
+    st = gpu.last_stats()
+    assert st["tc_tiles"] > 0, "tensor-core scan did not run"
+    assert st["fallback_queries"] == 0
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+@pytest.mark.parametrize("nq", [1, 127, 128, 129, 300])
+def test_query_batch_edges(cldrd_lib, scan, nq):
+    xb, xq = O.synth(9000, 64, 30), O.synth(nq, 64, 31)
+    gpu = _gpu_index(xb, None, scan)
+    _check(gpu, xb, None, xq, 20)
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_fewer_rows_than_k_pads(cldrd_lib, scan):
+    xb, xq, ids = O.synth(37, 32, 40), O.synth(5, 32, 41), O.synth_ids(37, 42) + 2 ** 33
+    gpu = _gpu_index(xb, ids, scan)
+    D, I = _check(gpu, xb, ids, xq, 100)
+    assert (I[:, 37:] == -1).all() and (D[:, 37:] == O.NEG_FLT_MAX).all()
+    assert (I[:, :37] >= 2 ** 33).all()  # ids beyond 2^31 survive
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_exact_duplicates_tie_order(cldrd_lib, scan):
+    """Duplicate rows: equal scores must come back lower-row-first; a flood of ties bigger than
+    the candidate list forces the in-kernel exact compaction."""
+    base = O.synth(50, 64, 50)
+    xb = np.concatenate([base] * 200)          # 10000 rows, every vector 200 times
+    xq = O.synth(7, 64, 51)
+    gpu = _gpu_index(xb, None, scan)
+    D, I = gpu.search(xq, 500)
+    D_ref, I_ref = O.search(xb, None, xq, 500)
+    np.testing.assert_allclose(D, D_ref, rtol=1e-5)
+    # within a group of bit-equal scores rows are ascending
+    for i in range(xq.shape[0]):
+        same = D[i, 1:] == D[i, :-1]
+        assert (I[i, 1:][same] > I[i, :-1][same]).all()
+    r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, None, xq, 700, dtype=np.float64))
+    assert r["ok"], (scan, r, gpu.last_stats())
+    gpu.close()
+    # all rows identical: 6000 tied candidates > list capacity
+    xb = np.tile(O.synth(1, 64, 52), (6000, 1))
+    gpu = _gpu_index(xb, None, scan)
+    D, I = gpu.search(xq, 1000)
+    assert (I == np.arange(1000)[None, :]).all(), gpu.last_stats()
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", SCANS)
+def test_negative_scores_only(cldrd_lib, scan):
+    xb = np.abs(O.synth(5000, 64, 60))
+    xq = -np.abs(O.synth(9, 64, 61))
+    gpu = _gpu_index(xb, None, scan)
+    D, I = _check(gpu, xb, None, xq, 50)
+    assert (D < 0).all()
+    gpu.close()
+
+
+@pytest.mark.parametrize("scan", ["f16", "tf32", "simt"])
+def test_adversarial_order_uses_dense_fallback(cldrd_lib, scan):
+    """Rows sorted by ascending score for the queries: every chunk beats the running threshold,
+    the survivor buffers overflow and the dense fallback must still return the exact answer."""
+    d = 64
+    qdir = O.synth(1, d, 70)[0]
+    qdir /= np.linalg.norm(qdir)
+    xb = O.synth(120_000, d, 71) * 0.05 + np.linspace(-3, 3, 120_000, dtype=np.float32)[:, None] * qdir[None, :]
+    xb = xb.astype(np.float32)
+    xq = (qdir[None, :] * 5 + O.synth(40, d, 72) * 0.01).astype(np.float32)
+    gpu = _gpu_index(xb, None, scan)
+    _check(gpu, xb, None, xq, 100)
+    assert gpu.last_stats()["fallback_queries"] > 0, gpu.last_stats()
+    gpu.close()
+
+
+def test_unaligned_dim_falls_back_to_simt_scan(cldrd_lib):
+    xb, xq = O.synth(4000, 30, 80), O.synth(11, 30, 81)
+    gpu = _gpu_index(xb, None, "f16")
+    assert gpu.scan == "simt"      # d*2 bytes is not a multiple of 16: TMA cannot describe it
+    _check(gpu, xb, None, xq, 10)
+    gpu.close()
+
+
+def test_fp16_range_guard_and_auto_mode(cldrd_lib):
+    import cldrd
+    xb, xq = O.synth(3000, 64, 90) * 1e5, O.synth(4, 64, 91)
+    with pytest.raises(cldrd.CldrdError):
+        _gpu_index(xb, None, "f16")
+    gpu = _gpu_index(xb, None, "auto")
+    assert gpu.scan == "tf32"
+    _check(gpu, xb, None, xq, 10)
+    gpu.close()
+
+
+def test_modes_agree_bit_exactly(cldrd_lib):
+    """Every returned score comes from the same fp32 re-score routine: scan modes must agree to the bit."""
+    xb, xq = O.synth(50_000, 256, 100), O.synth(64, 256, 101)
+    res = {}
+    for scan in SCANS:
+        gpu = _gpu_index(xb, None, scan)
+        res[scan] = gpu.search(xq, 100)
+        gpu.close()
+    for scan in SCANS[1:]:
+        assert np.array_equal(res[scan][0], res["simt"][0]), scan
+        assert np.array_equal(res[scan][1], res["simt"][1]), scan
+
+
+def test_k_limits_and_errors(cldrd_lib):
+    import cldrd
+    xb = O.synth(100, 16, 110)
+    gpu = _gpu_index(xb, None, "simt")
+    with pytest.raises(RuntimeError):
+        gpu.search(O.synth(1, 16, 0), 4096)
+    with pytest.raises(TypeError):
+        gpu.search(O.synth(1, 16, 0).astype(np.float64), 5)
+    with pytest.raises(AssertionError):
+        gpu.search(O.synth(1, 8, 0), 5)
+    D, I = gpu.search(np.empty((0, 16), dtype=np.float32), 5)
+    assert D.shape == (0, 5) and I.shape == (0, 5)
+    gpu.close()
+
+
+# ------------------------------------------------------------------------------------------
+# file -> HBM -> search -> run file, the reference's own helpers driving our objects
+# ------------------------------------------------------------------------------------------
+
+def test_file_to_run_file_end_to_end(cldrd_lib, tmp_path):
+    import cldrd
+    from cldrd import retrieval_utils as RU
+    xb, xq, ids = O.synth(20000, 96, 120), O.synth(300, 96, 121), O.synth_ids(20000, 122)
+    path = tmp_path / "checkpoint_120000.index"
+    O.write_index(str(path), xb, ids)                       # a file as real faiss would write it
+    index = cldrd.read_index(str(path))
+    index = RU.convert_index_to_gpu(index, 0, False)
+    nn_scores, nn_ids = RU.index_retrieve(index, xq, 100, batch=128)   # reference loop shape
+    assert isinstance(nn_scores, list) and len(nn_scores) == 300 and len(nn_ids[0]) == 100
+    D_ref, I_ref = O.search(xb, ids, xq, 100)
+    r = O.compare_topk(np.array(nn_scores, dtype=np.float32), np.array(nn_ids), D_ref, I_ref,
+                       *O.search(xb, ids, xq, 116, dtype=np.float64))
+    assert r["ok"], r
+    D, I = RU.index_retrieve_arrays(index, xq, 100)
+    assert np.array_equal(I, np.array(nn_ids))              # one pass == 128-query round trips
+    qids = np.arange(1000, 1300, dtype=np.int64)
+    run_a, run_b = tmp_path / "dev_a.run", tmp_path / "dev_b.run"
+    cldrd.write_run_file(str(run_a), qids, I, D)
+    O.write_run(str(run_b), qids.tolist(), nn_ids, nn_scores)
+    assert run_a.read_bytes() == run_b.read_bytes()
+
+
+def test_two_shards_merge_equals_single_shard(cldrd_lib):
+    """Row-sharded search + merge kernel == single-shard search, bit for bit."""
+    import torch
+    from cldrd import dist as CD
+    xb, xq, ids = O.synth(40_001, 128, 130), O.synth(150, 128, 131), O.synth_ids(40_001, 132)
+    rows = torch.from_numpy(xb).cuda()
+    q = torch.from_numpy(xq).cuda()
+    id_map = torch.from_numpy(ids).cuda()
+    one = CD.ShardedSearcher.from_rows(rows, 0, xb.shape[0], scan="f16", id_map=id_map)
+    D1, I1 = one.search(q, 100)
+    from cldrd.index import shard_ranges
+    Ds, Is = [], []
+    for rr in shard_ranges(xb.shape[0], 3):
+        part = rows[rr.start:rr.stop].contiguous()
+        sh = CD.ShardedSearcher.from_rows(part, rr.start, xb.shape[0], scan="f16")
+        D, I = sh.local.search_device(q, 100, translate_ids=False)
+        assert int(I.min()) >= rr.start and int(I.max()) < rr.stop
+        Ds.append(D)
+        Is.append(I)
+    Dm, Im = CD.merge_candidates(torch.stack(Ds), torch.stack(Is), id_map)
+    assert torch.equal(Dm, D1) and torch.equal(Im, I1)
+    D_ref, I_ref = O.search(xb, ids, xq, 100)
+    r = O.compare_topk(Dm.cpu().numpy(), Im.cpu().numpy(), D_ref, I_ref, *O.search(xb, ids, xq, 116, dtype=np.float64))
+    assert r["ok"], r
+
+
+def test_multi_gpu_in_process_shards(cldrd_lib):
+    import torch
+    import cldrd
+    from cldrd import retrieval_utils as RU
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    xb, xq, ids = O.synth(30_000, 64, 140), O.synth(50, 64, 141), O.synth_ids(30_000, 142)
+    host = cldrd.IndexIDMap(cldrd.IndexFlatIP(64))
+    host.add_with_ids(xb, ids)
+    gpu = RU.convert_index_to_gpu(host, [0, 1], False)
+    D, I = gpu.search(xq, 50)
+    D_ref, I_ref = O.search(xb, ids, xq, 50)
+    r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, ids, xq, 66, dtype=np.float64))
+    assert r["ok"], r
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1] shape): no oracle can walk 8.8M x 768 for many
+# queries in test time, so use size-independent properties.
+# ------------------------------------------------------------------------------------------
+
+def test_full_size_properties(cldrd_lib):
+    import torch
+    from cldrd import dist as CD
+    free, _ = torch.cuda.mem_get_info()
+    N, d, k = 8_841_823, 768, 1000
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~45 GB of free HBM")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rows = torch.empty((N, d), dtype=torch.float32, device="cuda")
+    step = 1 << 20
+    for r0 in range(0, N, step):
+        rows[r0:r0 + step].normal_(generator=g)
+    nq = 256
+    q = torch.randn((nq, d), generator=g, device="cuda")
+    # planted neighbours: query i has 3 known rows with a dominant score
+    planted = torch.randint(0, N, (nq, 3), generator=g, device="cuda")
+    for j in range(3):
+        rows[planted[:, j]] = q * (1.5 - 0.1 * j)
+    s16 = CD.ShardedSearcher.from_rows(rows, 0, N, scan="f16")
+    D16, I16 = s16.search(q, k)
+    st = s16.shard.stats()
+    assert st["tc_tiles"] > 0 and st["fallback_queries"] == 0, st
+    assert torch.equal(I16[:, :3], planted), "planted neighbours not on top"
+    assert (D16[:, 1:] <= D16[:, :-1]).all()
+    # oracle on a slice: exact fp32 re-score of the returned rows reproduces the returned scores
+    sel = I16[:8]
+    ref = (rows[sel.reshape(-1)].double().reshape(8, k, d) * q[:8].double()[:, None, :]).sum(-1)
+    assert torch.allclose(D16[:8].double(), ref, rtol=1e-5, atol=0)
+    # the tf32 scan over the raw fp32 rows returns the same bits
+    del s16
+    s32 = CD.ShardedSearcher.from_rows(rows, 0, N, scan="tf32")
+    D32, I32 = s32.search(q, k)
+    assert torch.equal(D32, D16) and torch.equal(I32, I16)
+    # k-th score is a true threshold: no row outside the result beats it (checked on a row sample)
+    samp = torch.randint(0, N, (20_000,), generator=g, device="cuda")
+    sc = q[:16] @ rows[samp].T
+    kth = D16[:16, -1:]
+    beat = sc > kth * (1 + 1e-5)
+    in_res = (samp[None, :, None] == I16[:16, None, :]).any(-1)
+    assert not (beat & ~in_res).any()

@@ -1,0 +1,172 @@
+"""Host-side logic of the faiss-shaped surface: index objects, file I/O through the C ABI,
+the run-file writer, and the reference's own evaluator consuming our output."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF = "/root/reference"
+
+
+def test_write_index_matches_oracle_bytes(cldrd_lib, tmp_path):
+    import cldrd
+    xb, ids = O.synth(257, 24, 0), O.synth_ids(257)
+    idx = cldrd.IndexIDMap(cldrd.IndexFlatIP(24))
+    idx.add_with_ids(xb[:100], ids[:100])
+    idx.add_with_ids(xb[100:], ids[100:])
+    assert idx.ntotal == 257 and idx.d == 24
+    p = tmp_path / "a.index"
+    cldrd.write_index(idx, str(p))
+    assert p.read_bytes() == O.write_index_bytes(xb, ids)
+    idx2 = cldrd.IndexIDMap2(cldrd.IndexFlatIP(24))
+    idx2.add_with_ids(xb, ids)
+    cldrd.write_index(idx2, str(p))
+    assert p.read_bytes() == O.write_index_bytes(xb, ids, idmap2=True)
+    flat = cldrd.index_factory(24, "Flat", cldrd.METRIC_INNER_PRODUCT)
+    flat.add(xb)
+    cldrd.write_index(flat, str(p))
+    assert p.read_bytes() == O.write_index_bytes(xb, None)
+
+
+def test_read_index_golden_and_lazy(cldrd_lib):
+    import cldrd
+    idx = cldrd.read_index(os.path.join(GOLD, "tiny_ixmp.index"))
+    assert isinstance(idx, cldrd.IndexIDMap) and idx.ntotal == 2 and idx.d == 4
+    assert idx._rows.file is not None  # rows not read yet
+    assert idx.id_map.tolist() == [7, 2 ** 33 + 5]
+    assert idx._rows.materialize().tolist() == [[1.0, 2.0, 3.0, 4.0], [-1.0, 0.5, 0.25, 8.0]]
+
+
+def test_streaming_writer_and_row_reads(cldrd_lib, tmp_path):
+    import ctypes as C
+    from cldrd._lib import check, ptr
+    xb, ids = O.synth(1000, 16, 2), O.synth_ids(1000)
+    p = str(tmp_path / "s.index").encode()
+    w = C.c_void_p()
+    check(cldrd_lib.cldrd_index_writer_begin(C.byref(w), p, 1000, 16, 1, 0))
+    for r0 in range(0, 1000, 300):
+        part = np.ascontiguousarray(xb[r0:r0 + 300])
+        check(cldrd_lib.cldrd_index_writer_append(w, ptr(part), part.shape[0]))
+    check(cldrd_lib.cldrd_index_writer_finish(w, ptr(ids)))
+    assert open(p, "rb").read() == O.write_index_bytes(xb, ids)
+    out = np.empty((10, 16), dtype=np.float32)
+    check(cldrd_lib.cldrd_index_read_rows(p, 495, 10, ptr(out)))
+    assert np.array_equal(out, xb[495:505])
+    oi = np.empty((7,), dtype=np.int64)
+    check(cldrd_lib.cldrd_index_read_ids(p, 993, 7, ptr(oi)))
+    assert np.array_equal(oi, ids[993:])
+    assert cldrd_lib.cldrd_index_read_rows(p, 995, 10, ptr(out)) != 0
+
+
+def test_bad_files_rejected(cldrd_lib, tmp_path):
+    import cldrd
+    p = tmp_path / "bad.index"
+    p.write_bytes(b"IwFl" + b"\0" * 100)
+    with pytest.raises(cldrd.CldrdError):
+        cldrd.read_index(str(p))
+    good = O.write_index_bytes(O.synth(4, 4, 0), O.synth_ids(4))
+    p.write_bytes(good[:-5])
+    with pytest.raises(cldrd.CldrdError):
+        cldrd.read_index(str(p))
+    l2 = bytearray(good)
+    l2[70:74] = (1).to_bytes(4, "little")  # inner metric = L2
+    p.write_bytes(bytes(l2))
+    with pytest.raises(cldrd.CldrdError):
+        cldrd.read_index(str(p))
+
+
+def test_dtype_and_shape_errors_like_faiss(cldrd_lib):
+    import cldrd
+    idx = cldrd.IndexIDMap(cldrd.IndexFlatIP(8))
+    with pytest.raises(TypeError):
+        idx.add_with_ids(np.zeros((2, 8), dtype=np.float64), np.arange(2, dtype=np.int64))
+    with pytest.raises(TypeError):
+        idx.add_with_ids(np.zeros((2, 8), dtype=np.float32), np.arange(2, dtype=np.int32))
+    with pytest.raises(AssertionError):
+        idx.add_with_ids(np.zeros((2, 7), dtype=np.float32), np.arange(2, dtype=np.int64))
+    with pytest.raises(AssertionError):
+        idx.add_with_ids(np.zeros((2, 8), dtype=np.float32), np.arange(3, dtype=np.int64))
+
+
+def test_run_writer_bytes_equal_reference_loop(cldrd_lib, tmp_path):
+    import cldrd
+    rng = np.random.default_rng(0)
+    n, k = 37, 50
+    D = (rng.standard_normal((n, k)) * np.array([1e-6, 1e-3, 1, 100, 1e7])[rng.integers(0, 5, (n, k))]).astype(np.float32)
+    D[0, :5] = [0.0, -0.0, 1e16, 9.999e15, 1e-4]
+    I = rng.integers(-1, 2 ** 40, (n, k), dtype=np.int64)
+    qids = rng.permutation(10 ** 6)[:n].astype(np.int64)
+    a, b = tmp_path / "a.tsv", tmp_path / "b.tsv"
+    avg_a = cldrd.write_run_file(str(a), qids, I, D)
+    avg_b = O.write_run(str(b), qids.tolist(), I, D)
+    assert a.read_bytes() == b.read_bytes()
+    assert avg_a == avg_b == k
+    # duplicate qids regroup exactly like the reference's dict
+    qd = qids.copy()
+    qd[5] = qd[1]
+    qd[9] = qd[1]
+    avg_a = cldrd.write_run_file(str(a), qd, I, D)
+    avg_b = O.write_run(str(b), qd.tolist(), I, D)
+    assert a.read_bytes() == b.read_bytes() and avg_a == avg_b
+    with open(os.path.join(GOLD, "run_golden.tsv"), "rb") as f:
+        gold = f.read()
+    Dr = np.array([[103.856, 71.5, 0.1, -2.25e-5], [1e16, 3.0, 1.5e-7, -0.0]], dtype=np.float32)
+    Ir = np.array([[5, 2 ** 33 + 5, 0, -1], [9, 8, 7, 6]], dtype=np.int64)
+    cldrd.write_run_file(str(a), [1048585, 2], Ir, Dr)
+    assert a.read_bytes() == gold
+
+
+def test_score_text_matches_python_repr(cldrd_lib):
+    import cldrd
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([
+        rng.standard_normal(2000).astype(np.float32) * 100,
+        (10.0 ** rng.uniform(-12, 20, 2000)).astype(np.float32),
+        np.array([0, -0.0, 1, 16777216, 1e16, 9.9999998e15, 1e-4, 9.9999e-5, 3.4028235e38, 1.4e-45], dtype=np.float32),
+    ])
+    for v in vals:
+        assert cldrd.format_score(v) == repr(float(v)), float(v)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+def test_reference_evaluator_consumes_our_run_file(cldrd_lib, tmp_path):
+    """evaluation/retrieval_evaluator.py:42-76 reads cols 0,1 in file order: feed it our writer's output."""
+    import importlib.util
+    import cldrd
+    spec = importlib.util.spec_from_file_location("ref_eval", os.path.join(REF, "evaluation", "retrieval_evaluator.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xb, xq, ids = O.synth(2000, 32, 0), O.synth(20, 32, 1), O.synth_ids(2000)
+    D, I = O.search(xb, ids, xq, 100)
+    qids = np.arange(100, 120, dtype=np.int64)
+    run = tmp_path / "runs" / "dev.run"
+    cldrd.write_run_file(str(run), qids, I, D)
+    qrels = tmp_path / "qrels.tsv"
+    with open(qrels, "w") as f:
+        for i, q in enumerate(qids):
+            f.write(f"{q}\t0\t{I[i, i % 7]}\t1\n")  # the relevant passage sits at rank (i%7)+1
+    ev = mod.RankingEvaluator(str(qrels))
+    m = ev.compute_metrics(str(run))
+    exp = np.mean([1.0 / (i % 7 + 1) for i in range(20)])
+    assert abs(m["MRR@10"] - exp) < 1e-9 and m["QueriesRanked"] == 20
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+def test_reference_retrieval_utils_imports_against_our_faiss(cldrd_lib):
+    """retriever/retrieval_utils.py does `import faiss`; with cl-drd_b200/compat on the path it
+    gets ours, and its own convert_index_to_gpu / index_retrieve can drive our objects."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import faiss, retriever.retrieval_utils as ru\n"
+        "assert faiss.__version__=='cldrd-b200'\n"
+        "assert callable(ru.index_retrieve) and callable(ru.convert_index_to_gpu)\n"
+        "idx=faiss.IndexIDMap(faiss.IndexFlatIP(8)); print('ok', idx.ntotal)\n"
+    ) % (os.path.join(root, "cl-drd_b200", "compat"), os.path.join(root, "cl-drd_b200"), REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REF, timeout=300)
+    assert r.returncode == 0 and "ok 0" in r.stdout, r.stderr[-2000:]

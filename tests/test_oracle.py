@@ -1,0 +1,117 @@
+"""CPU tests of the oracle against the committed golden vectors (oracle/flat_ip.py).
+PARITY UNPINNED upstream: see the oracle header."""
+import os
+import struct
+
+import numpy as np
+
+from oracle import flat_ip as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# hand-assembled IxMp{IxFI}: 2 vectors, d=4, ids (7, 2**33+5)  -- SURVEY §8 a-2 byte offsets
+TINY = (
+    b"IxMp" + struct.pack("<i", 4) + struct.pack("<q", 2) + struct.pack("<q", 1 << 20) * 2 + b"\x01" + struct.pack("<i", 0)
+    + b"IxFI" + struct.pack("<i", 4) + struct.pack("<q", 2) + struct.pack("<q", 1 << 20) * 2 + b"\x01" + struct.pack("<i", 0)
+    + struct.pack("<Q", 8) + struct.pack("<8f", 1.0, 2.0, 3.0, 4.0, -1.0, 0.5, 0.25, 8.0)
+    + struct.pack("<Q", 2) + struct.pack("<2q", 7, 2 ** 33 + 5)
+)
+
+
+def test_tiny_file_layout_offsets():
+    assert len(TINY) == 82 + 4 * 2 * 4 + 8 + 8 * 2
+    assert TINY[0:4] == b"IxMp" and TINY[37:41] == b"IxFI"
+    assert struct.unpack_from("<Q", TINY, 74)[0] == 8          # count = ntotal*d at byte 74
+    assert struct.unpack_from("<f", TINY, 82)[0] == 1.0        # payload starts at byte 82
+    with open(os.path.join(GOLD, "tiny_ixmp.index"), "rb") as f:
+        assert f.read() == TINY
+
+
+def test_tiny_file_reader_writer():
+    xb, ids, info = O.read_index_bytes(TINY)
+    assert info["d"] == 4 and info["ntotal"] == 2 and info["data_off"] == 82 and info["metric"] == 0
+    assert xb.tolist() == [[1.0, 2.0, 3.0, 4.0], [-1.0, 0.5, 0.25, 8.0]]
+    assert ids.tolist() == [7, 2 ** 33 + 5]
+    assert O.write_index_bytes(xb, ids) == TINY
+    assert O.write_index_bytes(xb, ids, idmap2=True)[:4] == b"IxM2"
+    bare = O.write_index_bytes(xb, None)
+    assert bare[:4] == b"IxFI" and len(bare) == 45 + 32
+    xb2, ids2, _ = O.read_index_bytes(bare)
+    assert ids2 is None and np.array_equal(xb2, xb)
+
+
+def test_msmarco_file_size_formula():
+    N, d = 8841823, 768
+    assert 82 + 4 * N * d + 8 + 8 * N == 27232814930
+
+
+def test_search_tiny_known_answer():
+    xb, ids, _ = O.read_index_bytes(TINY)
+    q = np.array([[1, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
+    D, I = O.search(xb, ids, q, 3)
+    assert D[0].tolist()[:2] == [1.0, -1.0] and I[0].tolist() == [7, 2 ** 33 + 5, -1]
+    assert D[1].tolist()[:2] == [8.0, 4.0] and I[1].tolist() == [2 ** 33 + 5, 7, -1]
+    assert D[0, 2] == O.NEG_FLT_MAX
+
+
+def test_seeded_golden_1000x64():
+    g = np.load(os.path.join(GOLD, "seeded_1000x64.npz"))
+    xb, xq, ids = O.synth(1000, 64, 0), O.synth(16, 64, 1), O.synth_ids(1000, 7)
+    for k in (10, 100):
+        D, I = O.search(xb, ids, xq, k)
+        assert np.array_equal(I, g[f"I{k}"])
+        np.testing.assert_allclose(D, g[f"D{k}"], rtol=1e-6)
+        # block-merged walk gives the same answer as the single-block walk
+        D2, R2 = O.search_rows(xb, xq, k, block=137)
+        assert np.array_equal(ids[R2], I)
+
+
+def test_ties_lower_row_first_and_padding():
+    xb = np.ones((5, 4), dtype=np.float32)
+    xb[3] = 2.0
+    q = np.ones((1, 4), dtype=np.float32)
+    D, R = O.search_rows(xb, q, 8)
+    assert R[0].tolist() == [3, 0, 1, 2, 4, -1, -1, -1]
+    assert D[0, 5] == O.NEG_FLT_MAX
+    D, R = O.search_rows(xb, q, 3, block=2)
+    assert R[0].tolist() == [3, 0, 1]
+
+
+def test_fp64_twin_agrees_with_fp32_within_tolerance():
+    xb, xq = O.synth(3000, 768, 3), O.synth(4, 768, 4)
+    D32, R32 = O.search_rows(xb, xq, 50)
+    D64, R64 = O.search_rows(xb, xq, 51, dtype=np.float64)
+    r = O.compare_topk(D32, R32, D64[:, :50].astype(np.float32), R64[:, :50], D64, R64)
+    assert r["ok"], r
+
+
+def test_compare_topk_flags_real_differences():
+    xb, xq = O.synth(500, 32, 5), O.synth(3, 32, 6)
+    D, R = O.search_rows(xb, xq, 20)
+    assert O.compare_topk(D, R, D, R)["ok"]
+    R2 = R.copy()
+    R2[0, 0], R2[0, 5] = R2[0, 5], R2[0, 0]
+    assert not O.compare_topk(D, R2, D, R)["ok"]
+    D2 = D.copy()
+    D2[1, 3] *= 1.001
+    assert not O.compare_topk(D2, R, D, R)["ok"]
+
+
+def test_index_retrieve_shapes():
+    xb, xq, ids = O.synth(300, 16, 0), O.synth(10, 16, 1), O.synth_ids(300)
+    D, I = O.index_retrieve(xb, ids, xq, 5)
+    assert isinstance(D, np.ndarray) and D.shape == (10, 5)
+    s, nn = O.index_retrieve(xb, ids, xq, 5, batch=4)
+    assert isinstance(s, list) and len(s) == 10 and len(nn[0]) == 5
+    assert nn == I.tolist()
+
+
+def test_run_writer_golden(tmp_path):
+    Dr = np.array([[103.856, 71.5, 0.1, -2.25e-5], [1e16, 3.0, 1.5e-7, -0.0]], dtype=np.float32)
+    Ir = np.array([[5, 2 ** 33 + 5, 0, -1], [9, 8, 7, 6]], dtype=np.int64)
+    p = tmp_path / "run.tsv"
+    avg = O.write_run(str(p), [1048585, 2], Ir, Dr)
+    assert avg == 4.0
+    with open(os.path.join(GOLD, "run_golden.tsv")) as f:
+        assert p.read_text() == f.read()
+    assert p.read_text().splitlines()[0] == "1048585\t5\t1\t103.85600280761719"
