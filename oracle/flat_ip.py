@@ -311,25 +311,35 @@ def compare_topk(D_test: np.ndarray, I_test: np.ndarray, D_ref: np.ndarray, I_re
         brk = np.nonzero(gaps > rel_tol * np.maximum(np.abs(dr64[:-1]), 1e-30))[0] + 1
         starts = np.concatenate([[0], brk])
         ends = np.concatenate([brk, [kk]])
-        allowed_extra: set = set()
+        # Boundary band: ids whose fp64 score is chained (adjacent gaps <= tol) to the fp64
+        # k-th score, on BOTH sides of the cut.  fp32 and fp64 may order such rows differently,
+        # so either choice among them is a correct top-k.
+        band: set = set()
         if D_ref_ext is not None and kk == k:
             de = D_ref_ext[i].astype(np.float64)
             ie = I_ref_ext[i]
+
+            def close(a, b):
+                return abs(a - b) <= rel_tol * max(abs(a), abs(b), 1e-30)
+
             j = k
-            while j < de.shape[0] and ie[j] >= 0 and abs(de[j] - de[j - 1]) <= rel_tol * max(abs(de[j - 1]), 1e-30):
-                allowed_extra.add(int(ie[j]))
+            while j < de.shape[0] and ie[j] >= 0 and close(de[j], de[j - 1]):
+                band.add(int(ie[j]))
                 j += 1
+            if j > k:
+                band.add(int(ie[k - 1]))
+                j = k - 1
+                while j > 0 and close(de[j], de[j - 1]):
+                    band.add(int(ie[j - 1]))
+                    j -= 1
         miss = 0
         for s, e in zip(starts, ends):
             ref_set = set(irv[s:e].tolist())
             tst_set = set(itv[s:e].tolist())
             if ref_set == tst_set:
                 continue
-            if e == kk and allowed_extra:
-                # boundary run: ids may be swapped with the excused spill-over ids
-                extra = tst_set - ref_set
-                if extra <= allowed_extra and len(tst_set) == len(ref_set):
-                    continue
+            if band and (ref_set ^ tst_set) <= band:
+                continue
             miss += len(ref_set - tst_set)
         bad_ids += miss
         overlap_sum += 1.0 - miss / kk

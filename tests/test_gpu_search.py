@@ -38,9 +38,7 @@ def _check(gpu, xb, ids, xq, k, margin=16):
     assert r["ok"], (gpu.scan, k, r, gpu.last_stats())
     assert r["overlap"] == 1.0
     # sortedness: descending scores within every row
-    valid = I >= 0
-    d = np.where(valid, D, -np.inf)
-    assert (np.diff(d, axis=1) <= 0).all()
+    assert (np.diff(D, axis=1) <= 0).all()   # padding is -FLT_MAX, so this covers it too
     return D, I
 
 
