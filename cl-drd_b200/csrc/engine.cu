@@ -30,7 +30,12 @@ namespace {
 
 constexpr int kQueryBatch = 8192;   // queries processed per pass over the index
 constexpr int kDensePiece = 8192;   // rows per dense piece (first chunk and fallback)
-constexpr int kSurvCap = 8192;      // survivor slots per query per chunk
+constexpr int kSurvCap = 8192;      // survivors one select CTA can take in per chunk (shared memory)
+constexpr size_t kSurvTotal = size_t(kQueryBatch) * kSurvCap;  // survivor-buffer entries (all queries)
+constexpr int kMaxQStride = 65536;  // survivor slice per query when the batch is small
+constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width)
+constexpr size_t kSegCntInts = 655360;  // >= nq * groups for every plan (128*(32*148+64) < 655360)
+constexpr int kUnitsPerCta = 32;    // work units per persistent CTA: load balance of the tail
 
 struct DeviceGuard {
     int prev = -1;
@@ -118,7 +123,7 @@ struct cldrd_shard {
     float* w_thr = nullptr;
     float* w_band = nullptr;
     int* w_list_len = nullptr;
-    int* w_surv_cnt = nullptr;
+    int* w_seg_cnt = nullptr;
     int* w_fail = nullptr;
     int* w_fail_index = nullptr;
     uint64_t* w_list = nullptr;
@@ -159,7 +164,7 @@ void free_workspace(cldrd_shard* s) {
     cudaFree(s->w_thr);
     cudaFree(s->w_band);
     cudaFree(s->w_list_len);
-    cudaFree(s->w_surv_cnt);
+    cudaFree(s->w_seg_cnt);
     cudaFree(s->w_fail);
     cudaFree(s->w_fail_index);
     cudaFree(s->w_list);
@@ -171,7 +176,7 @@ void free_workspace(cldrd_shard* s) {
     if (s->h_stats) cudaFreeHost(s->h_stats);
     if (s->h_fail) cudaFreeHost(s->h_fail);
     s->w_thr = s->w_band = nullptr;
-    s->w_list_len = s->w_surv_cnt = s->w_fail = s->w_fail_index = nullptr;
+    s->w_list_len = s->w_seg_cnt = s->w_fail = s->w_fail_index = nullptr;
     s->w_list = s->w_surv = nullptr;
     s->w_dense = nullptr;
     s->w_qlp = nullptr;
@@ -189,11 +194,11 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMalloc(&s->w_thr, Q * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_band, Q * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_list_len, Q * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->w_surv_cnt, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_seg_cnt, kSegCntInts * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
-    CU_TRY(cudaMalloc(&s->w_surv, Q * kSurvCap * sizeof(uint64_t)));
+    CU_TRY(cudaMalloc(&s->w_surv, kSurvTotal * sizeof(uint64_t)));
     CU_TRY(cudaMalloc(&s->w_dense, Q * kDensePiece * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_qfail, Q * size_t(s->d) * sizeof(float)));
     if (lp_kind_of(s->scan_eff)) CU_TRY(cudaMalloc(&s->w_qlp, Q * size_t(s->d) * 2));
@@ -233,7 +238,30 @@ struct BatchCtx {
     bool have_tmA = false;
     int64_t launches = 0;
     int64_t chunks = 0;
+    // survivor-buffer plan of the current chunk (scan writes it, select reads it)
+    int q_stride = 0, seg_cap = 0, groups = 1, run_len = 1;
 };
+
+// Work-unit plan for one chunk: `groups` runs of `run_len` row tiles per query tile, enough units
+// to balance the persistent CTAs; the query's survivor slice is cut into one segment per group.
+void plan_chunk(BatchCtx& c, int nrows) {
+    cldrd_shard* s = c.s;
+    const int nq_pad = ((c.nq + TC_BM - 1) / TC_BM) * TC_BM;
+    c.q_stride = int(std::min<size_t>(kSurvTotal / size_t(nq_pad), size_t(kMaxQStride)));
+    if (!is_tc(s->scan_eff)) {
+        c.groups = 1;
+        c.run_len = 1;
+        c.seg_cap = c.q_stride;
+        return;
+    }
+    const int num_m = nq_pad / TC_BM;
+    const int num_n = std::max(1, (nrows + TC_BN - 1) / TC_BN);
+    int g = (kUnitsPerCta * s->num_sms + num_m - 1) / num_m;
+    g = std::max(1, std::min(g, std::min(num_n, kMaxGroups)));
+    c.run_len = (num_n + g - 1) / g;
+    c.groups = (num_n + c.run_len - 1) / c.run_len;
+    c.seg_cap = std::max(1, c.q_stride / c.groups);
+}
 
 cudaEvent_t next_event(cldrd_shard* s) {
     if (s->ev_used == s->ev.size()) {
@@ -254,10 +282,14 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     p.nq = c.nq;
     p.row_begin = row_begin;
     p.nrows = nrows;
+    plan_chunk(c, nrows);
     p.thr = s->w_thr;
     p.surv = s->w_surv;
-    p.surv_cnt = s->w_surv_cnt;
-    p.surv_cap = kSurvCap;
+    p.seg_cnt = s->w_seg_cnt;
+    p.q_stride = c.q_stride;
+    p.seg_cap = c.seg_cap;
+    p.groups = c.groups;
+    p.run_len = c.run_len;
     p.dense = s->w_dense;
     p.dense_ld = kDensePiece;
     p.stats = s->w_stats;
@@ -265,8 +297,8 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
         const int esz = (s->scan_eff == CLDRD_SCAN_TC_TF32) ? 4 : 2;
         p.kb_elems = TC_KB_BYTES / esz;
         p.num_kb = (s->d * esz + TC_KB_BYTES - 1) / TC_KB_BYTES;
-        const long long tiles = (long long)((c.nq + TC_BM - 1) / TC_BM) * ((nrows + TC_BN - 1) / TC_BN);
-        const int grid = int(std::min<long long>(tiles, s->num_sms));
+        const long long units = (long long)((c.nq + TC_BM - 1) / TC_BM) * c.groups;
+        const int grid = int(std::min<long long>(units, s->num_sms));
         if (grid <= 0) {
             if (s->profile) cudaEventRecord(next_event(s), c.st);
             return CLDRD_OK;
@@ -313,7 +345,10 @@ int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     p.list_len = s->w_list_len;
     p.keep_cap = s->ws_keep_cap;
     p.surv = s->w_surv;
-    p.surv_cnt = s->w_surv_cnt;
+    p.seg_cnt = s->w_seg_cnt;
+    p.q_stride = c.q_stride;
+    p.seg_cap = c.seg_cap;
+    p.groups = c.groups;
     p.surv_cap = kSurvCap;
     p.dense = dense ? s->w_dense : nullptr;
     p.dense_ld = kDensePiece;
@@ -347,9 +382,9 @@ int launch_prep(BatchCtx& c) {
     p.band = s->w_band;
     p.thr = s->w_thr;
     p.list_len = s->w_list_len;
-    p.surv_cnt = s->w_surv_cnt;
     p.fail = s->w_fail;
     p.stats = s->w_stats;
+    CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, kSegCntInts * sizeof(int), c.st));
     const int threads = 256;
     const int blocks = (c.nq * 32 + threads - 1) / threads;
     query_prep_kernel<<<blocks, threads, 0, c.st>>>(p);

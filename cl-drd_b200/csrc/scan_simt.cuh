@@ -14,11 +14,16 @@ struct ScanParams {
     int nq;
     int64_t row_begin;    // first local row of the chunk
     int nrows;            // rows in the chunk
-    // fused filter
+    // fused filter.  Survivors of query q land in its private slice surv[q*q_stride ..), which
+    // is cut into `groups` segments of seg_cap entries; seg_cnt[q*groups + g] counts segment g
+    // (the count keeps running past seg_cap so that overflow is detectable).
     const float* thr;     // [nq]
-    uint64_t* surv;       // [nq][surv_cap]
-    int* surv_cnt;        // [nq]
-    int surv_cap;
+    uint64_t* surv;       // [nq][q_stride]
+    int* seg_cnt;         // [nq][groups]
+    int q_stride;
+    int seg_cap;
+    int groups;           // SIMT scan: 1 (atomic append).  TC scan: one segment per work unit group
+    int run_len;          // TC scan: consecutive row tiles per work unit
     // dense dump
     float* dense;         // [nq][dense_ld]
     int dense_ld;
@@ -132,9 +137,9 @@ __global__ void __launch_bounds__(256) scan_simt_kernel(ScanParams p) {
             if (DENSE) {
                 p.dense[size_t(qi) * p.dense_ld + col] = v;
             } else if (v >= t) {
-                const int slot = atomicAdd(&p.surv_cnt[qi], 1);
-                if (slot < p.surv_cap)
-                    p.surv[size_t(qi) * p.surv_cap + slot] = make_key(v, uint32_t(p.row_begin + col));
+                const int slot = atomicAdd(&p.seg_cnt[qi], 1);
+                if (slot < p.seg_cap)
+                    p.surv[size_t(qi) * p.q_stride + slot] = make_key(v, uint32_t(p.row_begin + col));
             }
         }
     }

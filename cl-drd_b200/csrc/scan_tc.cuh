@@ -6,10 +6,14 @@
 //   accumulators  2 x 256 fp32 columns = all 512 TMEM columns: the epilogue of tile i overlaps
 //                 the MMAs of tile i+1
 //   warps         0: TMA producer   1: MMA issuer + TMEM owner   2..5: epilogue (one per TMEM
-//                 lane quadrant; thread = one query, its threshold lives in a register)
-//   schedule      persistent CTAs; tile t -> (query tile t % num_m, row tile t / num_m) so the
-//                 CTAs in flight share a handful of row tiles through L2 while HBM sees each
-//                 index row once per pass
+//                 lane quadrant; thread = one query: its threshold, its survivor count and its
+//                 output cursor live in registers)
+//   work units    unit u = (query tile m = u % num_m, group g = u / num_m) covers `run_len`
+//                 consecutive row tiles for ONE query tile.  Persistent CTAs take units round
+//                 robin, so the CTAs in flight hold every query tile for ~3 groups: each index
+//                 row tile is pulled from HBM once and then served to the other query tiles
+//                 from L2, and a thread appends survivors to a slice nobody else writes
+//                 (no atomics, no shared counters).
 #pragma once
 #include "device_common.cuh"
 #include "scan_simt.cuh"  // ScanParams
@@ -57,7 +61,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int num_m = (p.nq + TC_BM - 1) / TC_BM;
     const int num_n = (p.nrows + TC_BN - 1) / TC_BN;
-    const long long num_tiles = (long long)num_m * num_n;
+    const int num_units = num_m * p.groups;   // groups * run_len >= num_n (host guarantees)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -85,24 +89,27 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m = int(t % num_m), n = int(t / num_m);
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int m = u % num_m, g = u / num_m;
+            const int n_end = min(num_n, (g + 1) * p.run_len);
             const int crd_q = m * TC_BM;
-            const int crd_r = int(p.row_begin) + n * TC_BN;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                    // queries are re-read by every row tile: keep them in L2; index rows stream
-                    tma_load_2d(smemA + size_t(stage) * TC_A_STAGE, &tmA, &full_bar[stage],
-                                kb * p.kb_elems, crd_q, kEvictLast);
-                    tma_load_2d(smemB + size_t(stage) * TC_B_STAGE, &tmB, &full_bar[stage],
-                                kb * p.kb_elems, crd_r, kEvictNormal);
-                }
-                __syncwarp();
-                if (++stage == TC_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+            for (int n = g * p.run_len; n < n_end; ++n) {
+                const int crd_r = int(p.row_begin) + n * TC_BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                        // queries are re-read by every row tile: keep them in L2; index rows stream
+                        tma_load_2d(smemA + size_t(stage) * TC_A_STAGE, &tmA, &full_bar[stage],
+                                    kb * p.kb_elems, crd_q, kEvictLast);
+                        tma_load_2d(smemB + size_t(stage) * TC_B_STAGE, &tmB, &full_bar[stage],
+                                    kb * p.kb_elems, crd_r, kEvictNormal);
+                    }
+                    __syncwarp();
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -111,127 +118,107 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t idesc = tc_idesc(KIND);
         int stage = 0;
         uint32_t phase = 0;
-        long long it = 0;
-        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-            const int as = int(it & 1);
-            const uint32_t aphase = uint32_t((it >> 1) & 1);
-            mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + uint32_t(as * TC_BN);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase, err, 300 + stage);
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int g = u / num_m;
+            const int n_end = min(num_n, (g + 1) * p.run_len);
+            for (int n = g * p.run_len; n < n_end; ++n, ++it) {
+                const uint32_t as = it & 1u;
+                const uint32_t aphase = (it >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t a_desc = umma_desc_sw128(smem_u32(smemA + size_t(stage) * TC_A_STAGE));
-                    const uint64_t b_desc = umma_desc_sw128(smem_u32(smemB + size_t(stage) * TC_B_STAGE));
+                const uint32_t d_tmem = tmem_base + as * uint32_t(TC_BN);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, err, 300 + stage);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t a_desc = umma_desc_sw128(smem_u32(smemA + size_t(stage) * TC_A_STAGE));
+                        const uint64_t b_desc = umma_desc_sw128(smem_u32(smemB + size_t(stage) * TC_B_STAGE));
 #pragma unroll
-                    for (int kk = 0; kk < TC_KB_BYTES / 32; ++kk) {
-                        // one MMA consumes 32 bytes of K: +2 in the 16-byte start-address field
-                        tc_mma_ss<KIND == 2>(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2),
-                                             idesc, uint32_t((kb | kk) != 0));
+                        for (int kk = 0; kk < TC_KB_BYTES / 32; ++kk) {
+                            // one MMA consumes 32 bytes of K: +2 in the 16-byte start-address field
+                            tc_mma_ss<KIND == 2>(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2),
+                                                 idesc, uint32_t((kb | kk) != 0));
+                        }
+                        tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                        if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);  // accumulator complete
                     }
-                    tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
-                    if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);  // accumulator complete
-                }
-                __syncwarp();
-                if (++stage == TC_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                    __syncwarp();
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> filter =====================
         const int qd = warp & 3;  // the TMEM lane quadrant this warp may read
-        long long it = 0;
-        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-            const int m = int(t % num_m), n = int(t / num_m);
-            const int as = int(it & 1);
-            const uint32_t aphase = uint32_t((it >> 1) & 1);
+        uint32_t it = 0;
+        unsigned long long tiles_done = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int m = u % num_m, g = u / num_m;
+            const int n_end = min(num_n, (g + 1) * p.run_len);
             const int qrow = m * TC_BM + qd * 32 + lane;
             const bool qvalid = qrow < p.nq;
-            const int valid_n = min(TC_BN, p.nrows - n * TC_BN);
-            const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + uint32_t(as * TC_BN);
             float thr = INFINITY;
             if (!DENSE && qvalid) thr = p.thr[qrow];
-            mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
-            tc_fence_after();
-            float v[32];
-            if (DENSE) {
+            uint64_t* dst = DENSE ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(g) * p.seg_cap;
+            int cnt = 0;
+            for (int n = g * p.run_len; n < n_end; ++n, ++it) {
+                const uint32_t as = it & 1u;
+                const uint32_t aphase = (it >> 1) & 1u;
+                const int valid_n = min(TC_BN, p.nrows - n * TC_BN);
+                const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + as * uint32_t(TC_BN);
+                mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
+                tc_fence_after();
+                float v[32];
+                if (DENSE) {
 #pragma unroll 1
-                for (int b = 0; b < TC_BN / 32; ++b) {
-                    tmem_ld32(taddr + uint32_t(b * 32), v);
-                    if (qvalid) {
-                        float* dst = p.dense + size_t(qrow) * p.dense_ld + size_t(n) * TC_BN + b * 32;
-                        if (b * 32 + 32 <= valid_n && (p.dense_ld & 3) == 0) {
+                    for (int b = 0; b < TC_BN / 32; ++b) {
+                        tmem_ld32(taddr + uint32_t(b * 32), v);
+                        if (qvalid) {
+                            float* o = p.dense + size_t(qrow) * p.dense_ld + size_t(n) * TC_BN + b * 32;
+                            if (b * 32 + 32 <= valid_n && (p.dense_ld & 3) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (b * 32 + j < valid_n) dst[j] = v[j];
+                                for (int j = 0; j < 32; ++j)
+                                    if (b * 32 + j < valid_n) o[j] = v[j];
+                            }
                         }
                     }
-                }
-            } else {
-                // pass 1: which 32-column groups hold anything >= thr for this query?
-                uint32_t flags = 0;
-#pragma unroll
-                for (int b = 0; b < TC_BN / 32; ++b) {
-                    tmem_ld32(taddr + uint32_t(b * 32), v);
-                    float mx = v[0];
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                    flags |= (mx >= thr) ? (1u << b) : 0u;
-                }
-                const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
-                if (wflags) {
-                    // pass 2 (rare): exact survivor masks, one slot reservation per query per tile
-                    uint32_t masks[TC_BN / 32];
-                    int cnt = 0;
-#pragma unroll
+                } else {
+                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * TC_BN;
+#pragma unroll 1
                     for (int b = 0; b < TC_BN / 32; ++b) {
-                        masks[b] = 0;
-                        if ((wflags >> b) & 1u) {
-                            tmem_ld32(taddr + uint32_t(b * 32), v);
-                            uint32_t mk = 0;
+                        tmem_ld32(taddr + uint32_t(b * 32), v);
+                        float mx = v[0];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                mk |= (v[j] >= thr && (b * 32 + j) < valid_n) ? (1u << j) : 0u;
-                            masks[b] = mk;
-                            cnt += __popc(mk);
-                        }
-                    }
-                    int base = 0;
-                    if (cnt) base = atomicAdd(&p.surv_cnt[qrow], cnt);
-                    uint64_t* dst = p.surv + size_t(qvalid ? qrow : 0) * p.surv_cap;
-                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n * TC_BN);
-#pragma unroll
-                    for (int b = 0; b < TC_BN / 32; ++b) {
-                        if (__any_sync(0xffffffffu, masks[b] != 0)) {
-                            tmem_ld32(taddr + uint32_t(b * 32), v);
-                            const uint32_t mk = masks[b];
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                        if (__any_sync(0xffffffffu, mx >= thr)) {
+                            // rare: append this thread's survivors to its private segment
+                            const int lim = valid_n - b * 32;  // >= 32 except on the chunk's last tile
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                if ((mk >> j) & 1u) {
-                                    if (base < p.surv_cap) dst[base] = make_key(v[j], row0 + uint32_t(b * 32 + j));
-                                    ++base;
-                                }
+                                const bool hit = (v[j] >= thr) && (j < lim);
+                                if (hit && cnt < p.seg_cap) dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
+                                cnt += hit ? 1 : 0;
                             }
                         }
                     }
                 }
+                // accumulator stage drained: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                ++tiles_done;
             }
-            // accumulator stage drained: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (!DENSE && qvalid) p.seg_cnt[size_t(qrow) * p.groups + g] = cnt;
         }
-        if (warp == 2 && lane == 0 && p.stats && blockIdx.x < num_tiles) {
-            long long mine = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-            atomicAdd(&p.stats[ST_TILES], (unsigned long long)mine);
-        }
+        if (warp == 2 && lane == 0 && p.stats) atomicAdd(&p.stats[ST_TILES], tiles_done);
     }
 
     tc_fence_before();

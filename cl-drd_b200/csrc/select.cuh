@@ -58,9 +58,12 @@ struct SelectParams {
     uint64_t* list;        // [nq][keep_cap]
     int* list_len;         // [nq]
     int keep_cap;
-    uint64_t* surv;        // [nq][surv_cap]   (filter mode)
-    int* surv_cnt;         // [nq]
-    int surv_cap;
+    uint64_t* surv;        // [nq][q_stride]   (filter mode): `groups` segments of seg_cap entries
+    int* seg_cnt;          // [nq][groups]     entries written per segment (may exceed seg_cap)
+    int q_stride;
+    int seg_cap;
+    int groups;            // <= 512
+    int surv_cap;          // survivors one CTA can take in (shared-memory space)
     const float* dense;    // [nq][dense_ld]   (dense mode, else nullptr)
     int dense_ld;
     int dense_n;           // valid columns
@@ -85,13 +88,12 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
     __shared__ uint32_t hist[256];
     __shared__ uint64_t bcast[2];
     __shared__ int s_n, s_out;
+    __shared__ int s_warp[32];
+    __shared__ int s_off[512];
 
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    if (p.fail[q]) {
-        if (tid == 0 && p.surv_cnt) p.surv_cnt[q] = 0;
-        return;
-    }
+    if (p.fail[q]) return;
     const int L = p.list_len[q];
     uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
     for (int i = tid; i < L; i += blockDim.x) keys[i] = my_list[i];
@@ -114,22 +116,54 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
         __syncthreads();
         n = s_n;
     } else {
-        const int S = p.surv_cnt[q];
-        if (S > p.surv_cap) {  // survivors were dropped: this query goes to the dense fallback
+        // gather this query's survivor segments: exclusive scan of the segment counts
+        const int G = p.groups;
+        int c = 0;
+        if (tid < G) {
+            c = p.seg_cnt[size_t(q) * G + tid];
+            p.seg_cnt[size_t(q) * G + tid] = 0;   // ready for the next chunk (SIMT scan appends atomically)
+        }
+        const bool over = c > p.seg_cap;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += t;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        const int any_over = __syncthreads_or(over ? 1 : 0);
+        if (tid < 32) {
+            int w = (tid < int(blockDim.x >> 5)) ? s_warp[tid] : 0;
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (tid >= o) wi += t;
+            }
+            s_warp[tid] = wi - w;                 // exclusive warp offsets
+            if (tid == 31) s_n = wi;              // total survivors
+        }
+        __syncthreads();
+        const int S = s_n;
+        if (any_over || S > p.surv_cap) {  // survivors were dropped: this query goes to the dense fallback
             if (tid == 0) {
                 p.fail[q] = 1;
-                p.surv_cnt[q] = 0;
                 atomicAdd(&p.stats[ST_FAILED], 1ull);
             }
             return;
         }
-        const uint64_t* sv = p.surv + size_t(q) * p.surv_cap;
-        for (int i = tid; i < S; i += blockDim.x) keys[L + i] = sv[i];
+        if (tid < G) s_off[tid] = s_warp[tid >> 5] + incl - c;
         __syncthreads();
-        if (tid == 0) {
-            p.surv_cnt[q] = 0;
-            atomicAdd(&p.stats[ST_SURVIVORS], (unsigned long long)S);
+        const uint64_t* sv = p.surv + size_t(q) * p.q_stride;
+        const int warp_id = tid >> 5, lane_id = tid & 31, nw = blockDim.x >> 5;
+        for (int g = warp_id; g < G; g += nw) {
+            const int off = s_off[g];
+            const int cg = ((g + 1 < G) ? s_off[g + 1] : S) - off;
+            const uint64_t* src = sv + size_t(g) * p.seg_cap;
+            for (int i = lane_id; i < cg; i += 32) keys[L + off + i] = src[i];
         }
+        __syncthreads();
+        if (tid == 0) atomicAdd(&p.stats[ST_SURVIVORS], (unsigned long long)S);
         n = L + S;
     }
     if (n == L) return;  // nothing new: list and threshold stay as they are
@@ -336,7 +370,6 @@ struct QueryPrepParams {
     float* band;       // 2*eps (slightly inflated)
     float* thr;
     int* list_len;
-    int* surv_cnt;
     int* fail;
     unsigned long long* stats;
 };
@@ -367,7 +400,6 @@ __global__ void query_prep_kernel(QueryPrepParams p) {
         p.band[warp] = 2.0f * eps * 1.0001f;
         p.thr[warp] = -INFINITY;
         p.list_len[warp] = 0;
-        p.surv_cnt[warp] = 0;
         p.fail[warp] = 0;
         if (p.lp_kind == 1 && !(mx < 65504.f)) atomicAdd(&p.stats[ST_RANGE_ERR], 1ull);
     }
