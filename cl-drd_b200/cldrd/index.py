@@ -345,6 +345,13 @@ class _Shard:
         check(lib().cldrd_shard_last_scan_time(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def scan_launches(self):
+        """[(rows, ms)] of every scan launch of the last search (profiling on)."""
+        ms = (C.c_double * 256)()
+        rows = (C.c_int64 * 256)()
+        n = lib().cldrd_shard_last_scan_launches(self.handle, ms, rows, 256)
+        return [(int(rows[j]), float(ms[j])) for j in range(max(n, 0))]
+
     @property
     def scan(self) -> str:
         code = lib().cldrd_shard_scan(self.handle)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
@@ -31,11 +32,12 @@ namespace {
 constexpr int kQueryBatch = 8192;   // queries processed per pass over the index
 constexpr int kDensePiece = 8192;   // rows per dense piece (first chunk and fallback)
 constexpr int kSurvCap = 8192;      // survivors one select CTA can take in per chunk (shared memory)
-constexpr size_t kSurvTotal = size_t(kQueryBatch) * kSurvCap;  // survivor-buffer entries (all queries)
+constexpr size_t kSurvTotal = size_t(kQueryBatch) * 16384;  // survivor-buffer entries (all queries), 1 GiB
 constexpr int kMaxQStride = 65536;  // survivor slice per query when the batch is small
-constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width)
-constexpr size_t kSegCntInts = 655360;  // >= nq * groups for every plan (128*(32*148+64) < 655360)
-constexpr int kUnitsPerCta = 32;    // work units per persistent CTA: load balance of the tail
+constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width) >= #SMs
+constexpr size_t kSegCntInts = size_t(kQueryBatch) * kMaxGroups;
+constexpr int kMaxRunLen = 16;      // row tiles per work unit: short runs keep the CTAs in flight
+                                    // inside a window of index rows that stays hot in L2
 
 struct DeviceGuard {
     int prev = -1;
@@ -156,6 +158,12 @@ struct cldrd_shard {
     size_t ev_used = 0;
     double scan_ms = 0.0;
     int64_t scan_launches = 0;
+    std::vector<int64_t> ev_rows;      // rows of each timed scan launch
+    std::vector<float> ev_ms;          // its device time
+
+    // tuning overrides (environment: CLDRD_RUN_LEN, CLDRD_GROWTH), 0 = automatic
+    int tune_run_len = 0;
+    double tune_growth = 0.0;
 };
 
 namespace {
@@ -239,11 +247,12 @@ struct BatchCtx {
     int64_t launches = 0;
     int64_t chunks = 0;
     // survivor-buffer plan of the current chunk (scan writes it, select reads it)
-    int q_stride = 0, seg_cap = 0, groups = 1, run_len = 1;
+    int q_stride = 0, seg_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
 };
 
-// Work-unit plan for one chunk: `groups` runs of `run_len` row tiles per query tile, enough units
-// to balance the persistent CTAs; the query's survivor slice is cut into one segment per group.
+// Work-unit plan for one chunk.  The grid is one persistent CTA per SM (fewer when there is less
+// work); a unit is `run_len` consecutive row tiles of one query tile; the query's survivor slice
+// is cut into one segment per CTA.
 void plan_chunk(BatchCtx& c, int nrows) {
     cldrd_shard* s = c.s;
     const int nq_pad = ((c.nq + TC_BM - 1) / TC_BM) * TC_BM;
@@ -252,14 +261,20 @@ void plan_chunk(BatchCtx& c, int nrows) {
         c.groups = 1;
         c.run_len = 1;
         c.seg_cap = c.q_stride;
+        c.grid = 0;
+        c.seg_by_group = 0;
         return;
     }
     const int num_m = nq_pad / TC_BM;
     const int num_n = std::max(1, (nrows + TC_BN - 1) / TC_BN);
-    int g = (kUnitsPerCta * s->num_sms + num_m - 1) / num_m;
-    g = std::max(1, std::min(g, std::min(num_n, kMaxGroups)));
-    c.run_len = (num_n + g - 1) / g;
-    c.groups = (num_n + c.run_len - 1) / c.run_len;
+    const long long tiles = (long long)num_m * num_n;
+    c.grid = int(std::min<long long>(tiles, std::min(s->num_sms, kMaxGroups)));
+    const long long per_cta = tiles / c.grid;
+    c.run_len = int(std::max<long long>(1, std::min<long long>(kMaxRunLen, per_cta / 16)));
+    if (s->tune_run_len > 0 && per_cta >= 16 * kMaxRunLen) c.run_len = s->tune_run_len;
+    const int num_groups = (num_n + c.run_len - 1) / c.run_len;
+    c.seg_by_group = num_groups <= c.grid ? 1 : 0;
+    c.groups = c.seg_by_group ? num_groups : c.grid;   // survivor segments per query
     c.seg_cap = std::max(1, c.q_stride / c.groups);
 }
 
@@ -274,7 +289,10 @@ cudaEvent_t next_event(cldrd_shard* s) {
 
 int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     cldrd_shard* s = c.s;
-    if (s->profile) cudaEventRecord(next_event(s), c.st);
+    if (s->profile) {
+        cudaEventRecord(next_event(s), c.st);
+        s->ev_rows.push_back(nrows);
+    }
     ScanParams p{};
     p.xb = s->xb;
     p.q = c.q;
@@ -290,6 +308,7 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     p.seg_cap = c.seg_cap;
     p.groups = c.groups;
     p.run_len = c.run_len;
+    p.seg_by_group = c.seg_by_group;
     p.dense = s->w_dense;
     p.dense_ld = kDensePiece;
     p.stats = s->w_stats;
@@ -297,8 +316,7 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
         const int esz = (s->scan_eff == CLDRD_SCAN_TC_TF32) ? 4 : 2;
         p.kb_elems = TC_KB_BYTES / esz;
         p.num_kb = (s->d * esz + TC_KB_BYTES - 1) / TC_KB_BYTES;
-        const long long units = (long long)((c.nq + TC_BM - 1) / TC_BM) * c.groups;
-        const int grid = int(std::min<long long>(units, s->num_sms));
+        const int grid = c.grid;
         if (grid <= 0) {
             if (s->profile) cudaEventRecord(next_event(s), c.st);
             return CLDRD_OK;
@@ -461,10 +479,13 @@ int run_pass(BatchCtx& c, bool dense_only) {
     }
     // Size the growing chunks from the candidate-list length after the first piece: a chunk of
     // m rows after `done` rows is expected to push about len * m / done survivors per query;
-    // keep that at a quarter of the survivor buffer.
+    // keep that at half of what a select CTA can take in (the counts are sums of many
+    // near-independent hits, so the spread around the mean is small; order-correlated data
+    // that breaks this goes to the dense fallback).
     if ((rc = read_stats(s, c.st))) return rc;
     const double k_eff = std::max<double>(c.k, double(s->h_stats[ST_MAX_LIST])) * 1.1;
-    const double growth = double(kSurvCap) / (4.0 * k_eff);
+    double growth = double(kSurvCap) / (2.0 * k_eff);
+    if (s->tune_growth > 0.0) growth = s->tune_growth;
     while (done < N) {
         int64_t m = int64_t(double(done) * growth);
         m = std::max<int64_t>(m, TC_BN);
@@ -548,6 +569,8 @@ int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrow
     s->d = d;
     s->scan = scan;
     s->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("CLDRD_RUN_LEN")) s->tune_run_len = atoi(e);
+    if (const char* e = getenv("CLDRD_GROWTH")) s->tune_growth = atof(e);
     *out = s;
     return CLDRD_OK;
 }
@@ -752,6 +775,8 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, 
     s->ev_used = 0;
     s->scan_ms = 0.0;
     s->scan_launches = 0;
+    s->ev_rows.clear();
+    s->ev_ms.clear();
     for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
         const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
         CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
@@ -768,6 +793,7 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, 
         for (size_t i = 0; i + 1 < s->ev_used; i += 2) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->scan_ms += ms;
+            s->ev_ms.push_back(ms);
             s->scan_launches++;
         }
     }
@@ -866,6 +892,16 @@ int cldrd_shard_last_scan_time(const cldrd_shard* s, double* scan_ms, int64_t* s
     if (scan_ms) *scan_ms = s->scan_ms;
     if (scan_launches) *scan_launches = s->scan_launches;
     return CLDRD_OK;
+}
+
+int cldrd_shard_last_scan_launches(const cldrd_shard* s, double* ms, int64_t* rows, int32_t cap) {
+    if (!s || !ms || !rows) return fail(CLDRD_EINVAL, "last_scan_launches: NULL");
+    const int n = int(std::min<size_t>(std::min(s->ev_ms.size(), s->ev_rows.size()), size_t(std::max(cap, 0))));
+    for (int i = 0; i < n; ++i) {
+        ms[i] = s->ev_ms[i];
+        rows[i] = s->ev_rows[i];
+    }
+    return n;
 }
 
 int cldrd_shard_last_stats(const cldrd_shard* s, int64_t stats[8]) {

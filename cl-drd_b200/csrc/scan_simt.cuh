@@ -22,7 +22,8 @@ struct ScanParams {
     int* seg_cnt;         // [nq][groups]
     int q_stride;
     int seg_cap;
-    int groups;           // SIMT scan: 1 (atomic append).  TC scan: one segment per work unit group
+    int groups;           // segments per query: SIMT scan 1 (atomic append), TC scan min(#groups, #CTAs)
+    int seg_by_group;     // TC scan: segment index = group (1) or CTA (0)
     int run_len;          // TC scan: consecutive row tiles per work unit
     // dense dump
     float* dense;         // [nq][dense_ld]

@@ -10,10 +10,14 @@
 //                 output cursor live in registers)
 //   work units    unit u = (query tile m = u % num_m, group g = u / num_m) covers `run_len`
 //                 consecutive row tiles for ONE query tile.  Persistent CTAs take units round
-//                 robin, so the CTAs in flight hold every query tile for ~3 groups: each index
-//                 row tile is pulled from HBM once and then served to the other query tiles
-//                 from L2, and a thread appends survivors to a slice nobody else writes
-//                 (no atomics, no shared counters).
+//                 robin, so the CTAs in flight hold every query tile for ~3 short groups: each
+//                 index row tile is pulled from HBM once and served to the other query tiles
+//                 from L2 while it is still hot.
+//   survivors     query q owns a slice of the survivor buffer cut into min(#groups, #CTAs)
+//                 segments: one per group while groups are few, one per CTA otherwise.  A
+//                 segment is written by exactly one thread at a time; its cursor is carried in
+//                 a register across a unit and parked in seg_cnt between units (no atomics, no
+//                 shared counters), and the survivors spread evenly over the segments.
 #pragma once
 #include "device_common.cuh"
 #include "scan_simt.cuh"  // ScanParams
@@ -61,7 +65,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int num_m = (p.nq + TC_BM - 1) / TC_BM;
     const int num_n = (p.nrows + TC_BN - 1) / TC_BN;
-    const int num_units = num_m * p.groups;   // groups * run_len >= num_n (host guarantees)
+    const int num_groups = (num_n + p.run_len - 1) / p.run_len;
+    const int num_units = num_m * num_groups;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -163,8 +168,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool qvalid = qrow < p.nq;
             float thr = INFINITY;
             if (!DENSE && qvalid) thr = p.thr[qrow];
-            uint64_t* dst = DENSE ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(g) * p.seg_cap;
+            // this thread's private segment: (query, group) while there are fewer groups than
+            // CTAs -- every unit then owns a fresh segment -- else (query, this CTA)
+            const int seg = p.seg_by_group ? g : int(blockIdx.x);
+            uint64_t* dst = DENSE ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(seg) * p.seg_cap;
+            int* cnt_slot = DENSE ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * p.groups + seg;
             int cnt = 0;
+            if (!DENSE && qvalid) cnt = *cnt_slot;
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {
                 const uint32_t as = it & 1u;
                 const uint32_t aphase = (it >> 1) & 1u;
@@ -216,7 +226,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 ++tiles_done;
             }
-            if (!DENSE && qvalid) p.seg_cnt[size_t(qrow) * p.groups + g] = cnt;
+            if (!DENSE && qvalid) *cnt_slot = cnt;
         }
         if (warp == 2 && lane == 0 && p.stats) atomicAdd(&p.stats[ST_TILES], tiles_done);
     }

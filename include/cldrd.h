@@ -155,6 +155,9 @@ int cldrd_shard_last_stats(const cldrd_shard* s, int64_t stats[8]);
  * device time of the scan kernels of that search and how many launches it covers. */
 int cldrd_shard_set_profiling(cldrd_shard* s, int32_t on);
 int cldrd_shard_last_scan_time(const cldrd_shard* s, double* scan_ms, int64_t* scan_launches);
+/* Per-launch detail of the same: fills ms[i] / rows[i] (index rows scanned by launch i) for up to
+ * `cap` launches and returns how many were written. */
+int cldrd_shard_last_scan_launches(const cldrd_shard* s, double* ms, int64_t* rows, int32_t cap);
 
 /* Debug / test hook: run only the scan kernel in dense mode and return the raw scan scores
  * (approximate for the tensor-core modes) of queries [0,nq) against local rows
