@@ -11,6 +11,7 @@ SCAN_SIMT_F32, SCAN_TC_TF32, SCAN_TC_F16, SCAN_TC_BF16 = 0, 1, 2, 3
 SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "fp16": SCAN_TC_F16,
               "bf16": SCAN_TC_BF16}
 MAX_K = 2048
+SEED_J = 24
 
 E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
 
@@ -50,6 +51,12 @@ SIGNATURES = {
     "cldrd_shard_scan": (C.c_int32, [C.c_void_p]),
     "cldrd_shard_scan_bytes": (C.c_int64, [C.c_void_p]),
     "cldrd_search_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_sample_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cldrd_seed_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cldrd_search_dev_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_verify_seed": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_shard_norm_bound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cldrd_shard_set_norm_bound": (C.c_int, [C.c_void_p, C.c_float]),
     "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),

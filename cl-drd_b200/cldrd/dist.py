@@ -105,14 +105,71 @@ class ShardedSearcher:
             id_map = torch.from_numpy(ids).to(f"cuda:{device}")
         return cls(sh, n.value, d.value, id_map, group)
 
+    SEED_MIN_ROWS = 1 << 20   # below this the per-shard progressive scheme is already cheap
+
+    def _sync_norm_bound(self):
+        """Shards of one index must use the same row-norm bound in their error band."""
+        if self.world == 1 or getattr(self, "_norm_synced", False):
+            return
+        b = C.c_float()
+        check(lib().cldrd_shard_norm_bound(self.shard.handle, C.byref(b)))
+        t = torch.tensor([b.value], dtype=torch.float32, device=f"cuda:{self.shard.device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        check(lib().cldrd_shard_set_norm_bound(self.shard.handle, C.c_float(float(t.item()))))
+        self._norm_synced = True
+
+    def _seed(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        """Steps 1+2: sample every shard, all-gather the per-shard sample scores (NCCL), take the
+        global SEED_J-th best as the scan-score threshold of each query."""
+        n = q.shape[0]
+        topj = self.local.sample_device(q, k)
+        allj = torch.empty((self.world,) + tuple(topj.shape), dtype=topj.dtype, device=topj.device)
+        dist.all_gather_into_tensor(allj, topj, group=self.group)
+        seed = torch.empty((n,), dtype=torch.float32, device=q.device)
+        st = torch.cuda.current_stream(q.device).cuda_stream
+        check(lib().cldrd_seed_from_samples(q.device.index, C.c_void_p(allj.data_ptr()), self.world, n,
+                                            C.c_void_p(seed.data_ptr()), C.c_void_p(st)))
+        return seed
+
     def search(self, q: torch.Tensor, k: int):
         """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
-        D, I = self.local.search_device(q, k, translate_ids=False)
         if self.world == 1:
+            D, I = self.local.search_device(q, k, translate_ids=False)
             if self.id_map is not None:
                 return merge_candidates(D.unsqueeze(0), I.unsqueeze(0), self.id_map)
             return D, I
+        self._sync_norm_bound()
+        n = q.shape[0]
+        seeded = self.ntotal >= self.SEED_MIN_ROWS and n > 0
+        seed = self._seed(q, k) if seeded else None
+        D, I, eps2 = self.local.search_device_seeded(q, k, seed)
         allD, allI = gather_candidates(D, I, dst=0, group=self.group)
+        outD = outI = None
+        nfail = torch.zeros((1,), dtype=torch.int64, device=q.device)
+        fail = torch.zeros((max(n, 1),), dtype=torch.int32, device=q.device)
+        if self.rank == 0:
+            # rows, not ids, are merged so that a retry can patch the same arrays; ids come last
+            outD, outI = merge_candidates(allD, allI, None)
+            if seeded:
+                st = torch.cuda.current_stream(q.device).cuda_stream
+                check(lib().cldrd_verify_seed(q.device.index, C.c_void_p(outD.data_ptr()), n, k,
+                                              C.c_void_p(seed.data_ptr()), C.c_void_p(eps2.data_ptr()),
+                                              C.c_void_p(fail.data_ptr()), C.c_void_p(st)))
+                nfail[0] = fail.sum()
+        if seeded:
+            dist.broadcast(nfail, src=0, group=self.group)
+            if int(nfail.item()) > 0:   # rare: the seed sat above the true k-th score for these queries
+                dist.broadcast(fail, src=0, group=self.group)
+                idx = torch.nonzero(fail[:n]).flatten()
+                D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
+                allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
+                if self.rank == 0:
+                    pD, pI = merge_candidates(allD2, allI2, None)
+                    outD[idx] = pD
+                    outI[idx] = pI
+            self.last_seed_misses = int(nfail.item())
         if self.rank != 0:
             return None, None
-        return merge_candidates(allD, allI, self.id_map)
+        if self.id_map is not None:
+            outI = torch.where(outI >= 0, self.id_map[outI.clamp_min(0)], outI)
+        return outD, outI

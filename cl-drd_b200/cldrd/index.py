@@ -427,6 +427,36 @@ class GpuIndexFlat:
                                              C.c_void_p(I.data_ptr()), C.c_void_p(stream)))
         return D, I
 
+    def sample_device(self, q, k: int):
+        """Step 1 of the sharded protocol: best SEED_J sample scan scores per query, [n, SEED_J]."""
+        import torch
+        q = q.contiguous()
+        n = q.shape[0]
+        out = torch.empty((n, _lib.SEED_J), dtype=torch.float32, device=q.device)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        with self._lock:
+            check(lib().cldrd_sample_dev(self._shard.handle, C.c_void_p(q.data_ptr()), n, int(k),
+                                         C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        return out
+
+    def search_device_seeded(self, q, k: int, seed=None, translate_ids: bool = False):
+        """Step 3: search with an external seed threshold per query (None = unseeded progressive).
+        Returns (D, I, eps2) with eps2 = 2*eps per query for the caller's verification."""
+        import torch
+        q = q.contiguous()
+        n = q.shape[0]
+        D = torch.empty((n, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=q.device)
+        eps2 = torch.empty((n,), dtype=torch.float32, device=q.device)
+        if n:
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            with self._lock:
+                check(lib().cldrd_search_dev_seeded(
+                    self._shard.handle, C.c_void_p(q.data_ptr()), n, int(k), 1 if translate_ids else 0,
+                    C.c_void_p(seed.data_ptr()) if seed is not None else None, C.c_void_p(D.data_ptr()),
+                    C.c_void_p(I.data_ptr()), C.c_void_p(eps2.data_ptr()), C.c_void_p(stream)))
+        return D, I, eps2
+
     def last_stats(self) -> dict:
         return self._shard.stats()
 

@@ -36,6 +36,7 @@ constexpr size_t kSurvTotal = size_t(kQueryBatch) * 16384;  // survivor-buffer e
 constexpr int kMaxQStride = 65536;  // survivor slice per query when the batch is small
 constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width) >= #SMs
 constexpr size_t kSegCntInts = size_t(kQueryBatch) * kMaxGroups;
+constexpr int64_t kSeedMinRows = 1 << 20;  // below this the progressive scheme is already cheap
 constexpr int kMaxRunLen = 16;      // row tiles per work unit: short runs keep the CTAs in flight
                                     // inside a window of index rows that stays hot in L2
 
@@ -124,6 +125,9 @@ struct cldrd_shard {
     size_t ws_d = 0;
     float* w_thr = nullptr;
     float* w_band = nullptr;
+    float* w_seed = nullptr;      // seed threshold per query (-inf = unseeded)
+    float* w_seed_in = nullptr;   // seed computed from this shard's own sample
+    float* w_topj = nullptr;      // [Q][CLDRD_SEED_J] sample scores
     int* w_list_len = nullptr;
     int* w_seg_cnt = nullptr;
     int* w_fail = nullptr;
@@ -164,6 +168,8 @@ struct cldrd_shard {
     // tuning overrides (environment: CLDRD_RUN_LEN, CLDRD_GROWTH), 0 = automatic
     int tune_run_len = 0;
     double tune_growth = 0.0;
+    bool no_seed = false;   // CLDRD_NO_SEED=1: always use the progressive scheme
+    float tune_seed_bias = 0.f;  // CLDRD_SEED_BIAS: added to every seed (tests force seed misses with it)
 };
 
 namespace {
@@ -171,6 +177,10 @@ namespace {
 void free_workspace(cldrd_shard* s) {
     cudaFree(s->w_thr);
     cudaFree(s->w_band);
+    cudaFree(s->w_seed);
+    cudaFree(s->w_seed_in);
+    cudaFree(s->w_topj);
+    s->w_seed = s->w_seed_in = s->w_topj = nullptr;
     cudaFree(s->w_list_len);
     cudaFree(s->w_seg_cnt);
     cudaFree(s->w_fail);
@@ -201,6 +211,9 @@ int ensure_workspace(cldrd_shard* s) {
     const size_t Q = kQueryBatch;
     CU_TRY(cudaMalloc(&s->w_thr, Q * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_band, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_seed, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_seed_in, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_topj, Q * CLDRD_SEED_J * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_list_len, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_seg_cnt, kSegCntInts * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
@@ -287,7 +300,7 @@ cudaEvent_t next_event(cldrd_shard* s) {
     return s->ev[s->ev_used++];
 }
 
-int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
+int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int tile_stride = 1) {
     cldrd_shard* s = c.s;
     if (s->profile) {
         cudaEventRecord(next_event(s), c.st);
@@ -300,6 +313,7 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     p.nq = c.nq;
     p.row_begin = row_begin;
     p.nrows = nrows;
+    p.tile_stride = tile_stride;
     plan_chunk(c, nrows);
     p.thr = s->w_thr;
     p.surv = s->w_surv;
@@ -356,7 +370,8 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
 
 size_t select_smem(const cldrd_shard* s) { return size_t(s->ws_keep_cap + kSurvCap) * 8 + size_t(s->d) * 4 + 16; }
 
-int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
+// k_sel: how many best rows the list must keep (the search's k, or the sample's j)
+int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_sel, int tile_stride = 1) {
     cldrd_shard* s = c.s;
     SelectParams p{};
     p.list = s->w_list;
@@ -372,9 +387,11 @@ int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows) {
     p.dense_ld = kDensePiece;
     p.dense_n = nrows;
     p.dense_row0 = uint32_t(row_begin);
+    p.dense_tile_stride = tile_stride;
     p.thr = s->w_thr;
+    p.seed = s->w_seed;
     p.band = s->w_band;
-    p.k = c.k;
+    p.k = k_sel;
     p.fail = s->w_fail;
     p.stats = s->w_stats;
     p.xb = s->xb;
@@ -398,6 +415,7 @@ int launch_prep(BatchCtx& c) {
     eps_coefs(s->scan_eff, s->d, &p.coef, &p.abs_coef);
     p.bmax_norm = s->bmax_norm;
     p.band = s->w_band;
+    p.seed = s->w_seed;
     p.thr = s->w_thr;
     p.list_len = s->w_list_len;
     p.fail = s->w_fail;
@@ -452,27 +470,93 @@ int read_stats(cldrd_shard* s, cudaStream_t st) {
     return CLDRD_OK;
 }
 
+// ---- seeded thresholds ---------------------------------------------------------
+
+// Sample geometry of a shard: every `stride`-th 256-row tile, `tiles` tiles in all.  The sample
+// fraction f = min(J / (3k), 1/64) makes the global J-th best sample score sit near rank J / f
+// (about 3k) of the whole index.
+struct SamplePlan {
+    int tiles = 0;
+    int stride = 1;
+};
+SamplePlan sample_plan(const cldrd_shard* s, int k) {
+    SamplePlan sp;
+    const int64_t full_tiles = s->nrows / TC_BN;   // only whole tiles are sampled
+    if (full_tiles <= 0) return sp;
+    const double f = std::min(double(CLDRD_SEED_J) / (3.0 * k), 1.0 / 64.0);
+    int64_t tiles = int64_t(std::ceil(f * double(s->nrows) / TC_BN));
+    tiles = std::max<int64_t>(1, std::min<int64_t>(tiles, full_tiles));
+    sp.tiles = int(tiles);
+    sp.stride = int(std::max<int64_t>(1, full_tiles / tiles));
+    return sp;
+}
+
+// Dense scan of the shard's sample; leaves each query's best CLDRD_SEED_J sample scores (scan
+// scores, best first, -inf padded) in out_topj [nq][CLDRD_SEED_J].  Uses the batch workspace.
+int run_sample(BatchCtx& c, float* out_topj) {
+    cldrd_shard* s = c.s;
+    const SamplePlan sp = sample_plan(s, c.k);
+    int rc;
+    const int tiles_per_piece = kDensePiece / TC_BN;
+    for (int t0 = 0; t0 < sp.tiles; t0 += tiles_per_piece) {
+        const int nt = std::min(tiles_per_piece, sp.tiles - t0);
+        const int64_t row_begin = int64_t(t0) * sp.stride * TC_BN;
+        if ((rc = launch_scan(c, true, row_begin, nt * TC_BN, sp.stride))) return rc;
+        if ((rc = launch_select(c, true, row_begin, nt * TC_BN, CLDRD_SEED_J, sp.stride))) return rc;
+    }
+    const int n_pad = s->ws_keep_cap;
+    export_topj_kernel<<<c.nq, 256, size_t(n_pad) * 8, c.st>>>(s->w_list, s->w_list_len, s->ws_keep_cap, n_pad,
+                                                              CLDRD_SEED_J, out_topj);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return CLDRD_OK;
+}
+
+int apply_seed(BatchCtx& c, const float* seed_in) {
+    cldrd_shard* s = c.s;
+    apply_seed_kernel<<<(c.nq + 255) / 256, 256, 0, c.st>>>(seed_in, c.nq, s->tune_seed_bias, s->w_seed, s->w_thr, s->w_list_len);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return CLDRD_OK;
+}
+
 // One pass of `c.nq` (<= kQueryBatch) queries over the whole shard.
-//   dense_only: every chunk is a dense piece (the fallback for queries whose survivor buffer
-//   overflowed; it cannot overflow itself).
-int run_pass(BatchCtx& c, bool dense_only) {
+//   PASS_SEEDED      thresholds start at the seed already applied to the workspace: a few big chunks
+//   PASS_PROGRESSIVE first piece dense, then geometrically growing filtered chunks
+//   PASS_DENSE       every piece dense: cannot overflow (last-resort fallback)
+enum PassKind { PASS_SEEDED, PASS_PROGRESSIVE, PASS_DENSE };
+
+int run_chunks(BatchCtx& c, PassKind kind) {
     cldrd_shard* s = c.s;
     const int64_t N = s->nrows;
-    int rc = launch_prep(c);
-    if (rc) return rc;
+    int rc;
+    if (kind == PASS_SEEDED) {
+        const int64_t target = int64_t(2500000);
+        const int nchunks = int(std::max<int64_t>(1, (N + target - 1) / target));
+        int64_t done = 0;
+        for (int i = 0; i < nchunks; ++i) {
+            int64_t m = (N * (i + 1)) / nchunks - done;
+            if (i + 1 < nchunks) m = (m / TC_BN) * TC_BN;
+            if (m <= 0) continue;
+            if ((rc = launch_scan(c, false, done, int(m)))) return rc;
+            if ((rc = launch_select(c, false, done, int(m), c.k))) return rc;
+            done += m;
+        }
+        return CLDRD_OK;
+    }
     int64_t done = 0;
     const int first = int(std::min<int64_t>(N, kDensePiece));
     if (first > 0) {
         if ((rc = launch_scan(c, true, 0, first))) return rc;
-        if ((rc = launch_select(c, true, 0, first))) return rc;
+        if ((rc = launch_select(c, true, 0, first, c.k))) return rc;
         done = first;
     }
     if (done >= N) return CLDRD_OK;
-    if (dense_only) {
+    if (kind == PASS_DENSE) {
         while (done < N) {
             const int m = int(std::min<int64_t>(N - done, kDensePiece));
             if ((rc = launch_scan(c, true, done, m))) return rc;
-            if ((rc = launch_select(c, true, done, m))) return rc;
+            if ((rc = launch_select(c, true, done, m, c.k))) return rc;
             done += m;
         }
         return CLDRD_OK;
@@ -493,56 +577,99 @@ int run_pass(BatchCtx& c, bool dense_only) {
         m = std::min<int64_t>(m, int64_t(1) << 30);
         if (m > N - done) m = N - done;
         if ((rc = launch_scan(c, false, done, int(m)))) return rc;
-        if ((rc = launch_select(c, false, done, int(m)))) return rc;
+        if ((rc = launch_select(c, false, done, int(m), c.k))) return rc;
         done += m;
     }
     return CLDRD_OK;
 }
 
-int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool translate, float* out_scores,
-                 int64_t* out_ids, cudaStream_t st, int64_t* launches, int64_t* chunks, int64_t* nfailed) {
+struct SearchTotals {
+    int64_t launches = 0, chunks = 0, fallback_queries = 0, seed_misses = 0;
+};
+
+// Queries flagged in the workspace's fail[] are searched again with a safer pass kind, results
+// scattered into their rows of the output.  Level 1: unseeded progressive.  Level 2: dense.
+int run_fallbacks(cldrd_shard* s, const float* q_dev, int nq, int k, bool translate, float* out_scores,
+                  int64_t* out_ids, cudaStream_t st, bool allow_progressive, SearchTotals* tot) {
+    std::vector<int> pending;
+    CU_TRY(cudaMemcpyAsync(s->h_fail, s->w_fail, size_t(nq) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nq; ++i)
+        if (s->h_fail[i]) pending.push_back(i);
+    tot->fallback_queries += int64_t(pending.size());
+    for (int level = allow_progressive ? 1 : 2; level <= 2 && !pending.empty(); ++level) {
+        const int nf = int(pending.size());
+        CU_TRY(cudaMemcpyAsync(s->w_fail_index, pending.data(), size_t(nf) * sizeof(int), cudaMemcpyHostToDevice, st));
+        gather_failed_kernel<<<nf, 128, 0, st>>>(q_dev, s->d, s->w_fail_index, nf, s->w_qfail);
+        CU_TRY(cudaGetLastError());
+        BatchCtx f{};
+        f.s = s;
+        f.st = st;
+        f.q = s->w_qfail;
+        f.nq = nf;
+        f.k = k;
+        int rc = launch_prep(f);
+        if (rc) return rc;
+        if ((rc = run_chunks(f, level == 1 ? PASS_PROGRESSIVE : PASS_DENSE))) return rc;
+        if ((rc = launch_rescore(f, out_scores, out_ids, translate, s->w_fail_index, s->w_fail))) return rc;
+        if ((rc = read_stats(s, st))) return rc;
+        tot->launches += f.launches + 1;
+        tot->chunks += f.chunks;
+        CU_TRY(cudaMemcpyAsync(s->h_fail, s->w_fail, size_t(nf) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        std::vector<int> next;
+        for (int i = 0; i < nf; ++i)
+            if (s->h_fail[i]) next.push_back(pending[i]);
+        pending.swap(next);
+    }
+    if (!pending.empty()) return fail(CLDRD_ECUDA, "internal: %zu queries failed the dense fallback", pending.size());
+    return CLDRD_OK;
+}
+
+// Search one batch.  seed_mode: 0 = none (progressive), 1 = automatic (sample this shard, verify
+// here: single-shard search), 2 = external seed_ext (no verification here: the caller verifies on
+// the merged result of all shards).
+int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool translate, int seed_mode,
+                 const float* seed_ext, float* out_scores, int64_t* out_ids, float* eps_out, cudaStream_t st,
+                 SearchTotals* tot) {
     BatchCtx c{};
     c.s = s;
     c.st = st;
     c.q = q_dev;
     c.nq = nq;
     c.k = k;
-    int rc = run_pass(c, false);
+    int rc = launch_prep(c);
     if (rc) return rc;
+    if (seed_mode == 1) {
+        if ((rc = run_sample(c, s->w_topj))) return rc;
+        seed_from_samples_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(s->w_topj, 1, nq, CLDRD_SEED_J, CLDRD_SEED_J,
+                                                                        s->w_seed_in);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+        if ((rc = apply_seed(c, s->w_seed_in))) return rc;
+    } else if (seed_mode == 2) {
+        if ((rc = apply_seed(c, seed_ext))) return rc;
+    }
+    if ((rc = run_chunks(c, seed_mode ? PASS_SEEDED : PASS_PROGRESSIVE))) return rc;
     if ((rc = launch_rescore(c, out_scores, out_ids, translate, nullptr, s->w_fail))) return rc;
-    // any query whose survivors overflowed?  (one small D2H; also surfaces watchdog / range errors)
+    if (eps_out) {   // eps = band / 2, for the caller's verification of an external seed
+        CU_TRY(cudaMemcpyAsync(eps_out, s->w_band, size_t(nq) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (seed_mode == 1) {
+        // survivors-overflow failures were counted by the select kernel; seed misses are added here
+        verify_seed_kernel<<<(nq + 255) / 256, 256, 0, st>>>(out_scores, nq, k, s->w_seed, s->w_band, s->w_fail, s->w_stats);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+    }
+    // any query to redo?  (one small D2H; also surfaces watchdog / range errors)
     if ((rc = read_stats(s, st))) return rc;
-    *launches += c.launches;
-    *chunks += c.chunks;
+    tot->launches += c.launches;
+    tot->chunks += c.chunks;
     if (s->h_stats[ST_RANGE_ERR])
         return fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
-    const unsigned long long nfail = s->h_stats[ST_FAILED];
-    if (nfail == 0) return CLDRD_OK;
-    *nfailed += int64_t(nfail);
-    // dense fallback for the failed queries only
-    CU_TRY(cudaMemcpyAsync(s->h_fail, s->w_fail, size_t(nq) * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    std::vector<int> idx;
-    for (int i = 0; i < nq; ++i)
-        if (s->h_fail[i]) idx.push_back(i);
-    CU_TRY(cudaMemcpyAsync(s->w_fail_index, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    gather_failed_kernel<<<int(idx.size()), 128, 0, st>>>(q_dev, s->d, s->w_fail_index, int(idx.size()), s->w_qfail);
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaStreamSynchronize(st));  // idx goes out of scope after this function
-    BatchCtx f{};
-    f.s = s;
-    f.st = st;
-    f.q = s->w_qfail;
-    f.nq = int(idx.size());
-    f.k = k;
-    const unsigned long long keep_failed = nfail;
-    if ((rc = run_pass(f, true))) return rc;
-    if ((rc = launch_rescore(f, out_scores, out_ids, translate, s->w_fail_index, nullptr))) return rc;
-    if ((rc = read_stats(s, st))) return rc;
-    s->h_stats[ST_FAILED] = keep_failed;
-    *launches += f.launches + 1;
-    *chunks += f.chunks;
-    return CLDRD_OK;
+    if (s->h_stats[ST_FAILED] == 0) return CLDRD_OK;
+    // seeded: first retry unseeded-progressive; unseeded: straight to dense
+    return run_fallbacks(s, q_dev, nq, k, translate, out_scores, out_ids, st, seed_mode != 0, tot);
 }
 
 }  // namespace
@@ -571,6 +698,8 @@ int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrow
     s->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("CLDRD_RUN_LEN")) s->tune_run_len = atoi(e);
     if (const char* e = getenv("CLDRD_GROWTH")) s->tune_growth = atof(e);
+    if (const char* e = getenv("CLDRD_NO_SEED")) s->no_seed = atoi(e) != 0;
+    if (const char* e = getenv("CLDRD_SEED_BIAS")) s->tune_seed_bias = float(atof(e));
     *out = s;
     return CLDRD_OK;
 }
@@ -747,6 +876,8 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
     CU_TRY(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(select_smem(s))));
     CU_TRY(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(size_t(s->ws_keep_cap) * 8 + size_t(s->d) * 4 + 16)));
+    CU_TRY(cudaFuncSetAttribute(export_topj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(size_t(s->ws_keep_cap) * 8)));
     s->finalized = true;
     return CLDRD_OK;
 }
@@ -760,8 +891,9 @@ int64_t cldrd_shard_scan_bytes(const cldrd_shard* s) {
     return s->nrows * int64_t(s->d) * esz;
 }
 
-int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
-                     float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
+                         int seed_mode, const float* seed_dev, float* out_scores_dev, int64_t* out_ids_dev,
+                         float* eps_out_dev, void* cuda_stream) {
     if (!s || nq < 0 || (nq && (!q_dev || !out_scores_dev || !out_ids_dev)))
         return fail(CLDRD_EINVAL, "search: NULL argument");
     if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "search: k=%d outside [1,%d]", k, CLDRD_MAX_K);
@@ -770,19 +902,20 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, 
         return fail(CLDRD_EINVAL, "search: query buffer must be 16-byte aligned");
     DeviceGuard g(s->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int64_t launches = 0, chunks = 0, nfailed = 0;
+    SearchTotals totals;
     unsigned long long tot[ST_COUNT] = {0};
     s->ev_used = 0;
     s->scan_ms = 0.0;
     s->scan_launches = 0;
     s->ev_rows.clear();
     s->ev_ms.clear();
+    if (seed_mode == 1 && (s->nrows < kSeedMinRows || s->no_seed)) seed_mode = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
         const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
         CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
-        int rc = search_batch(s, q_dev + size_t(q0) * s->d, nb, k, translate_ids != 0,
-                              out_scores_dev + size_t(q0) * k, out_ids_dev + size_t(q0) * k, st, &launches,
-                              &chunks, &nfailed);
+        int rc = search_batch(s, q_dev + size_t(q0) * s->d, nb, k, translate_ids != 0, seed_mode,
+                              seed_dev ? seed_dev + q0 : nullptr, out_scores_dev + size_t(q0) * k,
+                              out_ids_dev + size_t(q0) * k, eps_out_dev ? eps_out_dev + q0 : nullptr, st, &totals);
         if (rc) return rc;
         for (int i = 0; i < ST_COUNT; ++i) {
             if (i == ST_MAX_LIST) tot[i] = std::max(tot[i], s->h_stats[i]);
@@ -797,14 +930,85 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, 
             s->scan_launches++;
         }
     }
-    s->stats[0] = launches;
-    s->stats[1] = chunks;
-    s->stats[2] = nfailed;
+    s->stats[0] = totals.launches;
+    s->stats[1] = totals.chunks;
+    s->stats[2] = totals.fallback_queries;
     s->stats[3] = int64_t(tot[ST_RESCORED]);
     s->stats[4] = int64_t(tot[ST_SURVIVORS]);
     s->stats[5] = int64_t(tot[ST_MAX_LIST]);
     s->stats[6] = int64_t(tot[ST_TILES]);
     s->stats[7] = int64_t(tot[ST_EXACT_COMPACT]);
+    return CLDRD_OK;
+}
+
+int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
+                     float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    return search_common(s, q_dev, nq, k, translate_ids, 1, nullptr, out_scores_dev, out_ids_dev, nullptr, cuda_stream);
+}
+
+int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
+                            const float* seed_dev, float* out_scores_dev, int64_t* out_ids_dev, float* eps_out_dev,
+                            void* cuda_stream) {
+    return search_common(s, q_dev, nq, k, translate_ids, seed_dev ? 2 : 0, seed_dev, out_scores_dev, out_ids_dev,
+                         eps_out_dev, cuda_stream);
+}
+
+int cldrd_sample_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, float* out_topj_dev, void* cuda_stream) {
+    if (!s || !q_dev || !out_topj_dev || nq < 1) return fail(CLDRD_EINVAL, "sample: bad argument");
+    if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "sample: k=%d outside [1,%d]", k, CLDRD_MAX_K);
+    if (!s->finalized) return fail(CLDRD_ESTATE, "sample: shard not finalized");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
+        const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
+        CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+        BatchCtx c{};
+        c.s = s;
+        c.st = st;
+        c.q = q_dev + size_t(q0) * s->d;
+        c.nq = nb;
+        c.k = k;
+        int rc = launch_prep(c);
+        if (rc) return rc;
+        if ((rc = run_sample(c, out_topj_dev + size_t(q0) * CLDRD_SEED_J))) return rc;
+        if ((rc = read_stats(s, st))) return rc;
+    }
+    return CLDRD_OK;
+}
+
+int cldrd_seed_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq, float* seed_out_dev,
+                            void* cuda_stream) {
+    if (!topj_dev || !seed_out_dev || parts < 1 || nq < 1) return fail(CLDRD_EINVAL, "seed_from_samples: bad argument");
+    DeviceGuard g(device);
+    seed_from_samples_kernel<<<unsigned((nq * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        topj_dev, parts, int(nq), CLDRD_SEED_J, CLDRD_SEED_J, seed_out_dev);
+    CU_TRY(cudaGetLastError());
+    return CLDRD_OK;
+}
+
+int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k, const float* seed_dev,
+                      const float* eps2_dev, int32_t* fail_dev, void* cuda_stream) {
+    if (!scores_dev || !seed_dev || !eps2_dev || !fail_dev || nq < 1 || k < 1)
+        return fail(CLDRD_EINVAL, "verify_seed: bad argument");
+    DeviceGuard g(device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CU_TRY(cudaMemsetAsync(fail_dev, 0, size_t(nq) * sizeof(int32_t), st));
+    verify_seed_kernel<<<unsigned((nq + 255) / 256), 256, 0, st>>>(scores_dev, int(nq), k, seed_dev, eps2_dev, fail_dev,
+                                                                    nullptr);
+    CU_TRY(cudaGetLastError());
+    return CLDRD_OK;
+}
+
+int cldrd_shard_norm_bound(const cldrd_shard* s, float* out) {
+    if (!s || !out) return fail(CLDRD_EINVAL, "norm_bound: NULL");
+    *out = s->bmax_norm;
+    return CLDRD_OK;
+}
+
+int cldrd_shard_set_norm_bound(cldrd_shard* s, float bound) {
+    if (!s || !(bound >= 0.f)) return fail(CLDRD_EINVAL, "set_norm_bound: bad argument");
+    if (bound < s->bmax_norm) return fail(CLDRD_EINVAL, "set_norm_bound: below this shard's own bound");
+    s->bmax_norm = bound;
     return CLDRD_OK;
 }
 

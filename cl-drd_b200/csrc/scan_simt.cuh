@@ -13,7 +13,9 @@ struct ScanParams {
     int d;
     int nq;
     int64_t row_begin;    // first local row of the chunk
-    int nrows;            // rows in the chunk
+    int nrows;            // rows (score columns) in the chunk
+    int tile_stride;      // 1 = contiguous chunk; s > 1 = sampled scan: column c reads local row
+                          // row_begin + (c / 256) * s * 256 + c % 256   (every s-th 256-row tile)
     // fused filter.  Survivors of query q land in its private slice surv[q*q_stride ..), which
     // is cut into `groups` segments of seg_cap entries; seg_cnt[q*groups + g] counts segment g
     // (the count keeps running past seg_cap so that overflow is detectable).
@@ -45,7 +47,9 @@ __global__ void __launch_bounds__(256) scan_simt_kernel(ScanParams p) {
     const int m0 = blockIdx.y * SIMT_BM;
     const int n0 = blockIdx.x * SIMT_BN;
     const float* __restrict__ A = p.q;
-    const float* __restrict__ B = p.xb + size_t(p.row_begin) * p.d;
+    // source row of this CTA's first column (a 128-column tile never straddles a 256-row block)
+    const int64_t src0 = p.row_begin + int64_t(n0 >> 8) * p.tile_stride * 256 + (n0 & 255);
+    const float* __restrict__ B = p.xb + size_t(src0 - n0) * p.d;
     const int d = p.d;
 
     float acc[8][8];
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(256) scan_simt_kernel(ScanParams p) {
             } else if (v >= t) {
                 const int slot = atomicAdd(&p.seg_cnt[qi], 1);
                 if (slot < p.seg_cap)
-                    p.surv[size_t(qi) * p.q_stride + slot] = make_key(v, uint32_t(p.row_begin + col));
+                    p.surv[size_t(qi) * p.q_stride + slot] = make_key(v, uint32_t(src0 - n0 + col));
             }
         }
     }

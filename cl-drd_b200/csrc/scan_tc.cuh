@@ -99,7 +99,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n_end = min(num_n, (g + 1) * p.run_len);
             const int crd_q = m * TC_BM;
             for (int n = g * p.run_len; n < n_end; ++n) {
-                const int crd_r = int(p.row_begin) + n * TC_BN;
+                const int crd_r = int(p.row_begin) + n * TC_BN * p.tile_stride;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
                     if (lane == 0) {
@@ -201,7 +201,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 } else {
-                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * TC_BN;
+                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * uint32_t(TC_BN * p.tile_stride);
 #pragma unroll 1
                     for (int b = 0; b < TC_BN / 32; ++b) {
                         tmem_ld32(taddr + uint32_t(b * 32), v);

@@ -68,7 +68,9 @@ struct SelectParams {
     int dense_ld;
     int dense_n;           // valid columns
     uint32_t dense_row0;   // local row of dense column 0
+    int dense_tile_stride; // sampled scan: column j came from row dense_row0 + (j/256)*stride*256 + j%256
     float* thr;            // [nq]
+    const float* seed;     // [nq]  seed threshold (-inf when unseeded): thr never drops below it
     const float* band;     // [nq]  2*eps
     int k;
     int* fail;             // [nq]
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
             float v = row[j];
             if (v >= t) {
                 int slot = atomicAdd(&s_n, 1);
-                keys[slot] = make_key(v, p.dense_row0 + uint32_t(j));
+                keys[slot] = make_key(v, p.dense_row0 + uint32_t(j >> 8) * uint32_t(p.dense_tile_stride * 256) + uint32_t(j & 255));
             }
         }
         __syncthreads();
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
     }
     // k-th best scan score, then the band below it
     const uint32_t vk = uint32_t(block_radix_select<32>(keys, n, p.k, hist, bcast) >> 32);
-    const float cutf = ord2f(vk) - p.band[q];
+    // the list only ever held rows >= seed, so the cut cannot reach below it
+    const float cutf = fmaxf(ord2f(vk) - p.band[q], p.seed[q]);
     const uint32_t cut = f2ord(cutf);
     // count the band first: if it does not fit, trim by exact score instead
     int cnt = 0;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
     }
     if (tid == 0) {
         p.list_len[q] = p.k;
-        p.thr[q] = ord2f(uint32_t(kth >> 32)) - p.band[q];
+        p.thr[q] = fmaxf(ord2f(uint32_t(kth >> 32)) - p.band[q], p.seed[q]);
         atomicAdd(&p.stats[ST_EXACT_COMPACT], 1ull);
         atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)n);
         atomicMax(&p.stats[ST_MAX_LIST], (unsigned long long)p.k);
@@ -368,6 +371,7 @@ struct QueryPrepParams {
     float abs_coef;
     float bmax_norm;
     float* band;       // 2*eps (slightly inflated)
+    float* seed;       // reset to -inf
     float* thr;
     int* list_len;
     int* fail;
@@ -399,6 +403,7 @@ __global__ void query_prep_kernel(QueryPrepParams p) {
         const float eps = p.coef * qn * p.bmax_norm + p.abs_coef * (qn + p.bmax_norm);
         p.band[warp] = 2.0f * eps * 1.0001f;
         p.thr[warp] = -INFINITY;
+        p.seed[warp] = -INFINITY;
         p.list_len[warp] = 0;
         p.fail[warp] = 0;
         if (p.lp_kind == 1 && !(mx < 65504.f)) atomicAdd(&p.stats[ST_RANGE_ERR], 1ull);
@@ -442,6 +447,86 @@ __global__ void index_prep_kernel(const float* xb, int64_t nrows, int d, int lp_
         atomicMax(max_norm2_bits, __float_as_uint(best_ss));  // non-negative floats order as uints
         atomicMax(max_abs_bits, __float_as_uint(best_mx));
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Seeded thresholds.  A sample of the index rows is scanned densely first; the
+// j-th best sample score of a query is, in expectation, its (j / sample fraction)-th best score
+// overall, so it seeds the filter threshold of the real scan far above -inf.  ANY seed is safe
+// because the result is verified afterwards: every row with scan score >= seed was collected, an
+// uncollected row has exact score < seed + eps, so if the k-th returned exact score is
+// >= seed + eps nothing was missed.  Queries that fail the check are searched again unseeded.
+// ------------------------------------------------------------------------------------------
+
+// top-j scan scores of each query's candidate list, best first, -inf padded.  One CTA per query.
+// dyn smem: keys[n_pad] u64
+__global__ void __launch_bounds__(256) export_topj_kernel(const uint64_t* list, const int* list_len,
+                                                          int keep_cap, int n_pad_max, int j,
+                                                          float* out /*[nq][j]*/) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    const int q = blockIdx.x;
+    const int L = min(list_len[q], n_pad_max);
+    int n_pad = 2;
+    while (n_pad < L) n_pad <<= 1;
+    const uint64_t* my = list + size_t(q) * keep_cap;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = i < L ? my[i] : 0ull;
+    block_bitonic_desc(keys, n_pad);
+    for (int i = threadIdx.x; i < j; i += blockDim.x)
+        out[size_t(q) * j + i] = i < L ? ord2f(key_ord(keys[i])) : -INFINITY;
+}
+
+// seed[q] = j-th best of the parts*j sample scores gathered from all shards ([parts][nq][j]).
+// One warp per query (parts*j is small).  Fewer than j finite scores -> -inf (no seed).
+__global__ void seed_from_samples_kernel(const float* topj, int parts, int nq, int j, int rank_j,
+                                         float* seed) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int n = parts * j;
+    // rank_j-th largest by counting: value v is the answer if #(x > v) < rank_j <= #(x >= v)
+    float best = -INFINITY;
+    for (int c = lane; c < n; c += 32) {
+        const int part = c / j, i = c - part * j;
+        const float v = topj[(size_t(part) * nq + q) * j + i];
+        int gt = 0, ge = 0;
+        for (int t = 0; t < n; ++t) {
+            const int pt = t / j, it = t - pt * j;
+            const float x = topj[(size_t(pt) * nq + q) * j + it];
+            gt += x > v;
+            ge += x >= v;
+        }
+        if (gt < rank_j && rank_j <= ge) best = fmaxf(best, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) seed[q] = best;
+}
+
+// After the exact re-score: fail[q] = 1 unless the k-th returned score clears seed + eps.
+__global__ void verify_seed_kernel(const float* scores /*[nq][k]*/, int nq, int k, const float* seed,
+                                   const float* band /*2*eps*/, int* fail, unsigned long long* stats) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float s0 = seed[q];
+    if (s0 == -INFINITY) return;                       // unseeded query: nothing to verify
+    const float kth = scores[size_t(q) * k + (k - 1)];  // -FLT_MAX when fewer than k rows came back
+    if (!(kth >= s0 + 0.5f * band[q] * 1.0001f)) {
+        if (!fail[q]) {
+            fail[q] = 1;
+            if (stats) atomicAdd(&stats[ST_FAILED], 1ull);
+        }
+    }
+}
+
+// seed -> thr (start of a seeded pass) ; list emptied
+__global__ void apply_seed_kernel(const float* seed_in, int nq, float bias, float* seed, float* thr, int* list_len) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float s0 = seed_in[q] + bias;   // bias: test hook (CLDRD_SEED_BIAS) to force seed misses
+    seed[q] = s0;
+    thr[q] = s0;
+    list_len[q] = 0;
 }
 
 // gather failed queries into a compact matrix + remember where their results go

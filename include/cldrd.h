@@ -43,6 +43,7 @@ extern "C" {
 #define CLDRD_SCAN_TC_BF16  3  /* tcgen05 kind::f16 over a bf16 copy of the rows.                 */
 
 #define CLDRD_MAX_K 2048       /* same limit as faiss' GPU flat index */
+#define CLDRD_SEED_J 24        /* sample scores kept per query for the seeded threshold */
 
 typedef struct cldrd_shard cldrd_shard;
 
@@ -129,6 +130,33 @@ int64_t cldrd_shard_scan_bytes(const cldrd_shard* s);
 int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
                      int32_t translate_ids, float* out_scores_dev, int64_t* out_ids_dev,
                      void* cuda_stream);
+
+/* Sharded search, three steps per query batch; each rank owns one shard:
+ *   1. cldrd_sample_dev: dense scan of a small strided sample of this shard's rows; writes each
+ *      query's best CLDRD_SEED_J sample scan scores to out_topj_dev [nq][CLDRD_SEED_J].
+ *   2. all-gather those to [parts][nq][CLDRD_SEED_J] (NCCL, by the caller) and call
+ *      cldrd_seed_from_samples: seed[q] = CLDRD_SEED_J-th best of the union, i.e. a scan-score
+ *      threshold that sits near rank 3k of the WHOLE index.
+ *   3. cldrd_search_dev_seeded on every shard with that seed: only rows above it are collected,
+ *      re-scored and returned (top-k of the shard among them, -1 padded); eps2_out_dev receives
+ *      2*eps per query.  After the caller has merged the shards' lists (cldrd_merge),
+ *      cldrd_verify_seed flags every query whose k-th merged score does not clear seed + eps:
+ *      those (rare) queries must be searched again with seed_dev == NULL.
+ * Any seed is safe: it only decides how much work the filter does, never the result. */
+int cldrd_sample_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, float* out_topj_dev,
+                     void* cuda_stream);
+int cldrd_seed_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq,
+                            float* seed_out_dev, void* cuda_stream);
+int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
+                            int32_t translate_ids, const float* seed_dev, float* out_scores_dev,
+                            int64_t* out_ids_dev, float* eps2_out_dev, void* cuda_stream);
+int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k,
+                      const float* seed_dev, const float* eps2_dev, int32_t* fail_dev,
+                      void* cuda_stream);
+/* The error band uses the largest row norm of the index: shards of one index must agree on it
+ * (all-reduce MAX of cldrd_shard_norm_bound, then cldrd_shard_set_norm_bound on every shard). */
+int cldrd_shard_norm_bound(const cldrd_shard* s, float* out);
+int cldrd_shard_set_norm_bound(cldrd_shard* s, float bound);
 
 /* Host-buffer search: the call the faiss-shaped wrapper makes.  Copies q in through pinned
  * staging, searches, copies D and I out; synchronous on return like faiss. */

@@ -354,3 +354,117 @@ def test_full_size_properties(cldrd_lib):
     beat = sc > kth * (1 + 1e-5)
     in_res = (samp[None, :, None] == I16[:16, None, :]).any(-1)
     assert not (beat & ~in_res).any()
+
+
+# ------------------------------------------------------------------------------------------
+# seeded thresholds (shards of >= 2^20 rows): sample -> seed -> few big chunks -> verification
+# ------------------------------------------------------------------------------------------
+
+def _big(d=64, n=1_300_000, nq=96, seed=200):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    xq = rng.standard_normal((nq, d), dtype=np.float32)
+    return xb, xq
+
+
+@pytest.mark.parametrize("scan", ["f16", "tf32", "simt"])
+def test_seeded_search_parity(cldrd_lib, scan):
+    xb, xq = _big()
+    gpu = _gpu_index(xb, None, scan)
+    _check(gpu, xb, None, xq, 100)
+    st = gpu.last_stats()
+    # seeded pass: sample pieces + one chunk, far fewer survivors than the progressive scheme
+    assert st["chunks"] <= 6, st
+    assert st["survivors"] / xq.shape[0] < 40 * 100, st
+    gpu.close()
+
+
+def test_seed_miss_falls_back_and_stays_exact(cldrd_lib, monkeypatch):
+    """A seed far above every score collects nothing: verification must flag every query and the
+    unseeded retry must return the exact answer."""
+    xb, xq = _big(nq=40, seed=201)
+    monkeypatch.setenv("CLDRD_SEED_BIAS", "1e6")
+    gpu = _gpu_index(xb, None, "f16")
+    _check(gpu, xb, None, xq, 50)
+    assert gpu.last_stats()["fallback_queries"] == xq.shape[0], gpu.last_stats()
+    gpu.close()
+    monkeypatch.setenv("CLDRD_SEED_BIAS", "0")
+    monkeypatch.setenv("CLDRD_NO_SEED", "1")
+    gpu = _gpu_index(xb, None, "f16")
+    D0, I0 = gpu.search(xq, 50)
+    assert gpu.last_stats()["fallback_queries"] == 0
+    gpu.close()
+    monkeypatch.setenv("CLDRD_NO_SEED", "0")
+    gpu = _gpu_index(xb, None, "f16")
+    D1, I1 = gpu.search(xq, 50)
+    assert np.array_equal(D0, D1) and np.array_equal(I0, I1)   # seeded == progressive, to the bit
+    gpu.close()
+
+
+def test_sharded_seed_protocol_single_process(cldrd_lib):
+    """The three-step protocol of cldrd.dist driven by hand over 3 shards on one GPU:
+    sample -> seed from the gathered samples -> seeded search -> merge -> verify."""
+    import torch
+    from cldrd import dist as CD
+    from cldrd._lib import check, lib, SEED_J
+    from cldrd.index import shard_ranges
+    xb, xq = _big(nq=64, seed=202)
+    N = xb.shape[0]
+    rows = torch.from_numpy(xb).cuda()
+    q = torch.from_numpy(xq).cuda()
+    k = 100
+    shards = [CD.ShardedSearcher.from_rows(rows[rr.start:rr.stop], rr.start, N, scan="f16") for rr in shard_ranges(N, 3)]
+    bound = max(_norm_bound(s) for s in shards)
+    for s in shards:
+        check(lib().cldrd_shard_set_norm_bound(s.shard.handle, C.c_float(bound)))
+    topj = torch.stack([s.local.sample_device(q, k) for s in shards])
+    assert topj.shape == (3, 64, SEED_J)
+    seed = torch.empty((64,), dtype=torch.float32, device="cuda")
+    check(lib().cldrd_seed_from_samples(0, C.c_void_p(topj.data_ptr()), 3, 64, C.c_void_p(seed.data_ptr()), None))
+    outs = [s.local.search_device_seeded(q, k, seed) for s in shards]
+    D, I = CD.merge_candidates(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
+    fail = torch.ones((64,), dtype=torch.int32, device="cuda")
+    check(lib().cldrd_verify_seed(0, C.c_void_p(D.data_ptr()), 64, k, C.c_void_p(seed.data_ptr()),
+                                  C.c_void_p(outs[0][2].data_ptr()), C.c_void_p(fail.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert int(fail.sum()) <= 2          # the seed sits near rank 3k: misses are rare
+    ok = (fail == 0).cpu().numpy()
+    # the seed is a real filter: a shard collects ~J/f/3 rows per query, not its whole share
+    assert shards[0].shard.stats()["survivors"] / 64 < 3000, shards[0].shard.stats()
+    D_ref, I_ref = O.search(xb, None, xq, k)
+    r = O.compare_topk(D.cpu().numpy()[ok], I.cpu().numpy()[ok], D_ref[ok], I_ref[ok],
+                       *[a[ok] for a in O.search(xb, None, xq, k + 16, dtype=np.float64)])
+    assert r["ok"], r
+    # a hopeless seed is caught by the verification
+    bad = seed + 1e6
+    outs = [s.local.search_device_seeded(q, k, bad) for s in shards]
+    D, I = CD.merge_candidates(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
+    check(lib().cldrd_verify_seed(0, C.c_void_p(D.data_ptr()), 64, k, C.c_void_p(bad.data_ptr()),
+                                  C.c_void_p(outs[0][2].data_ptr()), C.c_void_p(fail.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert int(fail.sum()) == 64
+
+
+def _norm_bound(searcher):
+    from cldrd._lib import check, lib
+    b = C.c_float()
+    check(lib().cldrd_shard_norm_bound(searcher.shard.handle, C.byref(b)))
+    return b.value
+
+
+def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
+    """One process per GPU over NCCL (needs 2 GPUs): sharded result == single-GPU result, bit for bit."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "dist_result.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "dist_worker.py"), "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    res = json.loads(out.read_text())
+    assert res["bit_equal_small"] and res["bit_equal_big"] and res["oracle_ok"], res
