@@ -58,6 +58,8 @@ SIGNATURES = {
     "cldrd_shard_norm_bound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cldrd_shard_set_norm_bound": (C.c_int, [C.c_void_p, C.c_float]),
     "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cldrd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "cldrd_host_free": (None, [C.c_void_p]),
     "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),
     "cldrd_shard_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -96,3 +98,60 @@ def check(rc: int) -> None:
 def ptr(a) -> C.c_void_p:
     """void* of a numpy array (host) — caller keeps the array alive."""
     return C.c_void_p(a.ctypes.data)
+
+
+class _PinnedPool:
+    """Recycles page-locked result buffers: cudaHostAlloc costs milliseconds per 100 MB, a search
+    result is needed for every call.  A buffer returns to the pool when the ndarray that wraps it
+    (and every view of it) has been garbage-collected."""
+
+    def __init__(self, max_bytes: int = 1 << 30):
+        self.free = {}          # nbytes -> [ptr]
+        self.held = 0
+        self.max_bytes = max_bytes
+
+    def take(self, nbytes: int) -> int:
+        lst = self.free.get(nbytes)
+        if lst:
+            self.held -= nbytes
+            return lst.pop()
+        p = C.c_void_p()
+        check(lib().cldrd_host_alloc(C.byref(p), nbytes))
+        return p.value
+
+    def give(self, ptr_value: int, nbytes: int) -> None:
+        if self.held + nbytes > self.max_bytes:
+            lib().cldrd_host_free(C.c_void_p(ptr_value))
+            return
+        self.free.setdefault(nbytes, []).append(ptr_value)
+        self.held += nbytes
+
+
+_pool = _PinnedPool()
+
+
+class _PinnedOwner:
+    def __init__(self, nbytes: int):
+        self.nbytes = nbytes
+        self.ptr = _pool.take(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _pool.give(self.ptr, self.nbytes)
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked memory (falls back to pageable for empty arrays)."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.empty(shape, dtype=dtype)
+    owner = _PinnedOwner(n * dtype.itemsize)
+    buf = (C.c_char * owner.nbytes).from_address(owner.ptr)
+    buf._owner = owner                      # the ctypes buffer keeps the pinned block alive
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)

@@ -404,8 +404,9 @@ class GpuIndexFlat:
         if k > _lib.MAX_K:
             raise RuntimeError(f"search: k={k} above the GPU limit {_lib.MAX_K} (same limit as faiss GpuIndexFlat)")
         n = x.shape[0]
-        D = np.empty((n, k), dtype=np.float32)
-        I = np.empty((n, k), dtype=np.int64)
+        # results land in page-locked arrays the caller owns: one DMA, no staging copy
+        D = _lib.pinned_empty((n, k), np.float32)
+        I = _lib.pinned_empty((n, k), np.int64)
         if n:
             with self._lock:
                 check(lib().cldrd_search_host(self._shard.handle, ptr(x), n, k, ptr(D), ptr(I)))

@@ -300,7 +300,8 @@ cudaEvent_t next_event(cldrd_shard* s) {
     return s->ev[s->ev_used++];
 }
 
-int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int tile_stride = 1) {
+int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_stride = 1) {
+    const bool dense = mode != TC_FILTER;
     cldrd_shard* s = c.s;
     if (s->profile) {
         cudaEventRecord(next_event(s), c.st);
@@ -335,12 +336,14 @@ int launch_scan(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int tile_
             if (s->profile) cudaEventRecord(next_event(s), c.st);
             return CLDRD_OK;
         }
-#define LAUNCH_TC(KIND)                                                                               \
-    do {                                                                                              \
-        if (dense)                                                                                    \
-            scan_tc_kernel<KIND, true><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p);  \
-        else                                                                                          \
-            scan_tc_kernel<KIND, false><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p); \
+#define LAUNCH_TC(KIND)                                                                                   \
+    do {                                                                                                  \
+        if (mode == TC_DENSE)                                                                             \
+            scan_tc_kernel<KIND, TC_DENSE><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p);  \
+        else if (mode == TC_MAXES)                                                                        \
+            scan_tc_kernel<KIND, TC_MAXES><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p);  \
+        else                                                                                              \
+            scan_tc_kernel<KIND, TC_FILTER><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p); \
     } while (0)
         if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC(0);
         else if (s->scan_eff == CLDRD_SCAN_TC_BF16) LAUNCH_TC(1);
@@ -485,28 +488,30 @@ SamplePlan sample_plan(const cldrd_shard* s, int k) {
     if (full_tiles <= 0) return sp;
     const double f = std::min(double(CLDRD_SEED_J) / (3.0 * k), 1.0 / 64.0);
     int64_t tiles = int64_t(std::ceil(f * double(s->nrows) / TC_BN));
-    tiles = std::max<int64_t>(1, std::min<int64_t>(tiles, full_tiles));
+    // one launch: the tensor-core scan keeps 8 group maxima per tile in the dense buffer, the
+    // SIMT scan keeps raw scores (256 per tile)
+    const int64_t cap = is_tc(s->scan_eff) ? kDensePiece / (TC_BN / 32) : kDensePiece / TC_BN;
+    tiles = std::max<int64_t>(1, std::min<int64_t>(tiles, std::min<int64_t>(full_tiles, cap)));
     sp.tiles = int(tiles);
     sp.stride = int(std::max<int64_t>(1, full_tiles / tiles));
     return sp;
 }
 
-// Dense scan of the shard's sample; leaves each query's best CLDRD_SEED_J sample scores (scan
-// scores, best first, -inf padded) in out_topj [nq][CLDRD_SEED_J].  Uses the batch workspace.
+// Scan the shard's sample in one launch and leave each query's best CLDRD_SEED_J sample values
+// (best first, -inf padded) in out_topj [nq][CLDRD_SEED_J].  Uses the batch workspace.
 int run_sample(BatchCtx& c, float* out_topj) {
     cldrd_shard* s = c.s;
     const SamplePlan sp = sample_plan(s, c.k);
-    int rc;
-    const int tiles_per_piece = kDensePiece / TC_BN;
-    for (int t0 = 0; t0 < sp.tiles; t0 += tiles_per_piece) {
-        const int nt = std::min(tiles_per_piece, sp.tiles - t0);
-        const int64_t row_begin = int64_t(t0) * sp.stride * TC_BN;
-        if ((rc = launch_scan(c, true, row_begin, nt * TC_BN, sp.stride))) return rc;
-        if ((rc = launch_select(c, true, row_begin, nt * TC_BN, CLDRD_SEED_J, sp.stride))) return rc;
+    int cols = 0;
+    if (sp.tiles > 0) {
+        const bool tc = is_tc(s->scan_eff);
+        int rc = launch_scan(c, tc ? TC_MAXES : TC_DENSE, 0, sp.tiles * TC_BN, sp.stride);
+        if (rc) return rc;
+        cols = tc ? sp.tiles * (TC_BN / 32) : sp.tiles * TC_BN;
     }
-    const int n_pad = s->ws_keep_cap;
-    export_topj_kernel<<<c.nq, 256, size_t(n_pad) * 8, c.st>>>(s->w_list, s->w_list_len, s->ws_keep_cap, n_pad,
-                                                              CLDRD_SEED_J, out_topj);
+    int n_pad = 32;
+    while (n_pad < cols) n_pad <<= 1;
+    sample_topj_kernel<<<c.nq, 256, size_t(n_pad) * 4, c.st>>>(s->w_dense, kDensePiece, cols, n_pad, CLDRD_SEED_J, out_topj);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;
@@ -538,7 +543,7 @@ int run_chunks(BatchCtx& c, PassKind kind) {
             int64_t m = (N * (i + 1)) / nchunks - done;
             if (i + 1 < nchunks) m = (m / TC_BN) * TC_BN;
             if (m <= 0) continue;
-            if ((rc = launch_scan(c, false, done, int(m)))) return rc;
+            if ((rc = launch_scan(c, TC_FILTER, done, int(m)))) return rc;
             if ((rc = launch_select(c, false, done, int(m), c.k))) return rc;
             done += m;
         }
@@ -547,7 +552,7 @@ int run_chunks(BatchCtx& c, PassKind kind) {
     int64_t done = 0;
     const int first = int(std::min<int64_t>(N, kDensePiece));
     if (first > 0) {
-        if ((rc = launch_scan(c, true, 0, first))) return rc;
+        if ((rc = launch_scan(c, TC_DENSE, 0, first))) return rc;
         if ((rc = launch_select(c, true, 0, first, c.k))) return rc;
         done = first;
     }
@@ -555,7 +560,7 @@ int run_chunks(BatchCtx& c, PassKind kind) {
     if (kind == PASS_DENSE) {
         while (done < N) {
             const int m = int(std::min<int64_t>(N - done, kDensePiece));
-            if ((rc = launch_scan(c, true, done, m))) return rc;
+            if ((rc = launch_scan(c, TC_DENSE, done, m))) return rc;
             if ((rc = launch_select(c, true, done, m, c.k))) return rc;
             done += m;
         }
@@ -576,7 +581,7 @@ int run_chunks(BatchCtx& c, PassKind kind) {
         m = (m / TC_BN) * TC_BN;
         m = std::min<int64_t>(m, int64_t(1) << 30);
         if (m > N - done) m = N - done;
-        if ((rc = launch_scan(c, false, done, int(m)))) return rc;
+        if ((rc = launch_scan(c, TC_FILTER, done, int(m)))) return rc;
         if ((rc = launch_select(c, false, done, int(m), c.k))) return rc;
         done += m;
     }
@@ -864,20 +869,22 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
         const void* base = lp ? s->xlp : static_cast<const void*>(s->xb);
         int rc = make_tensor_map(&s->tmB, s->scan_eff, base, s->nrows, s->d, TC_BN);
         if (rc) return rc;
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
-        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<1, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
     }
     int rc = ensure_workspace(s);
     if (rc) return rc;
     CU_TRY(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(select_smem(s))));
     CU_TRY(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(size_t(s->ws_keep_cap) * 8 + size_t(s->d) * 4 + 16)));
-    CU_TRY(cudaFuncSetAttribute(export_topj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(size_t(s->ws_keep_cap) * 8)));
+
     s->finalized = true;
     return CLDRD_OK;
 }
@@ -1012,6 +1019,15 @@ int cldrd_shard_set_norm_bound(cldrd_shard* s, float bound) {
     return CLDRD_OK;
 }
 
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k, float* out_scores_host,
                       int64_t* out_ids_host) {
     if (!s || nq < 0 || (nq && (!q_host || !out_scores_host || !out_ids_host)))
@@ -1021,13 +1037,9 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
     DeviceGuard g(s->device);
     const size_t qbytes = size_t(nq) * s->d * sizeof(float);
     const size_t oelems = size_t(nq) * k;
-    if (qbytes > s->h_q_bytes) {
-        if (s->h_q) cudaFreeHost(s->h_q);
-        s->h_q = nullptr;
-        s->h_q_bytes = 0;
-        CU_TRY(cudaHostAlloc(&s->h_q, qbytes, cudaHostAllocDefault));
-        s->h_q_bytes = qbytes;
-    }
+    // outputs that already live in pinned memory (cldrd_host_alloc) are written by the DMA engine
+    // directly; pageable ones go through a pinned staging buffer
+    const bool direct_out = is_pinned_host(out_scores_host) && is_pinned_host(out_ids_host);
     if (qbytes > s->d_q_bytes) {
         cudaFree(s->d_q);
         s->d_q = nullptr;
@@ -1035,7 +1047,7 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
         CU_TRY(cudaMalloc(&s->d_q, qbytes));
         s->d_q_bytes = qbytes;
     }
-    if (oelems > s->h_out_elems) {
+    if (!direct_out && oelems > s->h_out_elems) {
         if (s->h_D) cudaFreeHost(s->h_D);
         if (s->h_I) cudaFreeHost(s->h_I);
         s->h_D = nullptr;
@@ -1056,16 +1068,37 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
         s->d_out_elems = oelems;
     }
     cudaStream_t st = cudaStreamPerThread;
-    memcpy(s->h_q, q_host, qbytes);
-    CU_TRY(cudaMemcpyAsync(s->d_q, s->h_q, qbytes, cudaMemcpyHostToDevice, st));
+    // pageable or pinned: the runtime stages pageable sources itself
+    CU_TRY(cudaMemcpyAsync(s->d_q, q_host, qbytes, cudaMemcpyHostToDevice, st));
     int rc = cldrd_search_dev(s, s->d_q, nq, k, 1, s->d_D, s->d_I, st);
     if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(s->h_D, s->d_D, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(s->h_I, s->d_I, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    float* dst_D = direct_out ? out_scores_host : s->h_D;
+    int64_t* dst_I = direct_out ? out_ids_host : s->h_I;
+    CU_TRY(cudaMemcpyAsync(dst_D, s->d_D, oelems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(dst_I, s->d_I, oelems * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    memcpy(out_scores_host, s->h_D, oelems * sizeof(float));
-    memcpy(out_ids_host, s->h_I, oelems * sizeof(int64_t));
+    if (!direct_out) {
+        memcpy(out_scores_host, s->h_D, oelems * sizeof(float));
+        memcpy(out_ids_host, s->h_I, oelems * sizeof(int64_t));
+    }
     return CLDRD_OK;
+}
+
+int cldrd_host_alloc(void** out, int64_t nbytes) {
+    if (!out || nbytes < 0) return fail(CLDRD_EINVAL, "host_alloc: bad argument");
+    *out = nullptr;
+    if (nbytes == 0) return CLDRD_OK;
+    cudaError_t e = cudaHostAlloc(out, size_t(nbytes), cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CLDRD_ENOMEM : CLDRD_ECUDA, "cudaHostAlloc(%lld) failed: %s",
+                    (long long)nbytes, cudaGetErrorString(e));
+    }
+    return CLDRD_OK;
+}
+
+void cldrd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t k,
@@ -1131,7 +1164,7 @@ int cldrd_scan_dense_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int64_t
     CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
     int rc = launch_prep(c);
     if (rc) return rc;
-    if ((rc = launch_scan(c, true, row_begin, int(nrows)))) return rc;
+    if ((rc = launch_scan(c, TC_DENSE, row_begin, int(nrows)))) return rc;
     CU_TRY(cudaMemcpy2DAsync(out_dev, size_t(nrows) * 4, s->w_dense, size_t(kDensePiece) * 4, size_t(nrows) * 4, size_t(nq),
                              cudaMemcpyDeviceToDevice, st));
     return read_stats(s, st);

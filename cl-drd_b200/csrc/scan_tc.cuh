@@ -43,7 +43,12 @@ __host__ __device__ constexpr uint32_t tc_idesc(int kind) {
            (uint32_t(TC_BM >> 4) << 24);
 }
 
-template <int KIND, bool DENSE>
+// MODE: what the epilogue does with a score tile
+constexpr int TC_FILTER = 0;  // append scores >= thr[q] to the query's survivor segment
+constexpr int TC_DENSE = 1;   // write every score to dense[q][col] (first piece, fallback, tests)
+constexpr int TC_MAXES = 2;   // write the max of every 32-column group to dense[q][col/32] (seed sample)
+
+template <int KIND, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                ScanParams p) {
@@ -167,14 +172,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int qrow = m * TC_BM + qd * 32 + lane;
             const bool qvalid = qrow < p.nq;
             float thr = INFINITY;
-            if (!DENSE && qvalid) thr = p.thr[qrow];
+            if (MODE == TC_FILTER && qvalid) thr = p.thr[qrow];
             // this thread's private segment: (query, group) while there are fewer groups than
             // CTAs -- every unit then owns a fresh segment -- else (query, this CTA)
             const int seg = p.seg_by_group ? g : int(blockIdx.x);
-            uint64_t* dst = DENSE ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(seg) * p.seg_cap;
-            int* cnt_slot = DENSE ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * p.groups + seg;
+            uint64_t* dst = MODE != TC_FILTER ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(seg) * p.seg_cap;
+            int* cnt_slot = MODE != TC_FILTER ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * p.groups + seg;
             int cnt = 0;
-            if (!DENSE && qvalid) cnt = *cnt_slot;
+            if (MODE == TC_FILTER && qvalid) cnt = *cnt_slot;
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {
                 const uint32_t as = it & 1u;
                 const uint32_t aphase = (it >> 1) & 1u;
@@ -183,7 +188,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
                 tc_fence_after();
                 float v[32];
-                if (DENSE) {
+                if (MODE == TC_MAXES) {
+                    // seed sample: only whole tiles are sampled, so every column is valid
+                    float mxs[TC_BN / 32];
+#pragma unroll
+                    for (int b = 0; b < TC_BN / 32; ++b) {
+                        tmem_ld32(taddr + uint32_t(b * 32), v);
+                        float mx = v[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                        mxs[b] = mx;
+                    }
+                    if (qvalid) {
+                        float4* o = reinterpret_cast<float4*>(p.dense + size_t(qrow) * p.dense_ld + size_t(n) * (TC_BN / 32));
+                        o[0] = make_float4(mxs[0], mxs[1], mxs[2], mxs[3]);
+                        o[1] = make_float4(mxs[4], mxs[5], mxs[6], mxs[7]);
+                    }
+                } else if (MODE == TC_DENSE) {
 #pragma unroll 1
                     for (int b = 0; b < TC_BN / 32; ++b) {
                         tmem_ld32(taddr + uint32_t(b * 32), v);
@@ -226,7 +247,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 ++tiles_done;
             }
-            if (!DENSE && qvalid) *cnt_slot = cnt;
+            if (MODE == TC_FILTER && qvalid) *cnt_slot = cnt;
         }
         if (warp == 2 && lane == 0 && p.stats) atomicAdd(&p.stats[ST_TILES], tiles_done);
     }

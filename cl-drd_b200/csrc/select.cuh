@@ -458,22 +458,37 @@ __global__ void index_prep_kernel(const float* xb, int64_t nrows, int d, int lp_
 // >= seed + eps nothing was missed.  Queries that fail the check are searched again unseeded.
 // ------------------------------------------------------------------------------------------
 
-// top-j scan scores of each query's candidate list, best first, -inf padded.  One CTA per query.
-// dyn smem: keys[n_pad] u64
-__global__ void __launch_bounds__(256) export_topj_kernel(const uint64_t* list, const int* list_len,
-                                                          int keep_cap, int n_pad_max, int j,
+// Best j of the `cols` sample values of each query (raw sample scores, or maxima of 32-column
+// groups: the j-th largest group maximum is a lower bound of the j-th largest score, which only
+// makes the seed more conservative).  One CTA per query; -inf padded.
+// dyn smem: vals[n_pad] u32 (orderable floats)
+__global__ void __launch_bounds__(256) sample_topj_kernel(const float* vals, int ld, int cols, int n_pad, int j,
                                                           float* out /*[nq][j]*/) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sm_raw);
     const int q = blockIdx.x;
-    const int L = min(list_len[q], n_pad_max);
-    int n_pad = 2;
-    while (n_pad < L) n_pad <<= 1;
-    const uint64_t* my = list + size_t(q) * keep_cap;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = i < L ? my[i] : 0ull;
-    block_bitonic_desc(keys, n_pad);
-    for (int i = threadIdx.x; i < j; i += blockDim.x)
-        out[size_t(q) * j + i] = i < L ? ord2f(key_ord(keys[i])) : -INFINITY;
+    const float* row = vals + size_t(q) * ld;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        float v = i < cols ? row[i] : -INFINITY;
+        keys[i] = (v == v) ? f2ord(v) : f2ord(-INFINITY);   // NaN never seeds a threshold
+    }
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                int hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint32_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < j; i += blockDim.x) out[size_t(q) * j + i] = i < cols ? ord2f(keys[i]) : -INFINITY;
 }
 
 // seed[q] = j-th best of the parts*j sample scores gathered from all shards ([parts][nq][j]).

@@ -163,6 +163,12 @@ int cldrd_shard_set_norm_bound(cldrd_shard* s, float bound);
 int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k,
                       float* out_scores_host, int64_t* out_ids_host);
 
+/* Page-locked host memory for result buffers: cldrd_search_host writes D and I straight into
+ * buffers obtained here (the DMA engine's only copy); any other host buffer is served through
+ * an internal pinned staging buffer plus one memcpy. */
+int  cldrd_host_alloc(void** out, int64_t nbytes);
+void cldrd_host_free(void* p);
+
 /* Merge per-shard candidate lists (replaces faiss IndexShards' CPU merge_knn_results behind
  * retriever/retrieval_utils.py:176-182).  Inputs are [parts][nq][k] device arrays of scores and
  * GLOBAL rows as produced by cldrd_search_dev(translate_ids=0) on each shard and gathered to
