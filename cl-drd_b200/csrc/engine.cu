@@ -486,7 +486,10 @@ SamplePlan sample_plan(const cldrd_shard* s, int k) {
     SamplePlan sp;
     const int64_t full_tiles = s->nrows / TC_BN;   // only whole tiles are sampled
     if (full_tiles <= 0) return sp;
-    const double f = std::min(double(CLDRD_SEED_J) / (3.0 * k), 1.0 / 64.0);
+    // target rank of the seed: comfortably beyond k plus the rows inside the error band, which is
+    // wider for the coarser scan formats
+    const double rank_factor = s->scan_eff == CLDRD_SCAN_TC_BF16 ? 8.0 : s->scan_eff == CLDRD_SCAN_TC_TF32 ? 4.0 : 3.0;
+    const double f = std::min(double(CLDRD_SEED_J) / (rank_factor * k), 1.0 / 64.0);
     int64_t tiles = int64_t(std::ceil(f * double(s->nrows) / TC_BN));
     // one launch: the tensor-core scan keeps 8 group maxima per tile in the dense buffer, the
     // SIMT scan keeps raw scores (256 per tile)

@@ -1,0 +1,86 @@
+"""Index build: same flags and outputs as the reference's retriever/index_text.py (:30-109):
+encodes the collection, writes `<index_dir>/<checkpoint stem>.index` in faiss' IndexIDMap{IndexFlatIP}
+layout and `meta.pkl`.  Rows are streamed to their final file offset batch by batch instead of being
+held in host memory twice."""
+import argparse
+import ctypes as C
+import os
+import pickle
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cldrd._lib import check, lib, ptr  # noqa: E402
+from cldrd.encoder import DualEncoder, SequenceDataset, load_checkpoint  # noqa: E402
+
+
+def get_args(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--resume", default="")
+    parser.add_argument("--model_name_or_path", default="distilbert-base-uncased")
+    parser.add_argument("--tokenizer_name_or_path", default="distilbert-base-uncased")
+    parser.add_argument("--passages_path", default="collection.tsv")
+    parser.add_argument("--queries_path", default="")
+    parser.add_argument("--max_length", default=256, type=int)
+    parser.add_argument("--index_dir", default="index/")
+    parser.add_argument("--is_query", default=False, action="store_true")
+    parser.add_argument("--is_parallel", default=True, type=lambda s: str(s).lower() not in ("0", "false", "no"))
+    parser.add_argument("--share_weights", action="store_true", default=False)
+    parser.add_argument("--batch_size", default=512, type=int)
+    parser.add_argument("--index_name", default="", help="index file stem when --resume is empty")
+    args = parser.parse_args(argv)
+    if args.resume:
+        assert args.index_dir[:-7] in args.resume     # same guard as the reference (:50)
+    if not os.path.exists(args.index_dir):
+        os.mkdir(args.index_dir)
+    return args
+
+
+def main(args):
+    from transformers import AutoTokenizer
+    model = DualEncoder(args.model_name_or_path, share_weights=args.share_weights)
+    print("************************* share weights = {} *************************".format(args.share_weights))
+    if args.resume:
+        print(f"load model from ==> {args.resume}")
+        load_checkpoint(model, args.resume, args.is_parallel)
+    elif not args.index_name:
+        raise ValueError("not index path defined.")
+    dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    model.to(dev).eval()
+    tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name_or_path)
+    path = args.queries_path if args.is_query else args.passages_path
+    dataset = SequenceDataset.create_from_seqs_file(path, tokenizer, args.max_length, is_query=args.is_query)
+    loader = DataLoader(dataset, batch_size=args.batch_size, shuffle=False, num_workers=0, collate_fn=dataset.collate_fn)
+    stem = (Path(args.resume).stem.split(".")[0] if args.resume else args.index_name) + ".index"
+    index_path = os.path.join(args.index_dir, stem)
+    n = len(dataset)
+    hidden = model.query_encoder.config.hidden_size
+    w = C.c_void_p()
+    check(lib().cldrd_index_writer_begin(C.byref(w), index_path.encode(), n, hidden, 1, 0))
+    text_ids = []
+    n_nan = 0
+    for batch in loader:
+        with torch.no_grad():
+            with torch.autocast(device_type=dev.type, dtype=torch.float16, enabled=dev.type == "cuda"):
+                seq = {k: v.to(dev) for k, v in batch["seq"].items()}
+                reps = model.query_embs(seq) if args.is_query else model.passage_embs(seq)
+        rows = np.ascontiguousarray(reps.float().cpu().numpy())
+        n_nan += int(np.isnan(rows).sum())
+        check(lib().cldrd_index_writer_append(w, ptr(rows), rows.shape[0]))
+        text_ids.extend(batch["id"])
+    print(f"# nan in embeddings: {n_nan}")
+    print("embs dtype: ", np.dtype(np.float32))
+    text_ids_arr = np.array(text_ids, dtype=np.int64)
+    check(lib().cldrd_index_writer_finish(w, ptr(text_ids_arr)))
+    meta = {"text_ids": text_ids_arr, "text_id_to_idx": {tid: idx for idx, tid in enumerate(text_ids)}}
+    with open(os.path.join(args.index_dir, "meta.pkl"), "wb") as f:
+        pickle.dump(meta, f)
+    return index_path
+
+
+if __name__ == "__main__":
+    main(get_args())

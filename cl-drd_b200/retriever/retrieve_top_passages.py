@@ -1,0 +1,69 @@
+"""Query search entry point: same flags, prints and run file as the reference's
+retriever/retrieve_top_passages.py (:28-109).  The search runs on the B200 kernels; the regroup and
+writer loops are one native call."""
+import argparse
+import os
+import sys
+
+import torch
+from torch.utils.data import DataLoader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cldrd  # noqa: E402
+from cldrd.encoder import DualEncoder, SequenceDataset, load_checkpoint  # noqa: E402
+from cldrd.retrieval_utils import convert_index_to_gpu, get_embeddings_from_scratch, index_retrieve_arrays  # noqa: E402
+
+
+def get_args(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--resume", default="")
+    parser.add_argument("--model_name_or_path", default="distilbert-base-uncased")
+    parser.add_argument("--tokenizer_name_or_path", default="distilbert-base-uncased")
+    parser.add_argument("--queries_path", default="queries.dev.small.tsv")
+    parser.add_argument("--index_path", default="")
+    parser.add_argument("--max_length", default=30, type=int)
+    parser.add_argument("--top_k", default=1000, type=int)
+    parser.add_argument("--is_parallel", default=True, type=lambda s: str(s).lower() not in ("0", "false", "no"))
+    parser.add_argument("--share_weights", action="store_true", default=False)
+    parser.add_argument("--output_path", default="")
+    parser.add_argument("--gpus", default="0", help="comma-separated device list; more than one = row-sharded index")
+    parser.add_argument("--precision", default="auto", choices=["auto", "f16", "bf16", "tf32", "simt"],
+                        help="scan mode; results are exact fp32 in every mode")
+    return parser.parse_args(argv)
+
+
+def check_paths(queries_path, output_path):
+    # retriever/retrieve_top_passages.py:48-59
+    for needle, tag, msg in (("train", "train", "retrieve train queries"), ("dev", "dev", "retrieve dev queries"),
+                             ("2019", "trec19", "retrieve trec-19 queries"), ("2020", "trec20", "retrieve trec-20 queries")):
+        if needle in queries_path:
+            print(msg)
+            assert tag in output_path
+
+
+def main(args, is_query_side=True, header="# unique query"):
+    from transformers import AutoTokenizer
+    check_paths(args.queries_path, args.output_path)
+    model = DualEncoder(args.model_name_or_path, share_weights=args.share_weights)
+    print("************************* share weights = {} *************************".format(args.share_weights))
+    if args.resume:
+        print(f"load model from ==> {args.resume}")
+        load_checkpoint(model, args.resume, args.is_parallel)
+    model.cuda()
+    tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name_or_path)
+    dataset = SequenceDataset.create_from_seqs_file(args.queries_path, tokenizer, args.max_length, is_query=is_query_side)
+    loader = DataLoader(dataset, batch_size=512, shuffle=False, num_workers=0, collate_fn=dataset.collate_fn)
+    query_embs, query_ids = get_embeddings_from_scratch(model, loader, use_fp16=True, is_query=is_query_side,
+                                                        show_progress_bar=True)
+    os.environ.setdefault("CLDRD_SCAN", args.precision)
+    index = cldrd.read_index(args.index_path)                      # headers only; rows stream file -> HBM
+    devs = [int(x) for x in str(args.gpus).split(",")]
+    index = convert_index_to_gpu(index, devs if len(devs) > 1 else devs[0], False)
+    nn_scores, nn_doc_ids = index_retrieve_arrays(index, query_embs, args.top_k)
+    print(f"{header} = {len(set(query_ids))}")
+    avg = cldrd.write_run_file(args.output_path, query_ids, nn_doc_ids, nn_scores)
+    print(f"average ranks per query = {avg}")
+
+
+if __name__ == "__main__":
+    main(get_args())

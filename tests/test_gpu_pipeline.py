@@ -1,0 +1,94 @@
+"""End-to-end pipeline on the GPU with a tiny random-init DistilBERT built offline:
+index_text -> index file + meta.pkl -> retrieve_top_passages -> run file, checked against the oracle
+run on the same embeddings (the reference's three-script flow, README.md:16-36)."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip as O
+
+pytestmark = pytest.mark.gpu
+
+WORDS = ["alpha", "beta", "gamma", "delta", "river", "stone", "cloud", "tensor", "query", "passage", "index", "score",
+         "blue", "green", "fast", "slow", "north", "south", "model", "train", "dev", "rank", "deep", "dense"]
+
+
+def _tiny_model_dir(tmp_path):
+    from transformers import BertTokenizerFast, DistilBertConfig, DistilBertModel
+    import torch
+    d = tmp_path / "tiny-distilbert"
+    d.mkdir()
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + WORDS
+    (d / "vocab.txt").write_text("\n".join(vocab) + "\n")
+    tok = BertTokenizerFast(vocab_file=str(d / "vocab.txt"), do_lower_case=True)
+    tok.save_pretrained(str(d))
+    torch.manual_seed(2)
+    cfg = DistilBertConfig(vocab_size=len(vocab), dim=64, n_layers=2, n_heads=4, hidden_dim=128, max_position_embeddings=64)
+    DistilBertModel(cfg).save_pretrained(str(d))
+    return str(d)
+
+
+def test_index_text_then_retrieve_top_passages(cldrd_lib, tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cl-drd_b200"))
+    import torch
+    from torch.utils.data import DataLoader
+    from transformers import AutoTokenizer
+    from cldrd.encoder import DualEncoder, SequenceDataset
+    from cldrd.retrieval_utils import get_embeddings_from_scratch
+    from retriever import index_text, retrieve_top_passages, retrieve_top_queries
+    model_dir = _tiny_model_dir(tmp_path)
+    rng = np.random.default_rng(0)
+    coll, quer = tmp_path / "collection.tsv", tmp_path / "queries.dev.tsv"
+    pids = rng.permutation(5000)[:300] + 7_000_000
+    with open(coll, "w") as f:
+        for pid in pids:
+            f.write(f"{pid}\t{' '.join(rng.choice(WORDS, size=rng.integers(5, 30)))}\n")
+    qids = rng.permutation(1000)[:25] + 1_048_000
+    with open(quer, "w") as f:
+        for qid in qids:
+            f.write(f"{qid}\t{' '.join(rng.choice(WORDS, size=rng.integers(2, 8)))}\n")
+    index_dir = str(tmp_path / "index") + "/"
+    a = index_text.get_args(["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir, "--passages_path", str(coll),
+                             "--index_dir", index_dir, "--index_name", "checkpoint_120000", "--share_weights", "--batch_size", "64"])
+    torch.manual_seed(3)
+    index_path = index_text.main(a)
+    assert index_path.endswith("checkpoint_120000.index")
+    xb, ids, info = O.read_index(index_path)                       # the oracle's reader parses our file
+    assert info["fourcc"] == "IxMp" and xb.shape == (300, 64) and ids.tolist() == pids.tolist()
+    meta = pickle.load(open(os.path.join(index_dir, "meta.pkl"), "rb"))
+    assert meta["text_ids"].tolist() == pids.tolist() and meta["text_id_to_idx"][int(pids[5])] == 5
+    run = tmp_path / "runs" / "dev.run"
+    b = retrieve_top_passages.get_args(["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir,
+                                        "--queries_path", str(quer), "--index_path", index_path, "--top_k", "20",
+                                        "--output_path", str(run), "--share_weights"])
+    retrieve_top_passages.main(b)
+    lines = [ln.split("\t") for ln in run.read_text().splitlines()]
+    assert len(lines) == 25 * 20 and [int(ln[2]) for ln in lines[:20]] == list(range(1, 21))
+    assert [int(ln[0]) for ln in lines[::20]] == qids.tolist()   # query-file order
+    # oracle on the same embeddings
+    model = DualEncoder(model_dir, share_weights=True).cuda()
+    tok = AutoTokenizer.from_pretrained(model_dir)
+    ds = SequenceDataset.create_from_seqs_file(str(quer), tok, 30, is_query=True)
+    xq, ids_q = get_embeddings_from_scratch(model, DataLoader(ds, batch_size=512, collate_fn=ds.collate_fn), True, True)
+    assert ids_q == qids.tolist()
+    D_ref, I_ref = O.search(xb, ids, xq, 20)
+    D_run = np.array([float(ln[3]) for ln in lines], dtype=np.float32).reshape(25, 20)
+    I_run = np.array([int(ln[1]) for ln in lines], dtype=np.int64).reshape(25, 20)
+    r = O.compare_topk(D_run, I_run, D_ref, I_ref, *O.search(xb, ids, xq, 36, dtype=np.float64))
+    assert r["ok"], r
+    # the transposed script: passages against the same index, top-5
+    run2 = tmp_path / "runs" / "passages.run"
+    c = retrieve_top_queries.get_args(["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir,
+                                       "--passages_path", str(coll), "--index_path", index_path, "--top_k", "5",
+                                       "--output_path", str(run2)])
+    retrieve_top_queries.main(c)
+    l2 = [ln.split("\t") for ln in run2.read_text().splitlines()]
+    assert len(l2) == 300 * 5
+    assert [int(ln[2]) for ln in l2[:5]] == [1, 2, 3, 4, 5]
+    assert [int(ln[0]) for ln in l2[::5]] == pids.tolist()          # passage-file order
+    s2 = np.array([float(ln[3]) for ln in l2]).reshape(300, 5)
+    assert (np.diff(s2, axis=1) <= 0).all()
+    assert set(int(ln[1]) for ln in l2) <= set(pids.tolist())

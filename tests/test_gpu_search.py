@@ -468,3 +468,26 @@ def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
     import json
     res = json.loads(out.read_text())
     assert res["bit_equal_small"] and res["bit_equal_big"] and res["oracle_ok"], res
+
+
+def test_more_queries_than_one_batch(cldrd_lib):
+    """nq above the internal 8192-query batch (config 5 streams 502k queries the same way)."""
+    xb, xq = O.synth(20_000, 64, 400), O.synth(8300, 64, 401)
+    gpu = _gpu_index(xb, None, "f16")
+    D, I = gpu.search(xq, 10)
+    D_ref, I_ref = O.search(xb, None, xq, 10)
+    r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, None, xq, 26, dtype=np.float64))
+    assert r["ok"], r
+    gpu.close()
+
+
+def test_bf16_scan_overlap_is_one(cldrd_lib):
+    """BASELINE.json configs[3]: bf16 index scan + fp32 rescore vs the fp32-exact path: overlap@k = 1.0
+    and identical bits, because both return the fp32 rescore of a provably complete candidate set."""
+    xb, xq = O.synth(200_000, 768, 410), O.synth(64, 768, 411)
+    res = {}
+    for scan in ("bf16", "tf32"):
+        gpu = _gpu_index(xb, None, scan)
+        res[scan] = gpu.search(xq, 1000)
+        gpu.close()
+    assert np.array_equal(res["bf16"][1], res["tf32"][1]) and np.array_equal(res["bf16"][0], res["tf32"][0])
