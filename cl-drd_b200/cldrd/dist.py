@@ -1,11 +1,14 @@
 """Row-sharded search with one process per GPU (torchrun), the B200-native form of the
 reference's `index_cpu_to_gpu_multiple(..., shard=True)` (retriever/retrieval_utils.py:174-182).
 
-rank r keeps passage rows shard_ranges(N, G)[r] resident in its HBM; queries are replicated;
-every rank runs the same fused search over its shard and emits [nq, k] (score, GLOBAL row);
-one NCCL gather over NVLink brings the candidate lists to rank 0, where the merge kernel
-(same u64 key order as the single-GPU search, so results are bit-identical) and the id_map
-gather finish the job.  torch.distributed is plumbing only; no collective touches the index.
+rank r keeps passage rows shard_ranges(N, G)[r] resident in its HBM; queries are replicated.
+Per query batch: every rank scans a small sample of its rows, the sample scores are
+all-gathered (NCCL) and turned into one global filter seed per query; every rank then runs the
+fused scan + filter + fp32 re-score over its shard with that seed and emits [nq, k] (score,
+GLOBAL row); one NCCL gather over NVLink brings the lists to rank 0, where the merge kernel (same
+u64 key order as the single-GPU search, so results are bit-identical), the seed verification and
+the id_map gather finish the job.  torch.distributed is plumbing only; no collective touches
+the index.
 """
 from __future__ import annotations
 
