@@ -11,7 +11,7 @@ SCAN_SIMT_F32, SCAN_TC_TF32, SCAN_TC_F16, SCAN_TC_BF16 = 0, 1, 2, 3
 SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "fp16": SCAN_TC_F16,
               "bf16": SCAN_TC_BF16}
 MAX_K = 2048
-SEED_J = 24
+SEED_J = 32
 
 E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
 

@@ -130,6 +130,7 @@ struct cldrd_shard {
     float* w_topj = nullptr;      // [Q][CLDRD_SEED_J] sample scores
     int* w_list_len = nullptr;
     int* w_seg_cnt = nullptr;
+    int* w_unit_ctr = nullptr;   // [kUnitCtrSlots] work-unit counters, one per scan launch of a pass
     int* w_fail = nullptr;
     int* w_fail_index = nullptr;
     uint64_t* w_list = nullptr;
@@ -169,6 +170,7 @@ struct cldrd_shard {
     int tune_run_len = 0;
     double tune_growth = 0.0;
     bool no_seed = false;   // CLDRD_NO_SEED=1: always use the progressive scheme
+    int tune_seed_chunks = 0;    // CLDRD_SEED_CHUNKS: force the number of launches of a seeded pass
     float tune_seed_bias = 0.f;  // CLDRD_SEED_BIAS: added to every seed (tests force seed misses with it)
 };
 
@@ -183,6 +185,8 @@ void free_workspace(cldrd_shard* s) {
     s->w_seed = s->w_seed_in = s->w_topj = nullptr;
     cudaFree(s->w_list_len);
     cudaFree(s->w_seg_cnt);
+    cudaFree(s->w_unit_ctr);
+    s->w_unit_ctr = nullptr;
     cudaFree(s->w_fail);
     cudaFree(s->w_fail_index);
     cudaFree(s->w_list);
@@ -216,6 +220,7 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMalloc(&s->w_topj, Q * CLDRD_SEED_J * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_list_len, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_seg_cnt, kSegCntInts * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_unit_ctr, sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
@@ -261,6 +266,7 @@ struct BatchCtx {
     int64_t chunks = 0;
     // survivor-buffer plan of the current chunk (scan writes it, select reads it)
     int q_stride = 0, seg_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
+    double seed_rank = 0.0;   // expected rank (in the whole index) of the seed threshold
 };
 
 // Work-unit plan for one chunk.  The grid is one persistent CTA per SM (fewer when there is less
@@ -324,6 +330,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
     p.groups = c.groups;
     p.run_len = c.run_len;
     p.seg_by_group = c.seg_by_group;
+    p.unit_ctr = s->w_unit_ctr;
     p.dense = s->w_dense;
     p.dense_ld = kDensePiece;
     p.stats = s->w_stats;
@@ -336,6 +343,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
             if (s->profile) cudaEventRecord(next_event(s), c.st);
             return CLDRD_OK;
         }
+        CU_TRY(cudaMemsetAsync(s->w_unit_ctr, 0, sizeof(int), c.st));
 #define LAUNCH_TC(KIND)                                                                                   \
     do {                                                                                                  \
         if (mode == TC_DENSE)                                                                             \
@@ -488,7 +496,7 @@ SamplePlan sample_plan(const cldrd_shard* s, int k) {
     if (full_tiles <= 0) return sp;
     // target rank of the seed: comfortably beyond k plus the rows inside the error band, which is
     // wider for the coarser scan formats
-    const double rank_factor = s->scan_eff == CLDRD_SCAN_TC_BF16 ? 8.0 : s->scan_eff == CLDRD_SCAN_TC_TF32 ? 4.0 : 3.0;
+    const double rank_factor = s->scan_eff == CLDRD_SCAN_TC_BF16 ? 8.0 : s->scan_eff == CLDRD_SCAN_TC_TF32 ? 4.5 : 3.5;
     const double f = std::min(double(CLDRD_SEED_J) / (rank_factor * k), 1.0 / 64.0);
     int64_t tiles = int64_t(std::ceil(f * double(s->nrows) / TC_BN));
     // one launch: the tensor-core scan keeps 8 group maxima per tile in the dense buffer, the
@@ -512,9 +520,8 @@ int run_sample(BatchCtx& c, float* out_topj) {
         if (rc) return rc;
         cols = tc ? sp.tiles * (TC_BN / 32) : sp.tiles * TC_BN;
     }
-    int n_pad = 32;
-    while (n_pad < cols) n_pad <<= 1;
-    sample_topj_kernel<<<c.nq, 256, size_t(n_pad) * 4, c.st>>>(s->w_dense, kDensePiece, cols, n_pad, CLDRD_SEED_J, out_topj);
+    static_assert(CLDRD_SEED_J <= 64, "sample_topj_kernel sorts at most 64 values");
+    sample_topj_kernel<<<c.nq, 256, size_t(std::max(cols, 1)) * 8, c.st>>>(s->w_dense, kDensePiece, cols, CLDRD_SEED_J, out_topj);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;
@@ -539,8 +546,15 @@ int run_chunks(BatchCtx& c, PassKind kind) {
     const int64_t N = s->nrows;
     int rc;
     if (kind == PASS_SEEDED) {
-        const int64_t target = int64_t(2500000);
-        const int nchunks = int(std::max<int64_t>(1, (N + target - 1) / target));
+        // The seed already sits near the final threshold, so the whole shard is ONE launch: no
+        // inter-chunk dependency, no select between chunks, one tail.  (Chunks only come back for
+        // shards beyond the int32 row range of a launch.)
+        const int64_t target = (int64_t(1) << 31) - TC_BN;
+        int nchunks = int(std::max<int64_t>(1, (N + target - 1) / target));
+        // ... or when the seed's expected rank exceeds what a select CTA takes in per launch
+        // (large k, or the small sample of the SIMT scan): then thresholds tighten between chunks
+        nchunks = std::max(nchunks, int(std::ceil(c.seed_rank / (0.5 * kSurvCap))));
+        if (s->tune_seed_chunks > 0) nchunks = s->tune_seed_chunks;
         int64_t done = 0;
         for (int i = 0; i < nchunks; ++i) {
             int64_t m = (N * (i + 1)) / nchunks - done;
@@ -648,6 +662,12 @@ int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool transla
     c.k = k;
     int rc = launch_prep(c);
     if (rc) return rc;
+    if (seed_mode) {
+        // expected rank of the seed = J / sample fraction (all shards sample the same fraction)
+        const SamplePlan sp = sample_plan(s, k);
+        const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
+        c.seed_rank = double(CLDRD_SEED_J) / frac;
+    }
     if (seed_mode == 1) {
         if ((rc = run_sample(c, s->w_topj))) return rc;
         seed_from_samples_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(s->w_topj, 1, nq, CLDRD_SEED_J, CLDRD_SEED_J,
@@ -708,6 +728,7 @@ int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrow
     if (const char* e = getenv("CLDRD_GROWTH")) s->tune_growth = atof(e);
     if (const char* e = getenv("CLDRD_NO_SEED")) s->no_seed = atoi(e) != 0;
     if (const char* e = getenv("CLDRD_SEED_BIAS")) s->tune_seed_bias = float(atof(e));
+    if (const char* e = getenv("CLDRD_SEED_CHUNKS")) s->tune_seed_chunks = atoi(e);
     *out = s;
     return CLDRD_OK;
 }
@@ -885,6 +906,7 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
     int rc = ensure_workspace(s);
     if (rc) return rc;
     CU_TRY(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(select_smem(s))));
+    CU_TRY(cudaFuncSetAttribute(sample_topj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kDensePiece) * 8));
     CU_TRY(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(size_t(s->ws_keep_cap) * 8 + size_t(s->d) * 4 + 16)));
 

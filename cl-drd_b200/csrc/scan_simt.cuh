@@ -27,6 +27,7 @@ struct ScanParams {
     int groups;           // segments per query: SIMT scan 1 (atomic append), TC scan min(#groups, #CTAs)
     int seg_by_group;     // TC scan: segment index = group (1) or CTA (0)
     int run_len;          // TC scan: consecutive row tiles per work unit
+    int* unit_ctr;        // TC scan: global work-unit counter of this launch (zeroed by the host)
     // dense dump
     float* dense;         // [nq][dense_ld]
     int dense_ld;

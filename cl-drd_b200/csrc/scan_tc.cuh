@@ -9,10 +9,13 @@
 //                 lane quadrant; thread = one query: its threshold, its survivor count and its
 //                 output cursor live in registers)
 //   work units    unit u = (query tile m = u % num_m, group g = u / num_m) covers `run_len`
-//                 consecutive row tiles for ONE query tile.  Persistent CTAs take units round
-//                 robin, so the CTAs in flight hold every query tile for ~3 short groups: each
-//                 index row tile is pulled from HBM once and served to the other query tiles
-//                 from L2 while it is still hot.
+//                 consecutive row tiles for ONE query tile.  Persistent CTAs draw units from a
+//                 global counter (the producer warp fetches the next id while it streams the
+//                 current unit and hands it to the other warps through a 4-deep shared-memory
+//                 ring), so at any moment the CTAs in flight sit on ~148 CONSECUTIVE units = every
+//                 query tile of ~3 short groups: each index row tile is pulled from HBM once and
+//                 served to the other query tiles from L2 while it is still hot, however long the
+//                 launch runs and however unevenly the SMs progress.
 //   survivors     query q owns a slice of the survivor buffer cut into min(#groups, #CTAs)
 //                 segments: one per group while groups are few, one per CTA otherwise.  A
 //                 segment is written by exactly one thread at a time; its cursor is carried in
@@ -33,7 +36,8 @@ constexpr int TC_B_STAGE = TC_BN * TC_KB_BYTES;  // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_STAGE + TC_B_STAGE;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 512;
-constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_UNIT_RING = 4;
+constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + unit ring*/;
 
 // kind: 0 = fp16, 1 = bf16, 2 = tf32.  Instruction descriptor (cute::UMMA::InstrDescriptor):
 // c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | K-major A and B (bits 15,16 = 0)
@@ -62,7 +66,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = bars + TC_STAGES;        // [STAGES] MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * TC_STAGES;    // [2] MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;  // [2] epilogue -> MMA
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* ufull_bar = bars + 2 * TC_STAGES + 4;                   // [RING] producer -> consumers: unit id published
+    uint64_t* uempty_bar = bars + 2 * TC_STAGES + 4 + TC_UNIT_RING;   // [RING] consumers -> producer: slot read
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4 + 2 * TC_UNIT_RING);
+    volatile int* unit_ring = reinterpret_cast<volatile int*>(tmem_base_slot + 2);    // [RING]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,6 +91,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4);
         }
+        for (int r = 0; r < TC_UNIT_RING; ++r) {
+            mbar_init(&ufull_bar[r], 1);
+            mbar_init(&uempty_bar[r], 5);   // MMA warp + 4 epilogue warps
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -99,7 +110,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int uq = 0;
+        uint32_t uphase = 0;
+        int u_next = 0;
+        if (lane == 0) u_next = atomicAdd(p.unit_ctr, 1);
+        for (;;) {
+            const int u = __shfl_sync(0xffffffffu, u_next, 0);
+            // publish the unit (or the end marker) to the MMA and epilogue warps
+            mbar_wait(&uempty_bar[uq], uphase ^ 1, err, 500 + uq);
+            if (lane == 0) {
+                unit_ring[uq] = u < num_units ? u : -1;
+                mbar_arrive(&ufull_bar[uq]);
+            }
+            if (++uq == TC_UNIT_RING) {
+                uq = 0;
+                uphase ^= 1;
+            }
+            if (u >= num_units) break;
+            if (lane == 0) u_next = atomicAdd(p.unit_ctr, 1);   // latency hidden behind this unit's loads
             const int m = u % num_m, g = u / num_m;
             const int n_end = min(num_n, (g + 1) * p.run_len);
             const int crd_q = m * TC_BM;
@@ -129,7 +157,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int uq = 0;
+        uint32_t uphase = 0;
+        for (;;) {
+            mbar_wait(&ufull_bar[uq], uphase, err, 600 + uq);
+            const int u = unit_ring[uq];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&uempty_bar[uq]);
+            if (++uq == TC_UNIT_RING) {
+                uq = 0;
+                uphase ^= 1;
+            }
+            if (u < 0) break;
             const int g = u / num_m;
             const int n_end = min(num_n, (g + 1) * p.run_len);
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {
@@ -166,7 +205,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int qd = warp & 3;  // the TMEM lane quadrant this warp may read
         uint32_t it = 0;
         unsigned long long tiles_done = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int uq = 0;
+        uint32_t uphase = 0;
+        for (;;) {
+            mbar_wait(&ufull_bar[uq], uphase, err, 700 + uq);
+            const int u = unit_ring[uq];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&uempty_bar[uq]);
+            if (++uq == TC_UNIT_RING) {
+                uq = 0;
+                uphase ^= 1;
+            }
+            if (u < 0) break;
             const int m = u % num_m, g = u / num_m;
             const int n_end = min(num_n, (g + 1) * p.run_len);
             const int qrow = m * TC_BM + qd * 32 + lane;

@@ -460,35 +460,57 @@ __global__ void index_prep_kernel(const float* xb, int64_t nrows, int d, int lp_
 
 // Best j of the `cols` sample values of each query (raw sample scores, or maxima of 32-column
 // groups: the j-th largest group maximum is a lower bound of the j-th largest score, which only
-// makes the seed more conservative).  One CTA per query; -inf padded.
-// dyn smem: vals[n_pad] u32 (orderable floats)
-__global__ void __launch_bounds__(256) sample_topj_kernel(const float* vals, int ld, int cols, int n_pad, int j,
+// makes the seed more conservative).  One CTA per query: radix-select the j-th largest, then sort
+// the few values at or above it.  Output best first, -inf padded.   j <= 64.
+// dyn smem: keys[cols] u64 (orderable float in the high half)
+__global__ void __launch_bounds__(256) sample_topj_kernel(const float* vals, int ld, int cols, int j,
                                                           float* out /*[nq][j]*/) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint32_t* keys = reinterpret_cast<uint32_t*>(sm_raw);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t bcast[2];
+    __shared__ uint64_t top[64];
+    __shared__ int s_cnt;
     const int q = blockIdx.x;
+    const int tid = threadIdx.x;
     const float* row = vals + size_t(q) * ld;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        float v = i < cols ? row[i] : -INFINITY;
-        keys[i] = (v == v) ? f2ord(v) : f2ord(-INFINITY);   // NaN never seeds a threshold
+    for (int i = tid; i < cols; i += blockDim.x) {
+        float v = row[i];
+        if (!(v == v)) v = -INFINITY;                       // NaN never seeds a threshold
+        keys[i] = uint64_t(f2ord(v)) << 32;
     }
-    for (int size = 2; size <= n_pad; size <<= 1) {
+    if (tid < 64) top[tid] = uint64_t(f2ord(-INFINITY)) << 32;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (cols > 0) {
+        const int jj = min(j, cols);
+        const uint64_t kth = block_radix_select<32>(keys, cols, jj, hist, bcast);   // high half = j-th largest
+        for (int i = tid; i < cols; i += blockDim.x) {
+            if (keys[i] >= kth) {
+                int slot = atomicAdd(&s_cnt, 1);
+                if (slot < 64) top[slot] = keys[i];          // ties beyond 64 slots equal kth anyway
+            }
+        }
+        __syncthreads();
+    }
+    // 64-element bitonic sort, descending
+    for (int size = 2; size <= 64; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
-                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+            if (tid < 32) {
+                int lo = ((tid / stride) * (stride << 1)) + (tid % stride);
                 int hi = lo + stride;
                 bool desc = ((lo & size) == 0);
-                uint32_t a = keys[lo], b = keys[hi];
+                uint64_t a = top[lo], b = top[hi];
                 if ((a < b) == desc) {
-                    keys[lo] = b;
-                    keys[hi] = a;
+                    top[lo] = b;
+                    top[hi] = a;
                 }
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < j; i += blockDim.x) out[size_t(q) * j + i] = i < cols ? ord2f(keys[i]) : -INFINITY;
+    for (int i = tid; i < j; i += blockDim.x) out[size_t(q) * j + i] = ord2f(uint32_t(top[i] >> 32));
 }
 
 // seed[q] = j-th best of the parts*j sample scores gathered from all shards ([parts][nq][j]).

@@ -43,7 +43,7 @@ extern "C" {
 #define CLDRD_SCAN_TC_BF16  3  /* tcgen05 kind::f16 over a bf16 copy of the rows.                 */
 
 #define CLDRD_MAX_K 2048       /* same limit as faiss' GPU flat index */
-#define CLDRD_SEED_J 24        /* sample scores kept per query for the seeded threshold */
+#define CLDRD_SEED_J 32        /* sample scores kept per query for the seeded threshold */
 
 typedef struct cldrd_shard cldrd_shard;
 

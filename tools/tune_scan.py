@@ -15,7 +15,7 @@ def main():
     ap.add_argument("--rows", type=int, default=8_841_823)
     ap.add_argument("--queries", type=int, default=6980)
     ap.add_argument("--k", type=int, default=1000)
-    ap.add_argument("--settings", default="0:0,4:0,8:0,16:0,32:0,64:0,16:1.7")
+    ap.add_argument("--settings", default="0:0:1,0:0:4,0:0:1,0:0:4,0:0:2")
     args = ap.parse_args()
     import torch
     from cldrd import dist as CD
@@ -26,9 +26,10 @@ def main():
         rows[r0:r0 + (1 << 20)].normal_(generator=g)
     q = torch.randn((args.queries, 768), generator=g, dtype=torch.float32, device=dev)
     for setting in args.settings.split(","):
-        rl, gr = setting.split(":")
+        rl, gr, ch = (setting.split(":") + ["0"])[:3]
         os.environ["CLDRD_RUN_LEN"] = rl
         os.environ["CLDRD_GROWTH"] = gr
+        os.environ["CLDRD_SEED_CHUNKS"] = ch
         s = CD.ShardedSearcher.from_rows(rows, 0, args.rows, scan=args.scan)
         s.shard.set_profiling(True)
         best = None
@@ -44,7 +45,7 @@ def main():
                 best = (tot, ms, s.shard.scan_launches(), s.shard.stats())
         tot, ms, launches, st = best
         per = " ".join(f"{r}:{t:.2f}ms({2 * args.queries * r * 768 / t / 1e9:.0f}TF)" for r, t in launches[:12])
-        print(f"run_len={rl} growth={gr}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
+        print(f"run_len={rl} growth={gr} seed_chunks={ch}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
               f"({2 * args.queries * args.rows * 768 / ms / 1e9:.0f} TF) surv/q {st['survivors'] / args.queries:.0f} | {per}",
               flush=True)
         s.shard.close()
