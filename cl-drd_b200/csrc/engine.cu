@@ -15,6 +15,7 @@
 #include "common_host.h"
 #include "scan_simt.cuh"
 #include "scan_tc.cuh"
+#include "scan_tc2.cuh"
 #include "select.cuh"
 
 using namespace cldrd;
@@ -32,13 +33,17 @@ namespace {
 constexpr int kQueryBatch = 8192;   // queries processed per pass over the index
 constexpr int kDensePiece = 8192;   // rows per dense piece (first chunk and fallback)
 constexpr int kSurvCap = 8192;      // survivors one select CTA can take in per chunk (shared memory)
-constexpr size_t kSurvTotal = size_t(kQueryBatch) * 16384;  // survivor-buffer entries (all queries), 1 GiB
+constexpr size_t kSurvTotal = size_t(kQueryBatch) * 32768;  // survivor-buffer entries (all queries), 2 GiB
 constexpr int kMaxQStride = 65536;  // survivor slice per query when the batch is small
 constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width) >= #SMs
 constexpr size_t kSegCntInts = size_t(kQueryBatch) * kMaxGroups;
 constexpr int64_t kSeedMinRows = 1 << 20;  // below this the progressive scheme is already cheap
 constexpr int kMaxRunLen = 16;      // row tiles per work unit: short runs keep the CTAs in flight
                                     // inside a window of index rows that stays hot in L2
+constexpr int kMaxRunLenByGroup = 64;  // ... stretched up to this if that makes #groups <= #CTAs: then
+                                    // every unit owns a fresh survivor segment and the survivors
+                                    // spread exactly evenly (with a few groups per CTA the
+                                    // (query, CTA) cells would be loaded very unevenly)
 
 struct DeviceGuard {
     int prev = -1;
@@ -119,6 +124,8 @@ struct cldrd_shard {
     int vec4 = 0;
     int num_sms = 0;
     CUtensorMap tmB;
+    CUtensorMap tmBh;        // half row tile (128 rows) for the 2-CTA scan
+    bool use_tc2 = false;    // CLDRD_TC2=1: cta_group::2 scan kernel
 
     // workspace for one query batch
     int ws_keep_cap = 0;
@@ -286,11 +293,29 @@ void plan_chunk(BatchCtx& c, int nrows) {
     }
     const int num_m = nq_pad / TC_BM;
     const int num_n = std::max(1, (nrows + TC_BN - 1) / TC_BN);
-    const long long tiles = (long long)num_m * num_n;
+    long long tiles = (long long)num_m * num_n;
+    if (s->use_tc2) {
+        // CTA pairs: a work unit covers two query tiles; the grid is an even number of CTAs
+        tiles = (long long)((num_m + 1) / 2) * num_n;
+        const int clusters = int(std::min<long long>(tiles, std::min(s->num_sms, kMaxGroups) / 2));
+        c.grid = 2 * clusters;
+        const long long per_cluster = tiles / clusters;
+        c.run_len = int(std::max<long long>(1, std::min<long long>(kMaxRunLen, per_cluster / 16)));
+        if (s->tune_run_len > 0 && per_cluster >= 16 * kMaxRunLen) c.run_len = s->tune_run_len;
+        if ((num_n + c.run_len - 1) / c.run_len > clusters && (num_n + clusters - 1) / clusters <= kMaxRunLenByGroup)
+            c.run_len = (num_n + clusters - 1) / clusters;
+        const int num_groups2 = (num_n + c.run_len - 1) / c.run_len;
+        c.seg_by_group = num_groups2 <= clusters ? 1 : 0;
+        c.groups = c.seg_by_group ? num_groups2 : clusters;   // one survivor segment per CTA pair
+        c.seg_cap = std::max(1, c.q_stride / c.groups);
+        return;
+    }
     c.grid = int(std::min<long long>(tiles, std::min(s->num_sms, kMaxGroups)));
     const long long per_cta = tiles / c.grid;
     c.run_len = int(std::max<long long>(1, std::min<long long>(kMaxRunLen, per_cta / 16)));
     if (s->tune_run_len > 0 && per_cta >= 16 * kMaxRunLen) c.run_len = s->tune_run_len;
+    if ((num_n + c.run_len - 1) / c.run_len > c.grid && (num_n + c.grid - 1) / c.grid <= kMaxRunLenByGroup)
+        c.run_len = (num_n + c.grid - 1) / c.grid;
     const int num_groups = (num_n + c.run_len - 1) / c.run_len;
     c.seg_by_group = num_groups <= c.grid ? 1 : 0;
     c.groups = c.seg_by_group ? num_groups : c.grid;   // survivor segments per query
@@ -353,10 +378,24 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
         else                                                                                              \
             scan_tc_kernel<KIND, TC_FILTER><<<grid, TC_THREADS, TC_SMEM_BYTES, c.st>>>(c.tmA, s->tmB, p); \
     } while (0)
-        if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC(0);
+#define LAUNCH_TC2(KIND)                                                                                      \
+    do {                                                                                                      \
+        if (mode == TC_DENSE)                                                                                 \
+            scan_tc2_kernel<KIND, TC_DENSE><<<grid, TC_THREADS, TC2_SMEM_BYTES, c.st>>>(c.tmA, s->tmBh, p);   \
+        else if (mode == TC_MAXES)                                                                            \
+            scan_tc2_kernel<KIND, TC_MAXES><<<grid, TC_THREADS, TC2_SMEM_BYTES, c.st>>>(c.tmA, s->tmBh, p);   \
+        else                                                                                                  \
+            scan_tc2_kernel<KIND, TC_FILTER><<<grid, TC_THREADS, TC2_SMEM_BYTES, c.st>>>(c.tmA, s->tmBh, p);  \
+    } while (0)
+        if (s->use_tc2) {
+            if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC2(0);
+            else if (s->scan_eff == CLDRD_SCAN_TC_BF16) LAUNCH_TC2(1);
+            else LAUNCH_TC2(2);
+        } else if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC(0);
         else if (s->scan_eff == CLDRD_SCAN_TC_BF16) LAUNCH_TC(1);
         else LAUNCH_TC(2);
 #undef LAUNCH_TC
+#undef LAUNCH_TC2
     } else {
         dim3 grid((nrows + SIMT_BN - 1) / SIMT_BN, (c.nq + SIMT_BM - 1) / SIMT_BM);
         if (grid.x == 0 || grid.y == 0) {
@@ -729,6 +768,7 @@ int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrow
     if (const char* e = getenv("CLDRD_NO_SEED")) s->no_seed = atoi(e) != 0;
     if (const char* e = getenv("CLDRD_SEED_BIAS")) s->tune_seed_bias = float(atof(e));
     if (const char* e = getenv("CLDRD_SEED_CHUNKS")) s->tune_seed_chunks = atoi(e);
+    if (const char* e = getenv("CLDRD_TC2")) s->use_tc2 = atoi(e) != 0;
     *out = s;
     return CLDRD_OK;
 }
@@ -893,6 +933,7 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
         const void* base = lp ? s->xlp : static_cast<const void*>(s->xb);
         int rc = make_tensor_map(&s->tmB, s->scan_eff, base, s->nrows, s->d, TC_BN);
         if (rc) return rc;
+        if ((rc = make_tensor_map(&s->tmBh, s->scan_eff, base, s->nrows, s->d, TC_BN / 2))) return rc;
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<0, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
@@ -902,6 +943,17 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
         CU_TRY(cudaFuncSetAttribute(scan_tc_kernel<2, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM_BYTES)));
+    }
+    if (is_tc(s->scan_eff) && s->nrows) {
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<0, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<0, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<0, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<1, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<1, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<1, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<2, TC_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<2, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
+        CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<2, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
     }
     int rc = ensure_workspace(s);
     if (rc) return rc;

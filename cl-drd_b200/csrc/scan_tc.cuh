@@ -8,7 +8,7 @@
 //   warps         0: TMA producer   1: MMA issuer + TMEM owner   2..5: epilogue (one per TMEM
 //                 lane quadrant; thread = one query: its threshold, its survivor count and its
 //                 output cursor live in registers)
-//   work units    unit u = (query tile m = u % num_m, group g = u / num_m) covers `run_len`
+//   work units    unit u = (group g = u / num_m, query tile m = hashed rotation of u % num_m) covers `run_len`
 //                 consecutive row tiles for ONE query tile.  Persistent CTAs draw units from a
 //                 global counter (the producer warp fetches the next id while it streams the
 //                 current unit and hands it to the other warps through a 4-deep shared-memory
@@ -51,6 +51,79 @@ __host__ __device__ constexpr uint32_t tc_idesc(int kind) {
 constexpr int TC_FILTER = 0;  // append scores >= thr[q] to the query's survivor segment
 constexpr int TC_DENSE = 1;   // write every score to dense[q][col] (first piece, fallback, tests)
 constexpr int TC_MAXES = 2;   // write the max of every 32-column group to dense[q][col/32] (seed sample)
+
+// Work unit u -> (query tile m, group g).  Units of one group are consecutive (so the CTAs in
+// flight share its row tiles through L2), but the query tile is rotated by a per-group hash:
+// without it a CTA that takes every gridDim-th unit would only ever see the query tiles of one
+// residue class mod gcd(gridDim, num_m), and those queries' survivors would pile up in a few
+// (query, CTA) segments instead of spreading over all of them.
+__device__ __forceinline__ void unit_to_tile(int u, int num_m, int& m, int& g) {
+    g = u / num_m;
+    const int j = u - g * num_m;
+    const uint32_t rot = (uint32_t(g) * 2654435761u) >> 12;
+    m = int((uint32_t(j) + rot) % uint32_t(num_m));
+}
+
+// One 128 x 256 score tile, seen by one epilogue thread (= one query = TMEM lane): `taddr` is
+// the accumulator stage at this warp's lane quadrant.  Shared by the 1-CTA and 2-CTA scans.
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue_tile(const ScanParams& p, uint32_t taddr, int qrow, bool qvalid,
+                                                 float thr, uint64_t* dst, int& cnt, int n, int valid_n) {
+    float v[32];
+    if (MODE == TC_MAXES) {
+        // seed sample: only whole tiles are sampled, so every column is valid
+        float mxs[TC_BN / 32];
+#pragma unroll
+        for (int b = 0; b < TC_BN / 32; ++b) {
+            tmem_ld32(taddr + uint32_t(b * 32), v);
+            float mx = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            mxs[b] = mx;
+        }
+        if (qvalid) {
+            float4* o = reinterpret_cast<float4*>(p.dense + size_t(qrow) * p.dense_ld + size_t(n) * (TC_BN / 32));
+            o[0] = make_float4(mxs[0], mxs[1], mxs[2], mxs[3]);
+            o[1] = make_float4(mxs[4], mxs[5], mxs[6], mxs[7]);
+        }
+    } else if (MODE == TC_DENSE) {
+#pragma unroll 1
+        for (int b = 0; b < TC_BN / 32; ++b) {
+            tmem_ld32(taddr + uint32_t(b * 32), v);
+            if (qvalid) {
+                float* o = p.dense + size_t(qrow) * p.dense_ld + size_t(n) * TC_BN + b * 32;
+                if (b * 32 + 32 <= valid_n && (p.dense_ld & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (b * 32 + j < valid_n) o[j] = v[j];
+                }
+            }
+        }
+    } else {
+        const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * uint32_t(TC_BN * p.tile_stride);
+#pragma unroll 1
+        for (int b = 0; b < TC_BN / 32; ++b) {
+            tmem_ld32(taddr + uint32_t(b * 32), v);
+            float mx = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            if (__any_sync(0xffffffffu, mx >= thr)) {
+                // rare: append this thread's survivors to its private segment
+                const int lim = valid_n - b * 32;  // >= 32 except on the chunk's last tile
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const bool hit = (v[j] >= thr) && (j < lim);
+                    if (hit && cnt < p.seg_cap) dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
+                    cnt += hit ? 1 : 0;
+                }
+            }
+        }
+    }
+}
 
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -128,7 +201,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (u >= num_units) break;
             if (lane == 0) u_next = atomicAdd(p.unit_ctr, 1);   // latency hidden behind this unit's loads
-            const int m = u % num_m, g = u / num_m;
+            int m, g;
+            unit_to_tile(u, num_m, m, g);
             const int n_end = min(num_n, (g + 1) * p.run_len);
             const int crd_q = m * TC_BM;
             for (int n = g * p.run_len; n < n_end; ++n) {
@@ -217,7 +291,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uphase ^= 1;
             }
             if (u < 0) break;
-            const int m = u % num_m, g = u / num_m;
+            int m, g;
+            unit_to_tile(u, num_m, m, g);
             const int n_end = min(num_n, (g + 1) * p.run_len);
             const int qrow = m * TC_BM + qd * 32 + lane;
             const bool qvalid = qrow < p.nq;
@@ -237,60 +312,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + as * uint32_t(TC_BN);
                 mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
                 tc_fence_after();
-                float v[32];
-                if (MODE == TC_MAXES) {
-                    // seed sample: only whole tiles are sampled, so every column is valid
-                    float mxs[TC_BN / 32];
-#pragma unroll
-                    for (int b = 0; b < TC_BN / 32; ++b) {
-                        tmem_ld32(taddr + uint32_t(b * 32), v);
-                        float mx = v[0];
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                        mxs[b] = mx;
-                    }
-                    if (qvalid) {
-                        float4* o = reinterpret_cast<float4*>(p.dense + size_t(qrow) * p.dense_ld + size_t(n) * (TC_BN / 32));
-                        o[0] = make_float4(mxs[0], mxs[1], mxs[2], mxs[3]);
-                        o[1] = make_float4(mxs[4], mxs[5], mxs[6], mxs[7]);
-                    }
-                } else if (MODE == TC_DENSE) {
-#pragma unroll 1
-                    for (int b = 0; b < TC_BN / 32; ++b) {
-                        tmem_ld32(taddr + uint32_t(b * 32), v);
-                        if (qvalid) {
-                            float* o = p.dense + size_t(qrow) * p.dense_ld + size_t(n) * TC_BN + b * 32;
-                            if (b * 32 + 32 <= valid_n && (p.dense_ld & 3) == 0) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4)
-                                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (b * 32 + j < valid_n) o[j] = v[j];
-                            }
-                        }
-                    }
-                } else {
-                    const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * uint32_t(TC_BN * p.tile_stride);
-#pragma unroll 1
-                    for (int b = 0; b < TC_BN / 32; ++b) {
-                        tmem_ld32(taddr + uint32_t(b * 32), v);
-                        float mx = v[0];
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                        if (__any_sync(0xffffffffu, mx >= thr)) {
-                            // rare: append this thread's survivors to its private segment
-                            const int lim = valid_n - b * 32;  // >= 32 except on the chunk's last tile
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const bool hit = (v[j] >= thr) && (j < lim);
-                                if (hit && cnt < p.seg_cap) dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
-                                cnt += hit ? 1 : 0;
-                            }
-                        }
-                    }
-                }
+                tc_epilogue_tile<MODE>(p, taddr, qrow, qvalid, thr, dst, cnt, n, valid_n);
                 // accumulator stage drained: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();

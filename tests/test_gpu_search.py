@@ -491,3 +491,22 @@ def test_bf16_scan_overlap_is_one(cldrd_lib):
         res[scan] = gpu.search(xq, 1000)
         gpu.close()
     assert np.array_equal(res["bf16"][1], res["tf32"][1]) and np.array_equal(res["bf16"][0], res["tf32"][0])
+
+
+@pytest.mark.parametrize("nq", [4700, 8192])
+def test_query_tile_counts_that_share_factors_with_the_grid(cldrd_lib, nq):
+    """37 and 64 query tiles share factors with the 148-CTA grid: without the per-group rotation of
+    the work units a CTA would only ever see some query tiles and their survivors would overflow a
+    few (query, CTA) segments.  Checked against the SIMT scan (bit-equal) and: no fallback."""
+    rng = np.random.Generator(np.random.PCG64(500))
+    xb = rng.standard_normal((1_200_000, 64), dtype=np.float32)
+    xq = rng.standard_normal((nq, 64), dtype=np.float32)
+    gpu = _gpu_index(xb, None, "f16")
+    D, I = gpu.search(xq, 100)
+    st = gpu.last_stats()
+    gpu.close()
+    assert st["fallback_queries"] <= 2, st      # only genuine seed misses, if any
+    ref = _gpu_index(xb, None, "simt")
+    D0, I0 = ref.search(xq[:512], 100)
+    ref.close()
+    assert np.array_equal(D[:512], D0) and np.array_equal(I[:512], I0)

@@ -15,7 +15,7 @@ def main():
     ap.add_argument("--rows", type=int, default=8_841_823)
     ap.add_argument("--queries", type=int, default=6980)
     ap.add_argument("--k", type=int, default=1000)
-    ap.add_argument("--settings", default="0:0:1,0:0:4,0:0:1,0:0:4,0:0:2")
+    ap.add_argument("--settings", default="0:0:0:0,0:0:0:1,0:0:0:0,0:0:0:1")
     args = ap.parse_args()
     import torch
     from cldrd import dist as CD
@@ -26,7 +26,8 @@ def main():
         rows[r0:r0 + (1 << 20)].normal_(generator=g)
     q = torch.randn((args.queries, 768), generator=g, dtype=torch.float32, device=dev)
     for setting in args.settings.split(","):
-        rl, gr, ch = (setting.split(":") + ["0"])[:3]
+        rl, gr, ch, tc2 = (setting.split(":") + ["0", "0"])[:4]
+        os.environ["CLDRD_TC2"] = tc2
         os.environ["CLDRD_RUN_LEN"] = rl
         os.environ["CLDRD_GROWTH"] = gr
         os.environ["CLDRD_SEED_CHUNKS"] = ch
@@ -45,7 +46,7 @@ def main():
                 best = (tot, ms, s.shard.scan_launches(), s.shard.stats())
         tot, ms, launches, st = best
         per = " ".join(f"{r}:{t:.2f}ms({2 * args.queries * r * 768 / t / 1e9:.0f}TF)" for r, t in launches[:12])
-        print(f"run_len={rl} growth={gr} seed_chunks={ch}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
+        print(f"run_len={rl} growth={gr} seed_chunks={ch} tc2={tc2}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
               f"({2 * args.queries * args.rows * 768 / ms / 1e9:.0f} TF) surv/q {st['survivors'] / args.queries:.0f} | {per}",
               flush=True)
         s.shard.close()
