@@ -212,9 +212,9 @@ def main():
         step_dev()
     shard.set_profiling(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
     if sampler:
-        sampler.start()
+        sampler.start()      # before the barrier: spawning nvidia-smi must not delay rank 0 inside the timed region
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms_total, scan_launches, launches = 0.0, 0, 0
     e0.record()
@@ -287,6 +287,7 @@ def main():
         cpu_baseline = CB.time_cpu_search(n_rows, d, k, sample_rows, sq)
         cpu_baseline.pop("seconds", None)
 
+    phase_ms = getattr(searcher, "last_phase_ms", None)
     if rank == 0:
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -310,6 +311,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        if phase_ms:
+            line["phase_ms_last_step"] = phase_ms
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

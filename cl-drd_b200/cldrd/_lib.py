@@ -60,6 +60,7 @@ SIGNATURES = {
     "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cldrd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "cldrd_host_free": (None, [C.c_void_p]),
+    "cldrd_merge_w": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),
     "cldrd_shard_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -13,6 +13,7 @@ the index.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -42,18 +43,20 @@ def gather_candidates(D_local: torch.Tensor, I_local: torch.Tensor, dst: int = 0
     return None, None
 
 
-def merge_candidates(allD: torch.Tensor, allI: torch.Tensor, id_map: Optional[torch.Tensor] = None
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[P,nq,k] scores + global rows (CUDA) -> merged [nq,k] via the libcldrd merge kernel."""
+def merge_candidates(allD: torch.Tensor, allI: torch.Tensor, id_map: Optional[torch.Tensor] = None,
+                     k: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[P,nq,w] scores + global rows (CUDA, -1 padded) -> merged [nq,k] via the libcldrd merge kernel
+    (k defaults to w)."""
     assert allD.is_cuda and allD.dim() == 3 and allI.shape == allD.shape
-    P, n, k = allD.shape
+    P, n, w = allD.shape
+    k = w if k is None else int(k)
     allD, allI = allD.contiguous(), allI.contiguous()
     outD = torch.empty((n, k), dtype=torch.float32, device=allD.device)
     outI = torch.empty((n, k), dtype=torch.int64, device=allD.device)
     st = torch.cuda.current_stream(allD.device).cuda_stream
-    check(lib().cldrd_merge(allD.device.index, C.c_void_p(allD.data_ptr()), C.c_void_p(allI.data_ptr()), P, n, k,
-                            C.c_void_p(id_map.data_ptr()) if id_map is not None else None,
-                            C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()), C.c_void_p(st)))
+    check(lib().cldrd_merge_w(allD.device.index, C.c_void_p(allD.data_ptr()), C.c_void_p(allI.data_ptr()), P, n, w, k,
+                              C.c_void_p(id_map.data_ptr()) if id_map is not None else None,
+                              C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()), C.c_void_p(st)))
     return outD, outI
 
 
@@ -134,6 +137,18 @@ class ShardedSearcher:
                                             C.c_void_p(seed.data_ptr()), C.c_void_p(st)))
         return seed
 
+    def _trim(self, D: torch.Tensor, I: torch.Tensor):
+        """A seeded shard returns far fewer than k valid rows per query (about 3.5k / world): agree
+        on the widest valid prefix over all ranks (one scalar all-reduce) and gather only that."""
+        if D.shape[0] == 0:
+            return D, I
+        w = (I >= 0).sum(dim=1).max().reshape(1)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX, group=self.group)
+        w = max(1, min(D.shape[1], (int(w.item()) + 63) // 64 * 64))
+        if w == D.shape[1]:
+            return D, I
+        return D[:, :w].contiguous(), I[:, :w].contiguous()
+
     def search(self, q: torch.Tensor, k: int):
         """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
         if self.world == 1:
@@ -143,34 +158,54 @@ class ShardedSearcher:
             return D, I
         self._sync_norm_bound()
         n = q.shape[0]
+        prof = os.environ.get("CLDRD_DIST_PROFILE") == "1"
+        marks = []
+
+        def mark(name):
+            if prof:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         seeded = self.ntotal >= self.SEED_MIN_ROWS and n > 0
         seed = self._seed(q, k) if seeded else None
+        mark("sample+allgather+seed")
         D, I, eps2 = self.local.search_device_seeded(q, k, seed)
+        mark("seeded search")
+        D, I = self._trim(D, I)
         allD, allI = gather_candidates(D, I, dst=0, group=self.group)
+        mark("gather")
         outD = outI = None
         nfail = torch.zeros((1,), dtype=torch.int64, device=q.device)
         fail = torch.zeros((max(n, 1),), dtype=torch.int32, device=q.device)
         if self.rank == 0:
             # rows, not ids, are merged so that a retry can patch the same arrays; ids come last
-            outD, outI = merge_candidates(allD, allI, None)
+            outD, outI = merge_candidates(allD, allI, None, k)
             if seeded:
                 st = torch.cuda.current_stream(q.device).cuda_stream
                 check(lib().cldrd_verify_seed(q.device.index, C.c_void_p(outD.data_ptr()), n, k,
                                               C.c_void_p(seed.data_ptr()), C.c_void_p(eps2.data_ptr()),
                                               C.c_void_p(fail.data_ptr()), C.c_void_p(st)))
                 nfail[0] = fail.sum()
+        mark("merge+verify")
         if seeded:
             dist.broadcast(nfail, src=0, group=self.group)
             if int(nfail.item()) > 0:   # rare: the seed sat above the true k-th score for these queries
                 dist.broadcast(fail, src=0, group=self.group)
                 idx = torch.nonzero(fail[:n]).flatten()
                 D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
+                D2, I2 = self._trim(D2, I2)
                 allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
                 if self.rank == 0:
-                    pD, pI = merge_candidates(allD2, allI2, None)
+                    pD, pI = merge_candidates(allD2, allI2, None, k)
                     outD[idx] = pD
                     outI[idx] = pI
             self.last_seed_misses = int(nfail.item())
+        mark("miss broadcast")
+        if prof:
+            torch.cuda.synchronize()
+            self.last_phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
         if self.rank != 0:
             return None, None
         if self.id_map is not None:

@@ -369,6 +369,8 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
             return CLDRD_OK;
         }
         CU_TRY(cudaMemsetAsync(s->w_unit_ctr, 0, sizeof(int), c.st));
+        if (mode == TC_FILTER)   // survivor cursors of this launch's segment layout start at zero
+            CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * c.groups * sizeof(int), c.st));
 #define LAUNCH_TC(KIND)                                                                                   \
     do {                                                                                                  \
         if (mode == TC_DENSE)                                                                             \
@@ -403,6 +405,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
             return CLDRD_OK;
         }
         const bool vec = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
+        if (!dense) CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * c.groups * sizeof(int), c.st));
         if (dense) {
             if (vec) scan_simt_kernel<true, true><<<grid, 256, 0, c.st>>>(p);
             else scan_simt_kernel<true, false><<<grid, 256, 0, c.st>>>(p);
@@ -470,7 +473,6 @@ int launch_prep(BatchCtx& c) {
     p.list_len = s->w_list_len;
     p.fail = s->w_fail;
     p.stats = s->w_stats;
-    CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, kSegCntInts * sizeof(int), c.st));
     const int threads = 256;
     const int blocks = (c.nq * 32 + threads - 1) / threads;
     query_prep_kernel<<<blocks, threads, 0, c.st>>>(p);
@@ -1178,21 +1180,28 @@ void cldrd_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t k,
-                const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
-    if (parts < 1 || nq < 0 || k < 1 || k > CLDRD_MAX_K || (nq && (!scores_dev || !rows_dev || !out_scores_dev || !out_ids_dev)))
+int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t w,
+                  int32_t k, const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    if (parts < 1 || nq < 0 || w < 1 || k < 1 || k > CLDRD_MAX_K ||
+        (nq && (!scores_dev || !rows_dev || !out_scores_dev || !out_ids_dev)))
         return fail(CLDRD_EINVAL, "merge: bad argument");
     if (nq == 0) return CLDRD_OK;
-    int n_pad = 2;
-    while (n_pad < parts * k) n_pad <<= 1;
-    const size_t smem = size_t(n_pad) * 8;
-    if (smem > 200 * 1024) return fail(CLDRD_EINVAL, "merge: parts*k=%d too large", parts * k);
+    int k_pad = 2;
+    while (k_pad < k) k_pad <<= 1;
+    const size_t smem = (size_t(parts) * w + size_t(k_pad)) * 8;
+    if (smem > 200 * 1024) return fail(CLDRD_EINVAL, "merge: parts*w=%d too large", parts * w);
     DeviceGuard g(device);
     CU_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     merge_kernel<<<unsigned(nq), 512, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        scores_dev, rows_dev, parts, nq, k, n_pad, id_map_dev, out_scores_dev, out_ids_dev);
+        scores_dev, rows_dev, parts, nq, w, k, k_pad, id_map_dev, out_scores_dev, out_ids_dev);
     CU_TRY(cudaGetLastError());
     return CLDRD_OK;
+}
+
+int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t k,
+                const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    return cldrd_merge_w(device, scores_dev, rows_dev, parts, nq, k, k, id_map_dev, out_scores_dev, out_ids_dev,
+                         cuda_stream);
 }
 
 int cldrd_shard_set_profiling(cldrd_shard* s, int32_t on) {

@@ -321,34 +321,56 @@ __global__ void __launch_bounds__(512) rescore_sort_kernel(RescoreParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Multi-shard merge: [parts][nq][k] (score, global row) -> [nq][k], same key order, so the
-// result is bit-identical to a single-shard search.  One CTA per query.
-// dyn smem: keys[n_pad] u64
+// Multi-shard merge: [parts][nq][w] (score, global row; -1 = padding) -> [nq][k], same key order
+// as the single-shard search, so the result is bit-identical to it.  One CTA per query:
+// compact the valid entries, radix-select the k-th key, sort only the k survivors.
+// dyn smem: keys[parts*w] u64 | top[k_pad] u64
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) merge_kernel(const float* scores, const int64_t* rows,
-                                                    int parts, int64_t nq, int k, int n_pad,
+                                                    int parts, int64_t nq, int w, int k, int k_pad,
                                                     const int64_t* id_map, float* out_scores,
                                                     int64_t* out_ids) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    uint64_t* top = keys + size_t(parts) * w;
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t bcast[2];
+    __shared__ int s_n, s_out;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n = parts * k;
-    for (int i = tid; i < n_pad; i += blockDim.x) {
-        uint64_t key = 0;
-        if (i < n) {
-            int part = i / k, j = i - part * k;
-            size_t off = (size_t(part) * nq + q) * k + j;
-            int64_t r = rows[off];
-            if (r >= 0) key = make_key(scores[off], uint32_t(r));
-        }
-        keys[i] = key;
+    const int n_in = parts * w;
+    if (tid == 0) {
+        s_n = 0;
+        s_out = 0;
     }
-    block_bitonic_desc(keys, n_pad);
+    for (int i = tid; i < k_pad; i += blockDim.x) top[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_in; i += blockDim.x) {
+        const int part = i / w, j = i - part * w;
+        const size_t off = (size_t(part) * nq + q) * w + j;
+        const int64_t r = rows[off];
+        if (r >= 0) keys[atomicAdd(&s_n, 1)] = make_key(scores[off], uint32_t(r));
+    }
+    __syncthreads();
+    const int n = s_n;
+    int m = n;                                  // how many go to the sort
+    if (n > k) {
+        const uint64_t kth = block_radix_select<64>(keys, n, k, hist, bcast);   // keys are distinct
+        for (int i = tid; i < n; i += blockDim.x) {
+            const uint64_t key = keys[i];
+            if (key >= kth) top[atomicAdd(&s_out, 1)] = key;
+        }
+        m = k;
+    } else {
+        for (int i = tid; i < n; i += blockDim.x) top[i] = keys[i];
+    }
+    int n_pad = 2;
+    while (n_pad < m) n_pad <<= 1;
+    block_bitonic_desc(top, n_pad);
     for (int i = tid; i < k; i += blockDim.x) {
-        uint64_t key = keys[i];
+        const uint64_t key = i < m ? top[i] : 0ull;
         if (key != 0) {
-            uint32_t row = key_row(key);
+            const uint32_t row = key_row(key);
             out_scores[q * k + i] = ord2f(key_ord(key));
             out_ids[q * k + i] = id_map ? id_map[row] : int64_t(row);
         } else {

@@ -177,6 +177,11 @@ void cldrd_host_free(void* p);
 int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
                 int64_t nq, int32_t k, const int64_t* id_map_dev, float* out_scores_dev,
                 int64_t* out_ids_dev, void* cuda_stream);
+/* Same with input lists of width w != k ([parts][nq][w]): a seeded sharded search returns far
+ * fewer than k valid rows per shard, so callers gather only the first w columns. */
+int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
+                  int64_t nq, int32_t w, int32_t k, const int64_t* id_map_dev,
+                  float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 
 /* Per-search statistics of the last cldrd_search_* call on this shard (for tests / bench):
  * stats[0] kernel launches, [1] index chunks scanned, [2] queries sent to the dense fallback,
