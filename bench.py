@@ -268,9 +268,18 @@ def main():
     achieved_gbs = scan_bytes * args.steps / max(scan_s, 1e-9) / 1e9
     # worst rank bounds the job
     achieved_tf = -max_over_ranks(-achieved_tf)
+    # DRAM traffic of the dominant launch from the committed ncu capture (same kernel, same shape);
+    # only meaningful for the configuration that was captured: 1 GPU, f16 scan, full workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    if world == 1 and shard.scan == "f16" and n_rows == N_ROWS and nq == N_QUERIES and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tflops"], "traffic": None,
-                "kernel": f"scan_tc_kernel<{shard.scan}> (filter + dense first chunk)",
+                "frac": achieved_tf / peaks["tflops"], "traffic": traffic,
+                "traffic_note": "dram read+write bytes of the full-index scan launch, ncu --set full (profiles/r01_scan_traffic.json); "
+                                "algorithmic bytes of that launch: %d" % (n_rows * d * (2 if shard.scan in ("f16", "bf16") else 4)),
+                "kernel": f"scan_tc_kernel<{shard.scan}> (seed-sample launch + full-index filter launch per step)",
                 "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['source']})",
                 "flops_per_step_per_gpu": flops_step_shard, "scan_launches": scan_launches,
                 "scan_ms_per_step": scan_ms_total / args.steps,
