@@ -35,8 +35,8 @@ constexpr int kDensePiece = 8192;   // rows per dense piece (first chunk and fal
 constexpr int kSurvCap = 8192;      // survivors one select CTA can take in per chunk (shared memory)
 constexpr size_t kSurvTotal = size_t(kQueryBatch) * 32768;  // survivor-buffer entries (all queries), 2 GiB
 constexpr int kMaxQStride = 65536;  // survivor slice per query when the batch is small
-constexpr int kMaxGroups = 512;     // segments per query slice (select kernel's scan width) >= #SMs
-constexpr size_t kSegCntInts = size_t(kQueryBatch) * kMaxGroups;
+constexpr int kMaxGroups = 511;     // segments per query slice (+1 pool slot = select kernel's scan width)
+constexpr size_t kSegCntInts = size_t(kQueryBatch) * (kMaxGroups + 1);
 constexpr int64_t kSeedMinRows = 1 << 20;  // below this the progressive scheme is already cheap
 constexpr int kMaxRunLen = 16;      // row tiles per work unit: short runs keep the CTAs in flight
                                     // inside a window of index rows that stays hot in L2
@@ -272,7 +272,7 @@ struct BatchCtx {
     int64_t launches = 0;
     int64_t chunks = 0;
     // survivor-buffer plan of the current chunk (scan writes it, select reads it)
-    int q_stride = 0, seg_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
+    int q_stride = 0, seg_cap = 0, pool_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
     double seed_rank = 0.0;   // expected rank (in the whole index) of the seed threshold
 };
 
@@ -286,7 +286,8 @@ void plan_chunk(BatchCtx& c, int nrows) {
     if (!is_tc(s->scan_eff)) {
         c.groups = 1;
         c.run_len = 1;
-        c.seg_cap = c.q_stride;
+        c.pool_cap = c.q_stride / 4;
+        c.seg_cap = c.q_stride - c.pool_cap;
         c.grid = 0;
         c.seg_by_group = 0;
         return;
@@ -307,7 +308,8 @@ void plan_chunk(BatchCtx& c, int nrows) {
         const int num_groups2 = (num_n + c.run_len - 1) / c.run_len;
         c.seg_by_group = num_groups2 <= clusters ? 1 : 0;
         c.groups = c.seg_by_group ? num_groups2 : clusters;   // one survivor segment per CTA pair
-        c.seg_cap = std::max(1, c.q_stride / c.groups);
+        c.pool_cap = c.q_stride / 4;
+        c.seg_cap = std::max(1, (c.q_stride - c.pool_cap) / c.groups);
         return;
     }
     c.grid = int(std::min<long long>(tiles, std::min(s->num_sms, kMaxGroups)));
@@ -319,7 +321,8 @@ void plan_chunk(BatchCtx& c, int nrows) {
     const int num_groups = (num_n + c.run_len - 1) / c.run_len;
     c.seg_by_group = num_groups <= c.grid ? 1 : 0;
     c.groups = c.seg_by_group ? num_groups : c.grid;   // survivor segments per query
-    c.seg_cap = std::max(1, c.q_stride / c.groups);
+    c.pool_cap = c.q_stride / 4;
+    c.seg_cap = std::max(1, (c.q_stride - c.pool_cap) / c.groups);
 }
 
 cudaEvent_t next_event(cldrd_shard* s) {
@@ -352,6 +355,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
     p.seg_cnt = s->w_seg_cnt;
     p.q_stride = c.q_stride;
     p.seg_cap = c.seg_cap;
+    p.pool_cap = c.pool_cap;
     p.groups = c.groups;
     p.run_len = c.run_len;
     p.seg_by_group = c.seg_by_group;
@@ -370,7 +374,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
         }
         CU_TRY(cudaMemsetAsync(s->w_unit_ctr, 0, sizeof(int), c.st));
         if (mode == TC_FILTER)   // survivor cursors of this launch's segment layout start at zero
-            CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * c.groups * sizeof(int), c.st));
+            CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
 #define LAUNCH_TC(KIND)                                                                                   \
     do {                                                                                                  \
         if (mode == TC_DENSE)                                                                             \
@@ -405,7 +409,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
             return CLDRD_OK;
         }
         const bool vec = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
-        if (!dense) CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * c.groups * sizeof(int), c.st));
+        if (!dense) CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
         if (dense) {
             if (vec) scan_simt_kernel<true, true><<<grid, 256, 0, c.st>>>(p);
             else scan_simt_kernel<true, false><<<grid, 256, 0, c.st>>>(p);
@@ -434,6 +438,7 @@ int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_s
     p.seg_cnt = s->w_seg_cnt;
     p.q_stride = c.q_stride;
     p.seg_cap = c.seg_cap;
+    p.pool_cap = c.pool_cap;
     p.groups = c.groups;
     p.surv_cap = kSurvCap;
     p.dense = dense ? s->w_dense : nullptr;

@@ -17,13 +17,16 @@ struct ScanParams {
     int tile_stride;      // 1 = contiguous chunk; s > 1 = sampled scan: column c reads local row
                           // row_begin + (c / 256) * s * 256 + c % 256   (every s-th 256-row tile)
     // fused filter.  Survivors of query q land in its private slice surv[q*q_stride ..), which
-    // is cut into `groups` segments of seg_cap entries; seg_cnt[q*groups + g] counts segment g
-    // (the count keeps running past seg_cap so that overflow is detectable).
+    // is cut into `groups` single-writer segments of seg_cap entries followed by one shared
+    // overflow pool of pool_cap entries (appended with atomics, only when a segment is full: a
+    // hot row range that one CTA happens to scan).  seg_cnt[q*(groups+1) + g] counts segment g
+    // (it keeps running past seg_cap: the excess went to the pool), slot `groups` counts the pool.
     const float* thr;     // [nq]
     uint64_t* surv;       // [nq][q_stride]
     int* seg_cnt;         // [nq][groups]
     int q_stride;
     int seg_cap;
+    int pool_cap;
     int groups;           // segments per query: SIMT scan 1 (atomic append), TC scan min(#groups, #CTAs)
     int seg_by_group;     // TC scan: segment index = group (1) or CTA (0)
     int run_len;          // TC scan: consecutive row tiles per work unit
@@ -143,9 +146,16 @@ __global__ void __launch_bounds__(256) scan_simt_kernel(ScanParams p) {
             if (DENSE) {
                 p.dense[size_t(qi) * p.dense_ld + col] = v;
             } else if (v >= t) {
-                const int slot = atomicAdd(&p.seg_cnt[qi], 1);
-                if (slot < p.seg_cap)
-                    p.surv[size_t(qi) * p.q_stride + slot] = make_key(v, uint32_t(src0 - n0 + col));
+                const uint64_t key = make_key(v, uint32_t(src0 - n0 + col));
+                int* cnts = p.seg_cnt + size_t(qi) * (p.groups + 1);
+                uint64_t* slice = p.surv + size_t(qi) * p.q_stride;
+                const int slot = atomicAdd(&cnts[0], 1);
+                if (slot < p.seg_cap) {
+                    slice[slot] = key;
+                } else {
+                    const int pos = atomicAdd(&cnts[p.groups], 1);
+                    if (pos < p.pool_cap) slice[size_t(p.groups) * p.seg_cap + pos] = key;
+                }
             }
         }
     }

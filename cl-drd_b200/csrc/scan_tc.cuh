@@ -117,8 +117,17 @@ __device__ __forceinline__ void tc_epilogue_tile(const ScanParams& p, uint32_t t
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const bool hit = (v[j] >= thr) && (j < lim);
-                    if (hit && cnt < p.seg_cap) dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
-                    cnt += hit ? 1 : 0;
+                    if (hit) {
+                        const uint64_t key = make_key(v[j], row0 + uint32_t(b * 32 + j));
+                        if (cnt < p.seg_cap) {
+                            dst[cnt] = key;
+                        } else {   // segment full (hot row range): spill to the query's shared pool
+                            const int pos = atomicAdd(p.seg_cnt + size_t(qrow) * (p.groups + 1) + p.groups, 1);
+                            if (pos < p.pool_cap)
+                                p.surv[size_t(qrow) * p.q_stride + size_t(p.groups) * p.seg_cap + pos] = key;
+                        }
+                        ++cnt;
+                    }
                 }
             }
         }
@@ -302,7 +311,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // CTAs -- every unit then owns a fresh segment -- else (query, this CTA)
             const int seg = p.seg_by_group ? g : int(blockIdx.x);
             uint64_t* dst = MODE != TC_FILTER ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(seg) * p.seg_cap;
-            int* cnt_slot = MODE != TC_FILTER ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * p.groups + seg;
+            int* cnt_slot = MODE != TC_FILTER ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * (p.groups + 1) + seg;
             int cnt = 0;
             if (MODE == TC_FILTER && qvalid) cnt = *cnt_slot;
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {

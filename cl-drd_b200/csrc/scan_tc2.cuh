@@ -320,7 +320,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (MODE == TC_FILTER && qvalid) thr = p.thr[qrow];
             const int seg = p.seg_by_group ? g : int(blockIdx.x >> 1);   // one segment per CTA PAIR: its two CTAs hold different query tiles
             uint64_t* dst = MODE != TC_FILTER ? nullptr : p.surv + size_t(qvalid ? qrow : 0) * p.q_stride + size_t(seg) * p.seg_cap;
-            int* cnt_slot = MODE != TC_FILTER ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * p.groups + seg;
+            int* cnt_slot = MODE != TC_FILTER ? nullptr : p.seg_cnt + size_t(qvalid ? qrow : 0) * (p.groups + 1) + seg;
             int cnt = 0;
             if (MODE == TC_FILTER && qvalid) cnt = *cnt_slot;
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {

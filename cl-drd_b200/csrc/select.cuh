@@ -62,7 +62,8 @@ struct SelectParams {
     int* seg_cnt;          // [nq][groups]     entries written per segment (may exceed seg_cap)
     int q_stride;
     int seg_cap;
-    int groups;            // <= 512
+    int pool_cap;          // shared overflow pool behind the segments (slot `groups`)
+    int groups;            // <= 511
     int surv_cap;          // survivors one CTA can take in (shared-memory space)
     const float* dense;    // [nq][dense_ld]   (dense mode, else nullptr)
     int dense_ld;
@@ -119,13 +120,16 @@ __global__ void __launch_bounds__(512) select_merge_kernel(SelectParams p) {
         n = s_n;
     } else {
         // gather this query's survivor segments: exclusive scan of the segment counts
-        const int G = p.groups;
+        // (slot G = the shared overflow pool; a segment's count above seg_cap means the excess is there)
+        const int G = p.groups + 1;
         int c = 0;
+        bool over = false;
         if (tid < G) {
             c = p.seg_cnt[size_t(q) * G + tid];
-            p.seg_cnt[size_t(q) * G + tid] = 0;   // ready for the next chunk (SIMT scan appends atomically)
+            p.seg_cnt[size_t(q) * G + tid] = 0;   // ready for the next chunk
+            if (tid < G - 1) c = min(c, p.seg_cap);
+            else over = c > p.pool_cap;
         }
-        const bool over = c > p.seg_cap;
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -510,3 +510,21 @@ def test_query_tile_counts_that_share_factors_with_the_grid(cldrd_lib, nq):
     D0, I0 = ref.search(xq[:512], 100)
     ref.close()
     assert np.array_equal(D[:512], D0) and np.array_equal(I[:512], I0)
+
+
+def test_hot_row_range_spills_to_the_pool_not_to_the_fallback(cldrd_lib):
+    """3000 contiguous rows that every query likes (passages of one topic stored together): one CTA
+    scans them in one or two work units and overflows its private survivor segment; the excess
+    must land in the query's shared pool, not send the query to the fallback."""
+    d = 64
+    rng = np.random.Generator(np.random.PCG64(600))
+    xb = rng.standard_normal((1_300_000, d), dtype=np.float32)
+    topic = rng.standard_normal((d,), dtype=np.float32)
+    topic /= np.linalg.norm(topic)
+    xb[500_000:503_000] += 6.0 * topic[None, :]
+    xq = (rng.standard_normal((64, d), dtype=np.float32) + 4.0 * topic[None, :]).astype(np.float32)
+    gpu = _gpu_index(xb, None, "f16")
+    _check(gpu, xb, None, xq, 1000)
+    st = gpu.last_stats()
+    assert st["fallback_queries"] == 0, st
+    gpu.close()
