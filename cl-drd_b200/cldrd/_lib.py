@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcldrd.so")
+LIB_PATH = os.environ.get("CLDRD_LIB_PATH") or os.path.join(_HERE, "libcldrd.so")   # override: A/B of two builds
 
 SCAN_SIMT_F32, SCAN_TC_TF32, SCAN_TC_F16, SCAN_TC_BF16 = 0, 1, 2, 3
 SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "fp16": SCAN_TC_F16,

@@ -64,6 +64,35 @@ __device__ __forceinline__ void unit_to_tile(int u, int num_m, int& m, int& g) {
     m = int((uint32_t(j) + rot) % uint32_t(num_m));
 }
 
+// Rare, warp-uniform path of the filter: some thread's single-writer segment may not have room for
+// 32 more survivors (a hot row range scanned by one CTA), or the tile is the chunk's ragged last
+// one.  Re-reads the 32-column group from TMEM and appends with every check; survivors that do not
+// fit the segment go to the query's shared overflow pool (atomic append).  Out of line so that the
+// common path carries neither the checks nor the register pressure of a call.
+__device__ __noinline__ int filter_group_generic(const ScanParams& p, uint32_t taddr_b, int qrow, float thr,
+                                                 uint32_t row0b, int lim, int cnt, uint64_t* dst) {
+    float v[32];
+    tmem_ld32(taddr_b, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if ((v[j] >= thr) && (j < lim)) {
+            const uint64_t key = make_key(v[j], row0b + uint32_t(j));
+            if (cnt < p.seg_cap) {
+                dst[cnt] = key;
+            } else {
+                const int pos = atomicAdd(p.seg_cnt + size_t(qrow) * (p.groups + 1) + p.groups, 1);
+                if (pos < p.pool_cap) p.surv[size_t(qrow) * p.q_stride + size_t(p.groups) * p.seg_cap + pos] = key;
+            }
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+__device__ __forceinline__ float max8(const float* v) {
+    return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+}
+
 // One 128 x 256 score tile, seen by one epilogue thread (= one query = TMEM lane): `taddr` is
 // the accumulator stage at this warp's lane quadrant.  Shared by the 1-CTA and 2-CTA scans.
 template <int MODE>
@@ -108,25 +137,29 @@ __device__ __forceinline__ void tc_epilogue_tile(const ScanParams& p, uint32_t t
 #pragma unroll 1
         for (int b = 0; b < TC_BN / 32; ++b) {
             tmem_ld32(taddr + uint32_t(b * 32), v);
-            float mx = v[0];
+            float m8[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            for (int s = 0; s < 4; ++s) m8[s] = max8(v + 8 * s);
+            const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
             if (__any_sync(0xffffffffu, mx >= thr)) {
-                // rare: append this thread's survivors to its private segment
-                const int lim = valid_n - b * 32;  // >= 32 except on the chunk's last tile
+                // some thread of the warp has a survivor in this 32-column group
+                const int lim = valid_n - b * 32;   // >= 32 except on the chunk's last tile
+                if (__any_sync(0xffffffffu, cnt + 32 > p.seg_cap) || lim < 32) {
+                    cnt = filter_group_generic(p, taddr + uint32_t(b * 32), qrow, thr, row0 + uint32_t(b * 32), lim, cnt, dst);
+                } else {
+                    // common: room for the whole group, every column valid.  Expand only the 8-column
+                    // sub-groups in which some thread of the warp has a hit.
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const bool hit = (v[j] >= thr) && (j < lim);
-                    if (hit) {
-                        const uint64_t key = make_key(v[j], row0 + uint32_t(b * 32 + j));
-                        if (cnt < p.seg_cap) {
-                            dst[cnt] = key;
-                        } else {   // segment full (hot row range): spill to the query's shared pool
-                            const int pos = atomicAdd(p.seg_cnt + size_t(qrow) * (p.groups + 1) + p.groups, 1);
-                            if (pos < p.pool_cap)
-                                p.surv[size_t(qrow) * p.q_stride + size_t(p.groups) * p.seg_cap + pos] = key;
+                    for (int s = 0; s < 4; ++s) {
+                        if (__any_sync(0xffffffffu, m8[s] >= thr)) {
+#pragma unroll
+                            for (int j = 8 * s; j < 8 * s + 8; ++j) {
+                                if (v[j] >= thr) {
+                                    dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
+                                    ++cnt;
+                                }
+                            }
                         }
-                        ++cnt;
                     }
                 }
             }
