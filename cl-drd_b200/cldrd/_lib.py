@@ -63,6 +63,7 @@ SIGNATURES = {
     "cldrd_merge_w": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),
+    "cldrd_shard_wait_cycles": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),
     "cldrd_shard_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "cldrd_shard_last_scan_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _c_i64p]),
     "cldrd_shard_last_scan_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _c_i64p, C.c_int32]),

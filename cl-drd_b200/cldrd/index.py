@@ -345,6 +345,13 @@ class _Shard:
         check(lib().cldrd_shard_last_scan_time(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def wait_cycles(self, reset: bool = True) -> dict:
+        """MMA-issuer wait breakdown of the profiled filter scans (fractions of the issuer's lifetime)."""
+        arr = (C.c_uint64 * 4)()
+        check(lib().cldrd_shard_wait_cycles(self.handle, arr, 1 if reset else 0))
+        tot = max(int(arr[3]), 1)
+        return {"operands": arr[0] / tot, "tmem_stage": arr[1] / tot, "unit_id": arr[2] / tot, "cycles": int(arr[3])}
+
     def scan_launches(self):
         """[(rows, ms)] of every scan launch of the last search (profiling on)."""
         ms = (C.c_double * 256)()

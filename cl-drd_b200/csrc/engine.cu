@@ -125,7 +125,7 @@ struct cldrd_shard {
     int num_sms = 0;
     CUtensorMap tmB;
     CUtensorMap tmBh;        // half row tile (128 rows) for the 2-CTA scan
-    bool use_tc2 = false;    // CLDRD_TC2=1: cta_group::2 scan kernel
+    bool use_tc2 = true;     // cta_group::2 scan kernel where it pays (CLDRD_TC2=0: always the 1-CTA kernel)
 
     // workspace for one query batch
     int ws_keep_cap = 0;
@@ -137,6 +137,7 @@ struct cldrd_shard {
     float* w_topj = nullptr;      // [Q][CLDRD_SEED_J] sample scores
     int* w_list_len = nullptr;
     int* w_seg_cnt = nullptr;
+    unsigned long long* w_wait = nullptr;   // [4] issuer wait-cycle breakdown of the profiled scans
     int* w_unit_ctr = nullptr;   // [kUnitCtrSlots] work-unit counters, one per scan launch of a pass
     int* w_fail = nullptr;
     int* w_fail_index = nullptr;
@@ -193,6 +194,8 @@ void free_workspace(cldrd_shard* s) {
     cudaFree(s->w_list_len);
     cudaFree(s->w_seg_cnt);
     cudaFree(s->w_unit_ctr);
+    cudaFree(s->w_wait);
+    s->w_wait = nullptr;
     s->w_unit_ctr = nullptr;
     cudaFree(s->w_fail);
     cudaFree(s->w_fail_index);
@@ -228,6 +231,8 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMalloc(&s->w_list_len, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_seg_cnt, kSegCntInts * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_unit_ctr, sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_wait, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(s->w_wait, 0, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
@@ -274,6 +279,7 @@ struct BatchCtx {
     // survivor-buffer plan of the current chunk (scan writes it, select reads it)
     int q_stride = 0, seg_cap = 0, pool_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
     double seed_rank = 0.0;   // expected rank (in the whole index) of the seed threshold
+    bool tc2 = false;         // this launch uses the CTA-pair kernel
 };
 
 // Work-unit plan for one chunk.  The grid is one persistent CTA per SM (fewer when there is less
@@ -295,7 +301,10 @@ void plan_chunk(BatchCtx& c, int nrows) {
     const int num_m = nq_pad / TC_BM;
     const int num_n = std::max(1, (nrows + TC_BN - 1) / TC_BN);
     long long tiles = (long long)num_m * num_n;
-    if (s->use_tc2) {
+    // CTA pairs compute 256-query tiles: they pay when the query tiles pair up without much padding
+    // (a lone 128-query tile would double the tensor work of the HBM-bound small-batch regime)
+    c.tc2 = s->use_tc2 && (num_m >= 8 || (num_m >= 2 && num_m % 2 == 0));
+    if (c.tc2) {
         // CTA pairs: a work unit covers two query tiles; the grid is an even number of CTAs
         tiles = (long long)((num_m + 1) / 2) * num_n;
         const int clusters = int(std::min<long long>(tiles, std::min(s->num_sms, kMaxGroups) / 2));
@@ -360,6 +369,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
     p.run_len = c.run_len;
     p.seg_by_group = c.seg_by_group;
     p.unit_ctr = s->w_unit_ctr;
+    p.wait_cycles = (s->profile && mode == TC_FILTER) ? s->w_wait : nullptr;
     p.dense = s->w_dense;
     p.dense_ld = kDensePiece;
     p.stats = s->w_stats;
@@ -393,7 +403,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
         else                                                                                                  \
             scan_tc2_kernel<KIND, TC_FILTER><<<grid, TC_THREADS, TC2_SMEM_BYTES, c.st>>>(c.tmA, s->tmBh, p);  \
     } while (0)
-        if (s->use_tc2) {
+        if (c.tc2) {
             if (s->scan_eff == CLDRD_SCAN_TC_F16) LAUNCH_TC2(0);
             else if (s->scan_eff == CLDRD_SCAN_TC_BF16) LAUNCH_TC2(1);
             else LAUNCH_TC2(2);
@@ -1230,6 +1240,15 @@ int cldrd_shard_last_scan_launches(const cldrd_shard* s, double* ms, int64_t* ro
         rows[i] = s->ev_rows[i];
     }
     return n;
+}
+
+int cldrd_shard_wait_cycles(cldrd_shard* s, uint64_t out[4], int32_t reset) {
+    if (!s || !out) return fail(CLDRD_EINVAL, "wait_cycles: NULL");
+    DeviceGuard g(s->device);
+    if (!s->w_wait) return fail(CLDRD_ESTATE, "wait_cycles: shard not finalized");
+    CU_TRY(cudaMemcpy(out, s->w_wait, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CU_TRY(cudaMemset(s->w_wait, 0, 4 * sizeof(unsigned long long)));
+    return CLDRD_OK;
 }
 
 int cldrd_shard_last_stats(const cldrd_shard* s, int64_t stats[8]) {

@@ -35,6 +35,7 @@ struct ScanParams {
     float* dense;         // [nq][dense_ld]
     int dense_ld;
     unsigned long long* stats;
+    unsigned long long* wait_cycles;   // TC scan, optional [4]: MMA issuer cycles waiting on operands / TMEM / unit ids, total
     // tensor-core scan only
     int num_kb;           // K blocks of 128 bytes
     int kb_elems;         // elements per K block (64 half, 32 tf32)

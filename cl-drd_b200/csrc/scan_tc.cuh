@@ -134,29 +134,35 @@ __device__ __forceinline__ void tc_epilogue_tile(const ScanParams& p, uint32_t t
         }
     } else {
         const uint32_t row0 = uint32_t(p.row_begin) + uint32_t(n) * uint32_t(TC_BN * p.tile_stride);
+        float w[64];
 #pragma unroll 1
-        for (int b = 0; b < TC_BN / 32; ++b) {
-            tmem_ld32(taddr + uint32_t(b * 32), v);
-            float m8[4];
+        for (int b2 = 0; b2 < TC_BN / 64; ++b2) {
+            tmem_ld64(taddr + uint32_t(b2 * 64), w);       // two 32-column groups per TMEM round trip
 #pragma unroll
-            for (int s = 0; s < 4; ++s) m8[s] = max8(v + 8 * s);
-            const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-            if (__any_sync(0xffffffffu, mx >= thr)) {
-                // some thread of the warp has a survivor in this 32-column group
-                const int lim = valid_n - b * 32;   // >= 32 except on the chunk's last tile
-                if (__any_sync(0xffffffffu, cnt + 32 > p.seg_cap) || lim < 32) {
-                    cnt = filter_group_generic(p, taddr + uint32_t(b * 32), qrow, thr, row0 + uint32_t(b * 32), lim, cnt, dst);
-                } else {
-                    // common: room for the whole group, every column valid.  Expand only the 8-column
-                    // sub-groups in which some thread of the warp has a hit.
+            for (int h = 0; h < 2; ++h) {
+                const int b = 2 * b2 + h;
+                const float* vv = w + 32 * h;
+                float m8[4];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        if (__any_sync(0xffffffffu, m8[s] >= thr)) {
+                for (int s = 0; s < 4; ++s) m8[s] = max8(vv + 8 * s);
+                const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                if (__any_sync(0xffffffffu, mx >= thr)) {
+                    // some thread of the warp has a survivor in this 32-column group
+                    const int lim = valid_n - b * 32;   // >= 32 except on the chunk's last tile
+                    if (__any_sync(0xffffffffu, cnt + 32 > p.seg_cap) || lim < 32) {
+                        cnt = filter_group_generic(p, taddr + uint32_t(b * 32), qrow, thr, row0 + uint32_t(b * 32), lim, cnt, dst);
+                    } else {
+                        // common: room for the whole group, every column valid.  Expand only the
+                        // 8-column sub-groups in which some thread of the warp has a hit.
 #pragma unroll
-                            for (int j = 8 * s; j < 8 * s + 8; ++j) {
-                                if (v[j] >= thr) {
-                                    dst[cnt] = make_key(v[j], row0 + uint32_t(b * 32 + j));
-                                    ++cnt;
+                        for (int s = 0; s < 4; ++s) {
+                            if (__any_sync(0xffffffffu, m8[s] >= thr)) {
+#pragma unroll
+                                for (int j = 8 * s; j < 8 * s + 8; ++j) {
+                                    if (vv[j] >= thr) {
+                                        dst[cnt] = make_key(vv[j], row0 + uint32_t(b * 32 + j));
+                                        ++cnt;
+                                    }
                                 }
                             }
                         }
@@ -275,8 +281,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t it = 0;
         int uq = 0;
         uint32_t uphase = 0;
+        long long t_full = 0, t_tempty = 0, t_unit = 0;     // cycles the issuer spent waiting, by cause
+        const long long t_begin = clock64();
         for (;;) {
+            long long t0 = clock64();
             mbar_wait(&ufull_bar[uq], uphase, err, 600 + uq);
+            t_unit += clock64() - t0;
             const int u = unit_ring[uq];
             __syncwarp();
             if (lane == 0) mbar_arrive(&uempty_bar[uq]);
@@ -290,11 +300,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int n = g * p.run_len; n < n_end; ++n, ++it) {
                 const uint32_t as = it & 1u;
                 const uint32_t aphase = (it >> 1) & 1u;
+                t0 = clock64();
                 mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+                t_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * uint32_t(TC_BN);
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    t0 = clock64();
                     mbar_wait(&full_bar[stage], phase, err, 300 + stage);
+                    t_full += clock64() - t0;
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t a_desc = umma_desc_sw128(smem_u32(smemA + size_t(stage) * TC_A_STAGE));
@@ -315,6 +329,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+        }
+        if (lane == 0 && p.wait_cycles) {
+            atomicAdd(&p.wait_cycles[0], (unsigned long long)t_full);
+            atomicAdd(&p.wait_cycles[1], (unsigned long long)t_tempty);
+            atomicAdd(&p.wait_cycles[2], (unsigned long long)t_unit);
+            atomicAdd(&p.wait_cycles[3], (unsigned long long)(clock64() - t_begin));
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> filter =====================

@@ -198,6 +198,11 @@ int cldrd_shard_last_scan_time(const cldrd_shard* s, double* scan_ms, int64_t* s
  * `cap` launches and returns how many were written. */
 int cldrd_shard_last_scan_launches(const cldrd_shard* s, double* ms, int64_t* rows, int32_t cap);
 
+/* Where the tensor pipe idles: cycles the MMA-issuing thread of the filter scans spent waiting,
+ * summed over CTAs since the last reset (profiling on): out[0] operands (TMA/L2), out[1] the
+ * epilogue handing back a TMEM stage, out[2] the next work-unit id, out[3] issuer lifetime. */
+int cldrd_shard_wait_cycles(cldrd_shard* s, uint64_t out[4], int32_t reset);
+
 /* Debug / test hook: run only the scan kernel in dense mode and return the raw scan scores
  * (approximate for the tensor-core modes) of queries [0,nq) against local rows
  * [row_begin, row_begin+nrows), nrows <= 8192.  out_dev: [nq, nrows] float32. */

@@ -45,6 +45,7 @@ def main():
             if i >= 1 and (best is None or tot < best[0]):
                 best = (tot, ms, s.shard.scan_launches(), s.shard.stats())
         tot, ms, launches, st = best
+        print("   issuer waits:", s.shard.wait_cycles())
         per = " ".join(f"{r}:{t:.2f}ms({2 * args.queries * r * 768 / t / 1e9:.0f}TF)" for r, t in launches[:12])
         print(f"run_len={rl} growth={gr} seed_chunks={ch} tc2={tc2}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
               f"({2 * args.queries * args.rows * 768 / ms / 1e9:.0f} TF) surv/q {st['survivors'] / args.queries:.0f} | {per}",
