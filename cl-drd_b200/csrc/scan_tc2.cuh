@@ -253,8 +253,12 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t it = 0;
             int uq = 0;
             uint32_t uphase = 0;
+            long long t_full = 0, t_tempty = 0, t_unit = 0;   // cycles the issuer spent waiting, by cause
+            const long long t_begin = clock64();
             for (;;) {
+                long long t0 = clock64();
                 mbar_wait(&ufull_bar[uq], uphase, err, 600 + uq);
+                t_unit += clock64() - t0;
                 const int u = unit_ring[uq];
                 __syncwarp();
                 if (lane == 0) release_unit_slot(uq);
@@ -268,11 +272,15 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int n = g * p.run_len; n < n_end; ++n, ++it) {
                     const uint32_t as = it & 1u;
                     const uint32_t aphase = (it >> 1) & 1u;
+                    t0 = clock64();
                     mbar_wait_cluster(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+                    t_tempty += clock64() - t0;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * uint32_t(TC_BN);
                     for (int kb = 0; kb < p.num_kb; ++kb) {
+                        t0 = clock64();
                         mbar_wait_cluster(&full_bar[stage], phase, err, 300 + stage);
+                        t_full += clock64() - t0;
                         tc_fence_after();
                         if (lane == 0) {
                             const uint64_t a_desc = umma_desc_sw128(smem_u32(smemA + size_t(stage) * TC2_A_STAGE));
@@ -291,6 +299,12 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
+            }
+            if (lane == 0 && p.wait_cycles) {
+                atomicAdd(&p.wait_cycles[0], (unsigned long long)t_full);
+                atomicAdd(&p.wait_cycles[1], (unsigned long long)t_tempty);
+                atomicAdd(&p.wait_cycles[2], (unsigned long long)t_unit);
+                atomicAdd(&p.wait_cycles[3], (unsigned long long)(clock64() - t_begin));
             }
         }
     } else {
