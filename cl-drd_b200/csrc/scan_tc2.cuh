@@ -10,6 +10,9 @@
 //   leader only warp 1  MMA issuer; its commits are multicast to both CTAs' empty / tmem-full
 //                       barriers; warp 0 also draws the work units and publishes each id into
 //                       both CTAs' unit rings (remote shared-memory store + remote mbarrier arrive)
+//   waits       plain CTA-scope mbarrier waits everywhere (operands arrive through the async proxy,
+//               accumulators through TMEM) except where a thread reads DATA another CTA stored:
+//               the unit ring in the peer (cluster-scope acquire; it costs an L1 invalidate)
 //   epilogue    identical to the 1-CTA kernel (tc_epilogue_tile); the peer's warps hand the
 //               accumulator stage back with a remote arrive on the leader's tmem-empty barrier
 #pragma once
@@ -199,7 +202,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int u;
             if (leader) {
                 u = __shfl_sync(0xffffffffu, u_next, 0);
-                mbar_wait_cluster(&uempty_bar[uq], uphase ^ 1, err, 500 + uq);
+                mbar_wait(&uempty_bar[uq], uphase ^ 1, err, 500 + uq);
                 if (lane == 0) {
                     const int id = u < num_units ? u : -1;
                     unit_ring[uq] = id;
@@ -228,7 +231,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int n = g * p.run_len; n < n_end; ++n) {
                 const int crd_r = int(p.row_begin) + (n * TC_BN) * p.tile_stride + int(rank) * (TC_BN / 2);
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait_cluster(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+                    mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
                     if (lane == 0) {
                         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);  // both CTAs' bytes
                         tma_load_2d_2sm(smemA + size_t(stage) * TC2_A_STAGE, &tmA, &full_bar[stage], kb * p.kb_elems,
@@ -273,13 +276,13 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t as = it & 1u;
                     const uint32_t aphase = (it >> 1) & 1u;
                     t0 = clock64();
-                    mbar_wait_cluster(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+                    mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
                     t_tempty += clock64() - t0;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * uint32_t(TC_BN);
                     for (int kb = 0; kb < p.num_kb; ++kb) {
                         t0 = clock64();
-                        mbar_wait_cluster(&full_bar[stage], phase, err, 300 + stage);
+                        mbar_wait(&full_bar[stage], phase, err, 300 + stage);
                         t_full += clock64() - t0;
                         tc_fence_after();
                         if (lane == 0) {
@@ -342,7 +345,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t aphase = (it >> 1) & 1u;
                 const int valid_n = min(TC_BN, p.nrows - n * TC_BN);
                 const uint32_t taddr = tmem_base + (uint32_t(qd * 32) << 16) + as * uint32_t(TC_BN);
-                mbar_wait_cluster(&tfull_bar[as], aphase, err, 400 + as);
+                mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
                 tc_fence_after();
                 tc_epilogue_tile<MODE>(p, taddr, qrow, qvalid, thr, dst, cnt, n, valid_n);
                 tc_fence_before();
