@@ -279,7 +279,7 @@ def main():
                 "frac": achieved_tf / peaks["tflops"], "traffic": traffic,
                 "traffic_note": "dram read+write bytes of the full-index scan launch, ncu --set full (profiles/r01_scan_traffic.json); "
                                 "algorithmic bytes of that launch: %d" % (n_rows * d * (2 if shard.scan in ("f16", "bf16") else 4)),
-                "kernel": f"scan_tc_kernel<{shard.scan}> (seed-sample launch + full-index filter launch per step)",
+                "kernel": f"scan_tc2_kernel<{shard.scan}> (cta_group::2; seed-sample launch + full-index filter launch per step)",
                 "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['source']})",
                 "flops_per_step_per_gpu": flops_step_shard, "scan_launches": scan_launches,
                 "scan_ms_per_step": scan_ms_total / args.steps,

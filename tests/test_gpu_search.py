@@ -528,3 +528,39 @@ def test_hot_row_range_spills_to_the_pool_not_to_the_fallback(cldrd_lib):
     st = gpu.last_stats()
     assert st["fallback_queries"] == 0, st
     gpu.close()
+
+
+@pytest.mark.parametrize("scan", ["tf32", "f16", "bf16"])
+def test_error_bound_holds_on_heavy_tailed_values(cldrd_lib, scan):
+    """The filter band is a worst-case bound c*|q|*|b|: check it on values with a huge dynamic range
+    (log-normal magnitudes, random signs, exact cancellations), not just on N(0,1)."""
+    import torch
+    from cldrd._lib import check
+    rng = np.random.Generator(np.random.PCG64(700))
+    d = 1024
+
+    def heavy(n):
+        mag = np.exp(rng.normal(0.0, 2.5, size=(n, d))).astype(np.float32)
+        return (mag * rng.choice([-1.0, 1.0], size=(n, d))).astype(np.float32)
+
+    xb, xq = heavy(2048), heavy(256)
+    xb[:64, 1::2] = -xb[:64, 0::2]          # pairs that cancel exactly
+    xq[:32, 1::2] = xq[:32, 0::2]
+    xb = np.clip(xb, -6e4, 6e4)             # stay inside fp16
+    gpu = _gpu_index(xb, None, scan)
+    q = torch.from_numpy(xq).cuda()
+    out = torch.empty((256, 2048), dtype=torch.float32, device="cuda")
+    check(cldrd_lib.cldrd_scan_dense_dev(gpu._shard.handle, C.c_void_p(q.data_ptr()), 256, 0, 2048, C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    ref = xq.astype(np.float64) @ xb.astype(np.float64).T
+    scale = np.linalg.norm(xq.astype(np.float64), axis=1)[:, None] * np.linalg.norm(xb.astype(np.float64), axis=1)[None, :]
+    rel = np.abs(got - ref) / scale
+    coef = {"tf32": 2.0 ** -9, "f16": 2.0 ** -10, "bf16": 2.0 ** -7}[scan] + 2.2 * d * 2.0 ** -23
+    assert rel.max() <= coef, (scan, rel.max(), coef)
+    # and the search on such data is still exact
+    D, I = gpu.search(xq[:40], 50)
+    D_ref, I_ref = O.search(xb, None, xq[:40], 50)
+    r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, None, xq[:40], 66, dtype=np.float64), rel_tol=1e-4)
+    assert r["bad_ids"] == 0, r
+    gpu.close()
