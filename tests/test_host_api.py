@@ -162,11 +162,12 @@ def test_reference_retrieval_utils_imports_against_our_faiss(cldrd_lib):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
-        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import sys; sys.path[:0]=[%r,%r]\n"
         "import faiss, retriever.retrieval_utils as ru\n"
+        "assert ru.__file__.startswith(%r), ru.__file__\n"
         "assert faiss.__version__=='cldrd-b200'\n"
         "assert callable(ru.index_retrieve) and callable(ru.convert_index_to_gpu)\n"
         "idx=faiss.IndexIDMap(faiss.IndexFlatIP(8)); print('ok', idx.ntotal)\n"
-    ) % (os.path.join(root, "cl-drd_b200", "compat"), os.path.join(root, "cl-drd_b200"), REF)
+    ) % (os.path.join(root, "cl-drd_b200", "compat"), REF, REF)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REF, timeout=300)
     assert r.returncode == 0 and "ok 0" in r.stdout, r.stderr[-2000:]
