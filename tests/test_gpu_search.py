@@ -564,3 +564,35 @@ def test_error_bound_holds_on_heavy_tailed_values(cldrd_lib, scan):
     r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, None, xq[:40], 66, dtype=np.float64), rel_tol=1e-4)
     assert r["bad_ids"] == 0, r
     gpu.close()
+
+
+def test_sharded_searcher_from_file_and_in_process_shards_from_file(cldrd_lib, tmp_path):
+    """File-backed paths: ShardedSearcher.from_file (each rank preads its own row range) and
+    index_cpu_to_gpu_multiple on a lazily read index (two shards, rows streamed file -> HBM)."""
+    import torch
+    import cldrd
+    from cldrd import dist as CD
+    xb, xq, ids = O.synth(30_001, 96, 800), O.synth(77, 96, 801), O.synth_ids(30_001, 802) + 10 ** 10
+    path = tmp_path / "ckpt.index"
+    O.write_index(str(path), xb, ids)
+    D_ref, I_ref = O.search(xb, ids, xq, 64)
+    ext = O.search(xb, ids, xq, 80, dtype=np.float64)
+    s = CD.ShardedSearcher.from_file(str(path), device=0, scan="f16")
+    assert s.ntotal == 30_001 and s.id_map is not None
+    D, I = s.search(torch.from_numpy(xq).cuda(), 64)
+    r = O.compare_topk(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, *ext)
+    assert r["ok"], r
+    host = cldrd.read_index(str(path))
+    assert host._rows.file is not None
+    vres, vdev = cldrd.GpuResourcesVector(), cldrd.IntVector()
+    for _ in range(2):
+        vres.push_back(cldrd.StandardGpuResources())
+        vdev.push_back(0)                      # two shards on the same device: exercises the merge path
+    co = cldrd.GpuMultipleClonerOptions()
+    co.shard = True
+    multi = cldrd.index_cpu_to_gpu_multiple(vres, vdev, host, co)
+    D2, I2 = multi.search(xq, 64)
+    r = O.compare_topk(D2, I2, D_ref, I_ref, *ext)
+    assert r["ok"], r
+    assert np.array_equal(D2, D.cpu().numpy()) and np.array_equal(I2, I.cpu().numpy())
+    multi.close()
