@@ -174,26 +174,49 @@ class ShardedSearcher:
         D, I, eps2 = self.local.search_device_seeded(q, k, seed)
         mark("seeded search")
         D, I = self._trim(D, I)
-        allD, allI = gather_candidates(D, I, dst=0, group=self.group)
-        mark("gather")
-        outD = outI = None
+        # Distributed merge: all-to-all so that rank j receives every shard's lists for the j-th
+        # slice of the queries, merges and verifies that slice, and only the merged [slice, k]
+        # results travel to rank 0.  (A plain gather would make rank 0 receive and merge everything.)
+        world, W = self.world, D.shape[1]
+        sl = (n + world - 1) // world
+        n_pad = sl * world
+        if n_pad != n:
+            D = torch.cat([D, D.new_full((n_pad - n, W), -3.4028234663852886e38)])
+            I = torch.cat([I, I.new_full((n_pad - n, W), -1)])
+        recvD, recvI = torch.empty_like(D), torch.empty_like(I)
+        dist.all_to_all_single(recvD, D, group=self.group)
+        dist.all_to_all_single(recvI, I, group=self.group)
+        mark("all-to-all")
+        mD, mI = merge_candidates(recvD.view(world, sl, W), recvI.view(world, sl, W), None, k)
         nfail = torch.zeros((1,), dtype=torch.int64, device=q.device)
-        fail = torch.zeros((max(n, 1),), dtype=torch.int32, device=q.device)
-        if self.rank == 0:
-            # rows, not ids, are merged so that a retry can patch the same arrays; ids come last
-            outD, outI = merge_candidates(allD, allI, None, k)
-            if seeded:
-                st = torch.cuda.current_stream(q.device).cuda_stream
-                check(lib().cldrd_verify_seed(q.device.index, C.c_void_p(outD.data_ptr()), n, k,
-                                              C.c_void_p(seed.data_ptr()), C.c_void_p(eps2.data_ptr()),
-                                              C.c_void_p(fail.data_ptr()), C.c_void_p(st)))
-                nfail[0] = fail.sum()
+        fail_sl = torch.zeros((sl,), dtype=torch.int32, device=q.device)
+        lo = self.rank * sl
+        n_mine = max(0, min(sl, n - lo))
+        if seeded and n_mine > 0:
+            st = torch.cuda.current_stream(q.device).cuda_stream
+            check(lib().cldrd_verify_seed(q.device.index, C.c_void_p(mD.data_ptr()), n_mine, k,
+                                          C.c_void_p(seed[lo:lo + n_mine].contiguous().data_ptr()),
+                                          C.c_void_p(eps2[lo:lo + n_mine].contiguous().data_ptr()),
+                                          C.c_void_p(fail_sl.data_ptr()), C.c_void_p(st)))
+            nfail[0] = fail_sl[:n_mine].sum()
         mark("merge+verify")
+        outD = outI = None
+        if self.rank == 0:
+            allD = torch.empty((world, sl, k), dtype=mD.dtype, device=q.device)
+            allI = torch.empty((world, sl, k), dtype=mI.dtype, device=q.device)
+            dist.gather(mD, list(allD.unbind(0)), dst=0, group=self.group)
+            dist.gather(mI, list(allI.unbind(0)), dst=0, group=self.group)
+            outD, outI = allD.view(n_pad, k)[:n], allI.view(n_pad, k)[:n]
+        else:
+            dist.gather(mD, None, dst=0, group=self.group)
+            dist.gather(mI, None, dst=0, group=self.group)
+        mark("gather")
         if seeded:
-            dist.broadcast(nfail, src=0, group=self.group)
+            dist.all_reduce(nfail, op=dist.ReduceOp.SUM, group=self.group)
             if int(nfail.item()) > 0:   # rare: the seed sat above the true k-th score for these queries
-                dist.broadcast(fail, src=0, group=self.group)
-                idx = torch.nonzero(fail[:n]).flatten()
+                fail_all = torch.empty((world, sl), dtype=torch.int32, device=q.device)
+                dist.all_gather_into_tensor(fail_all, fail_sl, group=self.group)
+                idx = torch.nonzero(fail_all.view(-1)[:n]).flatten()
                 D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
                 D2, I2 = self._trim(D2, I2)
                 allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)

@@ -139,7 +139,8 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
  *      threshold that sits near rank 3k of the WHOLE index.
  *   3. cldrd_search_dev_seeded on every shard with that seed: only rows above it are collected,
  *      re-scored and returned (top-k of the shard among them, -1 padded); eps2_out_dev receives
- *      2*eps per query.  After the caller has merged the shards' lists (cldrd_merge),
+ *      2*eps per query.  After the caller has merged the shards' lists (cldrd_merge_w; cldrd.dist
+ *      does it slice-wise on every rank after an all-to-all),
  *      cldrd_verify_seed flags every query whose k-th merged score does not clear seed + eps:
  *      those (rare) queries must be searched again with seed_dev == NULL.
  * Any seed is safe: it only decides how much work the filter does, never the result. */
