@@ -1072,7 +1072,8 @@ int cldrd_sample_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, 
         int rc = launch_prep(c);
         if (rc) return rc;
         if ((rc = run_sample(c, out_topj_dev + size_t(q0) * CLDRD_SEED_J))) return rc;
-        if ((rc = read_stats(s, st))) return rc;
+        // no synchronisation here: the caller's all-gather and the seeded search queue up behind
+        // this on the same stream; a watchdog code (if any) surfaces at the end of that search
     }
     return CLDRD_OK;
 }
