@@ -178,6 +178,9 @@ struct cldrd_shard {
     int tune_run_len = 0;
     double tune_growth = 0.0;
     bool no_seed = false;   // CLDRD_NO_SEED=1: always use the progressive scheme
+    bool pipeline = false;  // CLDRD_PIPELINE=1: re-score of the first half batch overlaps the scan of the second
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_half = nullptr, ev_aux_done = nullptr;
     int tune_seed_chunks = 0;    // CLDRD_SEED_CHUNKS: force the number of launches of a seeded pass
     float tune_seed_bias = 0.f;  // CLDRD_SEED_BIAS: added to every seed (tests force seed misses with it)
 };
@@ -243,6 +246,11 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMalloc(&s->w_stats, ST_COUNT * sizeof(unsigned long long)));
     CU_TRY(cudaHostAlloc(&s->h_stats, ST_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&s->h_fail, Q * sizeof(int), cudaHostAllocDefault));
+    if (!s->aux_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&s->ev_half, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s->ev_aux_done, cudaEventDisableTiming));
+    }
     s->ws_keep_cap = keep_cap;
     return CLDRD_OK;
 }
@@ -280,7 +288,15 @@ struct BatchCtx {
     int q_stride = 0, seg_cap = 0, pool_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
     double seed_rank = 0.0;   // expected rank (in the whole index) of the seed threshold
     bool tc2 = false;         // this launch uses the CTA-pair kernel
+    // Workspace view.  A batch normally owns the whole workspace (qoff = 0, region = 0, 1 region);
+    // a pipelined batch is cut in two halves that use disjoint query ranges of every per-query
+    // array (qoff) and disjoint halves of the survivor buffer / segment counters (region).
+    int qoff = 0;
+    int region = 0, regions = 1;
 };
+
+inline uint64_t* ws_surv(const BatchCtx& c) { return c.s->w_surv + size_t(c.region) * (kSurvTotal / size_t(c.regions)); }
+inline int* ws_seg_cnt(const BatchCtx& c) { return c.s->w_seg_cnt + size_t(c.region) * (kSegCntInts / size_t(c.regions)); }
 
 // Work-unit plan for one chunk.  The grid is one persistent CTA per SM (fewer when there is less
 // work); a unit is `run_len` consecutive row tiles of one query tile; the query's survivor slice
@@ -288,7 +304,7 @@ struct BatchCtx {
 void plan_chunk(BatchCtx& c, int nrows) {
     cldrd_shard* s = c.s;
     const int nq_pad = ((c.nq + TC_BM - 1) / TC_BM) * TC_BM;
-    c.q_stride = int(std::min<size_t>(kSurvTotal / size_t(nq_pad), size_t(kMaxQStride)));
+    c.q_stride = int(std::min<size_t>((kSurvTotal / size_t(c.regions)) / size_t(nq_pad), size_t(kMaxQStride)));
     if (!is_tc(s->scan_eff)) {
         c.groups = 1;
         c.run_len = 1;
@@ -359,9 +375,9 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
     p.nrows = nrows;
     p.tile_stride = tile_stride;
     plan_chunk(c, nrows);
-    p.thr = s->w_thr;
-    p.surv = s->w_surv;
-    p.seg_cnt = s->w_seg_cnt;
+    p.thr = s->w_thr + c.qoff;
+    p.surv = ws_surv(c);
+    p.seg_cnt = ws_seg_cnt(c);
     p.q_stride = c.q_stride;
     p.seg_cap = c.seg_cap;
     p.pool_cap = c.pool_cap;
@@ -370,7 +386,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
     p.seg_by_group = c.seg_by_group;
     p.unit_ctr = s->w_unit_ctr;
     p.wait_cycles = (s->profile && mode == TC_FILTER) ? s->w_wait : nullptr;
-    p.dense = s->w_dense;
+    p.dense = s->w_dense + size_t(c.qoff) * kDensePiece;
     p.dense_ld = kDensePiece;
     p.stats = s->w_stats;
     if (is_tc(s->scan_eff)) {
@@ -384,7 +400,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
         }
         CU_TRY(cudaMemsetAsync(s->w_unit_ctr, 0, sizeof(int), c.st));
         if (mode == TC_FILTER)   // survivor cursors of this launch's segment layout start at zero
-            CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
+            CU_TRY(cudaMemsetAsync(ws_seg_cnt(c), 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
 #define LAUNCH_TC(KIND)                                                                                   \
     do {                                                                                                  \
         if (mode == TC_DENSE)                                                                             \
@@ -419,7 +435,7 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
             return CLDRD_OK;
         }
         const bool vec = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
-        if (!dense) CU_TRY(cudaMemsetAsync(s->w_seg_cnt, 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
+        if (!dense) CU_TRY(cudaMemsetAsync(ws_seg_cnt(c), 0, size_t(c.nq) * (c.groups + 1) * sizeof(int), c.st));
         if (dense) {
             if (vec) scan_simt_kernel<true, true><<<grid, 256, 0, c.st>>>(p);
             else scan_simt_kernel<true, false><<<grid, 256, 0, c.st>>>(p);
@@ -441,26 +457,26 @@ size_t select_smem(const cldrd_shard* s) { return size_t(s->ws_keep_cap + kSurvC
 int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_sel, int tile_stride = 1) {
     cldrd_shard* s = c.s;
     SelectParams p{};
-    p.list = s->w_list;
-    p.list_len = s->w_list_len;
+    p.list = s->w_list + size_t(c.qoff) * s->ws_keep_cap;
+    p.list_len = s->w_list_len + c.qoff;
     p.keep_cap = s->ws_keep_cap;
-    p.surv = s->w_surv;
-    p.seg_cnt = s->w_seg_cnt;
+    p.surv = ws_surv(c);
+    p.seg_cnt = ws_seg_cnt(c);
     p.q_stride = c.q_stride;
     p.seg_cap = c.seg_cap;
     p.pool_cap = c.pool_cap;
     p.groups = c.groups;
     p.surv_cap = kSurvCap;
-    p.dense = dense ? s->w_dense : nullptr;
+    p.dense = dense ? s->w_dense + size_t(c.qoff) * kDensePiece : nullptr;
     p.dense_ld = kDensePiece;
     p.dense_n = nrows;
     p.dense_row0 = uint32_t(row_begin);
     p.dense_tile_stride = tile_stride;
-    p.thr = s->w_thr;
-    p.seed = s->w_seed;
-    p.band = s->w_band;
+    p.thr = s->w_thr + c.qoff;
+    p.seed = s->w_seed + c.qoff;
+    p.band = s->w_band + c.qoff;
     p.k = k_sel;
-    p.fail = s->w_fail;
+    p.fail = s->w_fail + c.qoff;
     p.stats = s->w_stats;
     p.xb = s->xb;
     p.q = c.q;
@@ -479,14 +495,15 @@ int launch_prep(BatchCtx& c) {
     p.nq = c.nq;
     p.d = s->d;
     p.lp_kind = lp_kind_of(s->scan_eff);
-    p.q_lp = s->w_qlp;
+    char* qlp = s->w_qlp ? static_cast<char*>(s->w_qlp) + size_t(c.qoff) * s->d * 2 : nullptr;
+    p.q_lp = qlp;
     eps_coefs(s->scan_eff, s->d, &p.coef, &p.abs_coef);
     p.bmax_norm = s->bmax_norm;
-    p.band = s->w_band;
-    p.seed = s->w_seed;
-    p.thr = s->w_thr;
-    p.list_len = s->w_list_len;
-    p.fail = s->w_fail;
+    p.band = s->w_band + c.qoff;
+    p.seed = s->w_seed + c.qoff;
+    p.thr = s->w_thr + c.qoff;
+    p.list_len = s->w_list_len + c.qoff;
+    p.fail = s->w_fail + c.qoff;
     p.stats = s->w_stats;
     const int threads = 256;
     const int blocks = (c.nq * 32 + threads - 1) / threads;
@@ -494,7 +511,7 @@ int launch_prep(BatchCtx& c) {
     CU_TRY(cudaGetLastError());
     c.launches++;
     if (is_tc(s->scan_eff)) {
-        const void* base = lp_kind_of(s->scan_eff) ? static_cast<const void*>(s->w_qlp) : static_cast<const void*>(c.q);
+        const void* base = lp_kind_of(s->scan_eff) ? static_cast<const void*>(qlp) : static_cast<const void*>(c.q);
         int rc = make_tensor_map(&c.tmA, s->scan_eff, base, c.nq, s->d, TC_BM);
         if (rc) return rc;
         c.have_tmA = true;
@@ -502,28 +519,34 @@ int launch_prep(BatchCtx& c) {
     return CLDRD_OK;
 }
 
+// out_scores / out_ids: the batch's output base (this view's qoff is applied here, unless the
+// rows are scattered through out_index).  n_pad_small > 0: launch with shared memory for lists of
+// at most that many entries (so that the CTAs fit next to a running scan CTA); longer lists are
+// flagged as failed and redone by the fallback.
 int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool translate, const int* out_index,
-                   const int* fail_flags) {
+                   int* fail_flags, cudaStream_t st, int n_pad_small = 0) {
     cldrd_shard* s = c.s;
     RescoreParams p{};
     p.xb = s->xb;
     p.q = c.q;
     p.d = s->d;
     p.vec4 = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
-    p.list = s->w_list;
-    p.list_len = s->w_list_len;
+    p.list = s->w_list + size_t(c.qoff) * s->ws_keep_cap;
+    p.list_len = s->w_list_len + c.qoff;
     p.keep_cap = s->ws_keep_cap;
-    p.n_pad = s->ws_keep_cap;
+    p.n_pad = n_pad_small > 0 ? std::min(n_pad_small, s->ws_keep_cap) : s->ws_keep_cap;
     p.k = c.k;
     p.row0 = s->row0;
     p.ids = (translate && s->ids) ? s->ids : nullptr;
-    p.out_scores = out_scores;
-    p.out_ids = out_ids;
+    const size_t ooff = out_index ? 0 : size_t(c.qoff) * c.k;
+    p.out_scores = out_scores + ooff;
+    p.out_ids = out_ids + ooff;
     p.out_index = out_index;
-    p.fail = fail_flags;
+    p.fail = fail_flags ? fail_flags + c.qoff : nullptr;
+    p.fail_set = fail_flags ? fail_flags + c.qoff : nullptr;
     p.stats = s->w_stats;
     const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
-    rescore_sort_kernel<<<c.nq, 512, smem, c.st>>>(p);
+    rescore_sort_kernel<<<c.nq, 512, smem, st>>>(p);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;
@@ -689,7 +712,7 @@ int run_fallbacks(cldrd_shard* s, const float* q_dev, int nq, int k, bool transl
         int rc = launch_prep(f);
         if (rc) return rc;
         if ((rc = run_chunks(f, level == 1 ? PASS_PROGRESSIVE : PASS_DENSE))) return rc;
-        if ((rc = launch_rescore(f, out_scores, out_ids, translate, s->w_fail_index, s->w_fail))) return rc;
+        if ((rc = launch_rescore(f, out_scores, out_ids, translate, s->w_fail_index, s->w_fail, st))) return rc;
         if ((rc = read_stats(s, st))) return rc;
         tot->launches += f.launches + 1;
         tot->chunks += f.chunks;
@@ -734,16 +757,62 @@ int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool transla
     } else if (seed_mode == 2) {
         if ((rc = apply_seed(c, seed_ext))) return rc;
     }
-    if ((rc = run_chunks(c, seed_mode ? PASS_SEEDED : PASS_PROGRESSIVE))) return rc;
-    if ((rc = launch_rescore(c, out_scores, out_ids, translate, nullptr, s->w_fail))) return rc;
+    // Pipelined halves (seeded tensor-core scans of big batches): the re-score of the first half is
+    // HBM-bound, the scan of the second half is tensor-bound, so they run concurrently -- the
+    // re-score on an auxiliary stream with a shared-memory footprint small enough for its CTAs to
+    // sit next to the persistent scan CTAs.  The halves use disjoint query ranges of every
+    // per-query array and disjoint halves of the survivor buffer.
+    const int half = ((nq / 2 + 2 * TC_BM - 1) / (2 * TC_BM)) * (2 * TC_BM);
+    const bool pipelined = s->pipeline && seed_mode != 0 && is_tc(s->scan_eff) && nq >= 8 * TC_BM && half < nq &&
+                           s->aux_stream != nullptr;
+    if (!pipelined) {
+        if ((rc = run_chunks(c, seed_mode ? PASS_SEEDED : PASS_PROGRESSIVE))) return rc;
+        if ((rc = launch_rescore(c, out_scores, out_ids, translate, nullptr, s->w_fail, st))) return rc;
+        if (seed_mode == 1) {
+            verify_seed_kernel<<<(nq + 255) / 256, 256, 0, st>>>(out_scores, nq, k, s->w_seed, s->w_band, s->w_fail, s->w_stats);
+            CU_TRY(cudaGetLastError());
+            c.launches++;
+        }
+    } else {
+        BatchCtx h[2] = {c, c};
+        h[0].nq = half;
+        h[1].nq = nq - half;
+        h[1].q = q_dev + size_t(half) * s->d;
+        h[1].qoff = half;
+        for (int i = 0; i < 2; ++i) {
+            h[i].region = i;
+            h[i].regions = 2;
+            h[i].launches = h[i].chunks = 0;
+            const void* base = lp_kind_of(s->scan_eff)
+                                   ? static_cast<const void*>(static_cast<char*>(s->w_qlp) + size_t(h[i].qoff) * s->d * 2)
+                                   : static_cast<const void*>(h[i].q);
+            if ((rc = make_tensor_map(&h[i].tmA, s->scan_eff, base, h[i].nq, s->d, TC_BM))) return rc;
+        }
+        auto verify = [&](BatchCtx& x, cudaStream_t vs) -> int {
+            if (seed_mode != 1) return CLDRD_OK;
+            verify_seed_kernel<<<(x.nq + 255) / 256, 256, 0, vs>>>(out_scores + size_t(x.qoff) * k, x.nq, k, s->w_seed + x.qoff,
+                                                                   s->w_band + x.qoff, s->w_fail + x.qoff, s->w_stats);
+            CU_TRY(cudaGetLastError());
+            x.launches++;
+            return CLDRD_OK;
+        };
+        // half 0: scan + select on the main stream, re-score (+verify) on the auxiliary stream
+        if ((rc = run_chunks(h[0], PASS_SEEDED))) return rc;
+        CU_TRY(cudaEventRecord(s->ev_half, st));
+        CU_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_half, 0));
+        if ((rc = launch_rescore(h[0], out_scores, out_ids, translate, nullptr, s->w_fail, s->aux_stream, 2048))) return rc;
+        if ((rc = verify(h[0], s->aux_stream))) return rc;
+        CU_TRY(cudaEventRecord(s->ev_aux_done, s->aux_stream));
+        // half 1: everything on the main stream, concurrent with half 0's re-score
+        if ((rc = run_chunks(h[1], PASS_SEEDED))) return rc;
+        if ((rc = launch_rescore(h[1], out_scores, out_ids, translate, nullptr, s->w_fail, st))) return rc;
+        if ((rc = verify(h[1], st))) return rc;
+        CU_TRY(cudaStreamWaitEvent(st, s->ev_aux_done, 0));
+        c.launches += h[0].launches + h[1].launches;
+        c.chunks += h[0].chunks + h[1].chunks;
+    }
     if (eps_out) {   // eps = band / 2, for the caller's verification of an external seed
         CU_TRY(cudaMemcpyAsync(eps_out, s->w_band, size_t(nq) * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
-    if (seed_mode == 1) {
-        // survivors-overflow failures were counted by the select kernel; seed misses are added here
-        verify_seed_kernel<<<(nq + 255) / 256, 256, 0, st>>>(out_scores, nq, k, s->w_seed, s->w_band, s->w_fail, s->w_stats);
-        CU_TRY(cudaGetLastError());
-        c.launches++;
     }
     // any query to redo?  (one small D2H; also surfaces watchdog / range errors)
     if ((rc = read_stats(s, st))) return rc;
@@ -786,6 +855,7 @@ int cldrd_shard_create(cldrd_shard** out, int device, int64_t row0, int64_t nrow
     if (const char* e = getenv("CLDRD_SEED_BIAS")) s->tune_seed_bias = float(atof(e));
     if (const char* e = getenv("CLDRD_SEED_CHUNKS")) s->tune_seed_chunks = atoi(e);
     if (const char* e = getenv("CLDRD_TC2")) s->use_tc2 = atoi(e) != 0;
+    if (const char* e = getenv("CLDRD_PIPELINE")) s->pipeline = atoi(e) != 0;
     *out = s;
     return CLDRD_OK;
 }
@@ -795,6 +865,9 @@ void cldrd_shard_destroy(cldrd_shard* s) {
     DeviceGuard g(s->device);
     free_workspace(s);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    if (s->ev_half) cudaEventDestroy(s->ev_half);
+    if (s->ev_aux_done) cudaEventDestroy(s->ev_aux_done);
     if (s->xb_owned) cudaFree(s->xb);
     cudaFree(s->xlp);
     cudaFree(s->ids);

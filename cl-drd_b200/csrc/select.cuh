@@ -281,6 +281,7 @@ struct RescoreParams {
     int64_t* out_ids;     // [*][k]
     const int* out_index; // optional: output row of query q (dense fallback scatter), or nullptr
     const int* fail;      // skip failed queries (nullptr = none)
+    int* fail_set;        // a list longer than n_pad (reduced-shared-memory launch) flags the query here
     unsigned long long* stats;
 };
 
@@ -294,6 +295,13 @@ __global__ void __launch_bounds__(512) rescore_sort_kernel(RescoreParams p) {
     const int tid = threadIdx.x;
     if (p.fail && p.fail[q]) return;
     const int L = p.list_len[q];
+    if (L > p.n_pad) {   // only possible when launched with less shared memory than keep_cap needs
+        if (tid == 0 && p.fail_set) {
+            p.fail_set[q] = 1;
+            atomicAdd(&p.stats[ST_FAILED], 1ull);
+        }
+        return;
+    }
     for (int i = tid; i < p.d; i += blockDim.x) q_s[i] = p.q[size_t(q) * p.d + i];
     int n_pad = 2;
     while (n_pad < L) n_pad <<= 1;

@@ -26,8 +26,9 @@ def main():
         rows[r0:r0 + (1 << 20)].normal_(generator=g)
     q = torch.randn((args.queries, 768), generator=g, dtype=torch.float32, device=dev)
     for setting in args.settings.split(","):
-        rl, gr, ch, tc2 = (setting.split(":") + ["0", "0"])[:4]
+        rl, gr, ch, tc2, pipe = (setting.split(":") + ["0", "0", "0"])[:5]
         os.environ["CLDRD_TC2"] = tc2
+        os.environ["CLDRD_PIPELINE"] = pipe
         os.environ["CLDRD_RUN_LEN"] = rl
         os.environ["CLDRD_GROWTH"] = gr
         os.environ["CLDRD_SEED_CHUNKS"] = ch
@@ -47,7 +48,7 @@ def main():
         tot, ms, launches, st = best
         print("   issuer waits:", s.shard.wait_cycles())
         per = " ".join(f"{r}:{t:.2f}ms({2 * args.queries * r * 768 / t / 1e9:.0f}TF)" for r, t in launches[:12])
-        print(f"run_len={rl} growth={gr} seed_chunks={ch} tc2={tc2}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
+        print(f"run_len={rl} growth={gr} seed_chunks={ch} tc2={tc2} pipe={pipe}: total {tot:.1f} ms scan {ms:.1f} ms fallback {st['fallback_queries']} "
               f"({2 * args.queries * args.rows * 768 / ms / 1e9:.0f} TF) surv/q {st['survivors'] / args.queries:.0f} | {per}",
               flush=True)
         s.shard.close()
