@@ -259,6 +259,19 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_qps = nq * args.steps / e2e_s
 
+    # the reference's own call pattern: index_retrieve(index, q, top_k, batch=128), i.e. one host-buffer
+    # search per 128 queries (retriever/retrieval_utils.py:141-147), without its .tolist() boxing
+    e2e_b128 = None
+    if world == 1:
+        for q0 in range(0, min(nq, 512), 128):
+            searcher.local.search(q_np[q0:q0 + 128], k)
+        t0 = time.perf_counter()
+        for q0 in range(0, nq, 128):
+            searcher.local.search(q_np[q0:q0 + 128], k)
+        dt = time.perf_counter() - t0
+        e2e_b128 = {"value": nq / dt, "unit": "queries/s", "ms_total": dt * 1e3, "calls": (nq + 127) // 128,
+                    "note": "one index pass per 128 queries: HBM-bound"}
+
     # ---- roofline of the scan kernel ----------------------------------------------------------------
     peaks = load_peaks()
     flops_step_shard = 2.0 * nq * len(rr) * d
@@ -322,6 +335,8 @@ def main():
         }
         if phase_ms:
             line["phase_ms_last_step"] = phase_ms
+        if e2e_b128:
+            line["e2e_reference_loop_batch128"] = e2e_b128
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
