@@ -14,3 +14,4 @@ from .index import (  # noqa: F401
 from .runfile import format_score, write_run_file  # noqa: F401
 
 __version__ = "0.1.0"
+from . import curriculum  # noqa: F401,E402

@@ -1,0 +1,132 @@
+"""Curriculum group files from a ranked run.
+
+The reference only ships the CONSUMER of these files: `NwayDataset.create_from_relT_most_semi_hard_file`
+(dataset/nway_dataset.py:213-261) reads one JSON object per line with the keys
+`qid`, `relT_pids`, `most_hard_pids`, `semi_hard_pids`, and `__getitem__` (dataset/nway_dataset.py:32-71)
+asserts the list lengths its `label_mode` expects (5/10/20/30 "relT" passages, the other 30-n split over the
+two negative groups).  The scripts that PRODUCE the files from the top-200 retrieval runs (scripts/unity/…,
+retrieve_top_passages.py with --top_k 200) are absent upstream, so the slicing rule is not pinned by code:
+here it is explicit and parameterised - rank windows over the (re-)ranked list of each query - and the
+defaults follow the shape the label modes fix (n_rel + n_most + n_semi = 30).
+
+Everything works on the arrays `index_retrieve` returns, so a search result can be turned into a
+training file without the run file in between (`groups_from_search`), or from a run file on disk
+(`read_run` -> `build_groups`).
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# (n_rel, n_most, n_semi) each `label_mode` of dataset/nway_dataset.py:41-70 accepts through
+# create_from_relT_most_semi_hard_file (neg_pids = most_hard_pids + semi_hard_pids)
+LABEL_MODE_SHAPES = {
+    "2": (10, 10, 10), "3": (10, 10, 10), "4": (10, 10, 10), "9": (10, 10, 10),
+    "5": (20, 5, 5), "10": (20, 5, 5),
+    "6": (30, 0, 0),
+    "7": (5, 12, 13), "8": (5, 12, 13),
+}
+
+
+def read_run(path) -> Tuple[np.ndarray, List[np.ndarray]]:
+    """Run file ("qid\\tpid[\\trank[\\tscore]]", what retrieve_top_passages.py:102-107 writes and
+    evaluation/retrieval_evaluator.py:46-63 reads) -> (qids in first-seen order, pids per query in file order)."""
+    order: Dict[int, int] = {}
+    lists: List[List[int]] = []
+    with open(path, "r") as f:
+        for line in f:
+            a = line.strip().split("\t")
+            if not 2 <= len(a) <= 4:
+                raise ValueError("array length is not legal.")
+            q, p = int(a[0]), int(a[1])
+            slot = order.get(q)
+            if slot is None:
+                slot = order[q] = len(lists)
+                lists.append([])
+            lists[slot].append(p)
+    qids = np.fromiter(order.keys(), dtype=np.int64, count=len(order))
+    return qids, [np.asarray(l, dtype=np.int64) for l in lists]
+
+
+def _window(ranked: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    return ranked[min(lo, ranked.shape[0]):min(hi, ranked.shape[0])]
+
+
+def build_groups(qids: Sequence[int], ranked_pids: Sequence[np.ndarray], n_rel: int = 10, n_most: int = 10,
+                 n_semi: int = 10, most_window: Optional[Tuple[int, int]] = None,
+                 semi_window: Optional[Tuple[int, int]] = None, qrels: Optional[Dict[int, Iterable[int]]] = None,
+                 seed: int = 0, strict: bool = True) -> List[dict]:
+    """One example per query: the first `n_rel` ranks are the teacher-relevant group, `n_most` passages are
+    drawn without replacement from ranks `most_window` (default: the n_rel..50 band) and `n_semi` from
+    `semi_window` (default: 50..200).  Draws keep rank order.  Padding ids (-1, an index with fewer rows than
+    top_k) are dropped first.  `qrels` (qid -> judged-relevant pids), when given, are moved to the front of the
+    relevant group - the human positive is always a member, like `rel_pid` in the reference's other loaders
+    (dataset/nway_dataset.py:204-209) - and never sampled as a negative.
+    strict: a query whose lists cannot be filled raises (the dataset would assert later); else it is skipped."""
+    assert n_rel >= 1 and n_most >= 0 and n_semi >= 0
+    most_window = most_window or (n_rel, max(50, n_rel + n_most))
+    semi_window = semi_window or (most_window[1], max(200, most_window[1] + n_semi))
+    assert most_window[0] >= n_rel and semi_window[0] >= most_window[1], "windows must not overlap"
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for qid, ranked in zip(qids, ranked_pids):
+        ranked = np.asarray(ranked, dtype=np.int64)
+        ranked = ranked[ranked >= 0]
+        _, first = np.unique(ranked, return_index=True)          # a reranked list may repeat a pid
+        ranked = ranked[np.sort(first)]
+        pos = [int(p) for p in qrels.get(int(qid), ())] if qrels else []
+        if pos:
+            ranked = ranked[~np.isin(ranked, pos)]
+            take = max(n_rel - len(pos), 0)
+            rel = (pos + ranked[:take].tolist())[:n_rel]
+            # window positions stay "rank in the list with the positives moved to the front"
+            ranked = np.concatenate([np.asarray(rel, dtype=np.int64), ranked[take:]])
+        else:
+            rel = ranked[:n_rel].tolist()
+        most_pool = _window(ranked, *most_window)
+        semi_pool = _window(ranked, *semi_window)
+        if len(rel) < n_rel or most_pool.shape[0] < n_most or semi_pool.shape[0] < n_semi:
+            if strict:
+                raise ValueError(f"qid {int(qid)}: {ranked.shape[0]} ranked passages cannot fill "
+                                 f"{n_rel}+{n_most}+{n_semi} from windows {most_window}, {semi_window}")
+            continue
+        most = most_pool[np.sort(rng.choice(most_pool.shape[0], n_most, replace=False))] if n_most else most_pool[:0]
+        semi = semi_pool[np.sort(rng.choice(semi_pool.shape[0], n_semi, replace=False))] if n_semi else semi_pool[:0]
+        out.append({"qid": int(qid), "relT_pids": [int(p) for p in rel],
+                    "most_hard_pids": most.tolist(), "semi_hard_pids": semi.tolist()})
+    return out
+
+
+def groups_for_label_mode(qids, ranked_pids, label_mode: str, **kw) -> List[dict]:
+    """Group sizes taken from the label mode the training run will use (dataset/nway_dataset.py:41-70)."""
+    n_rel, n_most, n_semi = LABEL_MODE_SHAPES[str(label_mode)]
+    return build_groups(qids, ranked_pids, n_rel, n_most, n_semi, **kw)
+
+
+def groups_from_search(query_ids, nn_ids, **kw) -> List[dict]:
+    """Straight from `index_retrieve`'s arrays (retriever/retrieval_utils.py:130-150): nn_ids [n, top_k]."""
+    nn_ids = np.asarray(nn_ids, dtype=np.int64)
+    return build_groups(np.asarray(query_ids, dtype=np.int64), list(nn_ids), **kw)
+
+
+def write_groups(path, examples: Iterable[dict]) -> int:
+    """One JSON object per line, the layout dataset/nway_dataset.py:241-250 parses."""
+    n = 0
+    with open(path, "w") as f:
+        for ex in examples:
+            f.write(json.dumps(ex) + "\n")
+            n += 1
+    return n
+
+
+def ranklists_for_evaluator(query_ids, nn_ids) -> Dict[int, List[int]]:
+    """In-memory hand-off to `RankingEvaluator._calculate_metrics_plain` (evaluation/retrieval_evaluator.py:79):
+    the `qid_to_ranklist` dict its `compute_metrics` builds from the run file (:46-63), without the file.
+    A qid that occurs twice continues its list, as the reader's `+=` does; padding ids are dropped."""
+    nn_ids = np.asarray(nn_ids, dtype=np.int64)
+    out: Dict[int, List[int]] = {}
+    for q, row in zip(np.asarray(query_ids, dtype=np.int64).tolist(), nn_ids):
+        out.setdefault(q, []).extend(row[row >= 0].tolist())
+    return out

@@ -1,0 +1,175 @@
+"""curriculum group files and the in-memory evaluator hand-off (host logic, CPU)."""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "cl-drd_b200")]
+REF = "/root/reference"
+
+from cldrd import curriculum as CU  # noqa: E402
+
+
+def _ranked(nq=12, depth=200, seed=3):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return np.arange(1000, 1000 + nq, dtype=np.int64), [rng.permutation(50_000)[:depth].astype(np.int64) for _ in range(nq)]
+
+
+@pytest.mark.parametrize("mode", sorted(CU.LABEL_MODE_SHAPES, key=int))
+def test_group_shapes_follow_label_mode(mode):
+    qids, lists = _ranked()
+    ex = CU.groups_for_label_mode(qids, lists, mode, seed=1)
+    n_rel, n_most, n_semi = CU.LABEL_MODE_SHAPES[mode]
+    assert len(ex) == len(qids)
+    for e, ranked in zip(ex, lists):
+        assert e["relT_pids"] == ranked[:n_rel].tolist()
+        assert len(e["most_hard_pids"]) == n_most and len(e["semi_hard_pids"]) == n_semi
+        pos = {int(p): i for i, p in enumerate(ranked)}
+        most_r = [pos[p] for p in e["most_hard_pids"]]
+        semi_r = [pos[p] for p in e["semi_hard_pids"]]
+        assert most_r == sorted(most_r) and semi_r == sorted(semi_r)            # rank order kept
+        assert all(n_rel <= r < 50 for r in most_r) and all(50 <= r < 200 for r in semi_r)
+        allp = e["relT_pids"] + e["most_hard_pids"] + e["semi_hard_pids"]
+        assert len(set(allp)) == len(allp) == 30
+
+
+def test_deterministic_and_seeded():
+    qids, lists = _ranked()
+    a = CU.build_groups(qids, lists, seed=5)
+    assert a == CU.build_groups(qids, lists, seed=5)
+    assert a != CU.build_groups(qids, lists, seed=6)
+
+
+def test_positives_lead_the_relevant_group_and_are_never_negatives():
+    qids, lists = _ranked(nq=4)
+    qrels = {int(qids[0]): [int(lists[0][120])],          # judged passage deep in the list
+             int(qids[1]): [777_777],                     # judged passage not retrieved at all
+             int(qids[2]): [int(lists[2][0])]}            # already on top
+    ex = CU.build_groups(qids, lists, qrels=qrels, seed=0)
+    assert ex[0]["relT_pids"][0] == int(lists[0][120]) and ex[0]["relT_pids"][1:] == lists[0][:9].tolist()
+    assert ex[1]["relT_pids"][0] == 777_777
+    assert ex[2]["relT_pids"] == lists[2][:10].tolist()
+    assert ex[3]["relT_pids"] == lists[3][:10].tolist()
+    for e, q in zip(ex, qids):
+        for p in qrels.get(int(q), []):
+            assert p not in e["most_hard_pids"] + e["semi_hard_pids"]
+
+
+def test_padding_duplicates_and_short_lists():
+    qids = np.array([1, 2], dtype=np.int64)
+    full = np.arange(200, dtype=np.int64)
+    short = np.concatenate([np.arange(40, dtype=np.int64), np.full(160, -1, dtype=np.int64)])   # index had 40 rows
+    with pytest.raises(ValueError):
+        CU.build_groups(qids, [full, short])
+    ex = CU.build_groups(qids, [full, short], strict=False)
+    assert [e["qid"] for e in ex] == [1]
+    dup = np.concatenate([np.arange(100), np.arange(100), np.arange(100, 300)]).astype(np.int64)
+    e = CU.build_groups([7], [dup])[0]
+    allp = e["relT_pids"] + e["most_hard_pids"] + e["semi_hard_pids"]
+    assert len(set(allp)) == 30 and e["relT_pids"] == list(range(10))
+
+
+def test_run_file_round_trip(tmp_path):
+    qids, lists = _ranked(nq=5, depth=200)
+    run = tmp_path / "top200.run"
+    with open(run, "w") as f:
+        for q, l in zip(qids, lists):
+            for r, p in enumerate(l):
+                f.write(f"{q}\t{p}\t{r + 1}\t{1.0 / (r + 1)}\n")
+    q2, l2 = CU.read_run(run)
+    assert q2.tolist() == qids.tolist() and all((a == b).all() for a, b in zip(l2, lists))
+    with open(tmp_path / "bad.run", "w") as f:
+        f.write("1\n")
+    with pytest.raises(ValueError):
+        CU.read_run(tmp_path / "bad.run")
+
+
+def test_cli_writes_what_the_loader_parses(tmp_path):
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "cl-drd_b200", "retriever", "make_curriculum_groups.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    qids, lists = _ranked(nq=6)
+    run, qrels, out = tmp_path / "r.run", tmp_path / "qrels.tsv", tmp_path / "groups.json"
+    with open(run, "w") as f:
+        for q, l in zip(qids, lists):
+            for r, p in enumerate(l):
+                f.write(f"{q}\t{p}\t{r + 1}\t0.5\n")
+    with open(qrels, "w") as f:
+        f.write(f"{qids[0]}\t0\t{lists[0][33]}\t1\n{qids[1]}\t0\t{lists[1][3]}\t0\n")
+    mk.main(mk.get_args(["--run_path", str(run), "--output_path", str(out), "--label_mode", "8", "--qrels_path", str(qrels)]))
+    rows = [json.loads(l) for l in open(out)]
+    assert len(rows) == 6 and rows[0]["relT_pids"][0] == int(lists[0][33])
+    assert rows[1]["relT_pids"] == lists[1][:5].tolist()       # rel=0 in the qrels is not a positive
+    assert all(len(r["relT_pids"]) == 5 and len(r["most_hard_pids"]) == 12 and len(r["semi_hard_pids"]) == 13 for r in rows)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+@pytest.mark.parametrize("mode", ["9", "8", "10", "6"])
+def test_reference_nway_dataset_accepts_our_file(tmp_path, mode, monkeypatch):
+    """dataset/nway_dataset.py:213-261 loads the file; __getitem__ (:32-71) asserts the group sizes of the label mode."""
+    if "ujson" not in sys.modules:
+        try:
+            import ujson  # noqa: F401
+        except ImportError:
+            monkeypatch.setitem(sys.modules, "ujson", types.SimpleNamespace(loads=json.loads, dumps=json.dumps))
+    pkg = types.ModuleType("refdataset")
+    pkg.__path__ = [os.path.join(REF, "dataset")]
+    monkeypatch.setitem(sys.modules, "refdataset", pkg)
+    spec = importlib.util.spec_from_file_location("refdataset.nway_dataset", os.path.join(REF, "dataset", "nway_dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "refdataset.nway_dataset", mod)
+    spec.loader.exec_module(mod)
+
+    qids, lists = _ranked(nq=5)
+    out = tmp_path / "groups.json"
+    CU.write_groups(out, CU.groups_for_label_mode(qids, lists, mode, seed=2))
+    queries, passages = tmp_path / "q.tsv", tmp_path / "p.tsv"
+    with open(queries, "w") as f:
+        for q in qids:
+            f.write(f"{q}\tquery {q}\n")
+    with open(passages, "w") as f:
+        for p in sorted({int(p) for l in lists for p in l}):
+            f.write(f"{p}\tpassage {p}\n")
+    ds = mod.NwayDataset.create_from_relT_most_semi_hard_file(str(queries), str(passages), str(out), tokenizer=None,
+                                                              max_query_len=16, max_passage_len=32, label_mode=mode)
+    assert len(ds) == 5
+    n_rel, n_most, n_semi = CU.LABEL_MODE_SHAPES[mode]
+    for i in range(len(ds)):
+        item = ds[i]                                         # raises if the sizes do not fit the label mode
+        assert len(item["relT_pids"]) == n_rel and len(item["neg_pids"]) == n_most + n_semi
+        assert len(item["labels"]) == 30 and item["query"] == f"query {item['qid']}"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+def test_in_memory_hand_off_matches_run_file_metrics(tmp_path):
+    """f-1: RankingEvaluator._calculate_metrics_plain (evaluation/retrieval_evaluator.py:79) on our dict ==
+    compute_metrics on the run file."""
+    sys.path.insert(0, ROOT)
+    from oracle import flat_ip as O
+    spec = importlib.util.spec_from_file_location("ref_eval2", os.path.join(REF, "evaluation", "retrieval_evaluator.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xb, xq, ids = O.synth(3000, 32, 0), O.synth(25, 32, 1), O.synth_ids(3000)
+    D, I = O.search(xb, ids, xq, 100)
+    qids = np.arange(500, 525, dtype=np.int64)
+    run = tmp_path / "dev.run"
+    with open(run, "w") as f:
+        for q, row in zip(qids, I):
+            for r, p in enumerate(row):
+                f.write(f"{q}\t{p}\t{r + 1}\n")
+    qrels = tmp_path / "qrels.tsv"
+    with open(qrels, "w") as f:
+        for i, q in enumerate(qids):
+            f.write(f"{q}\t0\t{I[i, (3 * i) % 11]}\t1\n")
+    ev = mod.RankingEvaluator(str(qrels))
+    from_file = ev.compute_metrics(str(run))
+    ranklists = CU.ranklists_for_evaluator(qids, I)
+    in_mem = ev._calculate_metrics_plain(ranklists, ev.qid_to_relevant_data, binarization_point=1.)
+    in_mem = in_mem[0] if isinstance(in_mem, tuple) else in_mem
+    for key, v in from_file.items():
+        assert in_mem[key] == v, key
