@@ -546,7 +546,11 @@ int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool transl
     p.fail_set = fail_flags ? fail_flags + c.qoff : nullptr;
     p.stats = s->w_stats;
     const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
-    rescore_sort_kernel<<<c.nq, 512, smem, st>>>(p);
+    // few queries (the reference's batch=128 loop): one CTA per query leaves most SMs with a single
+    // CTA, so give it twice the warps to keep the row gather's loads in flight; the per-row result
+    // does not depend on which warp computes it
+    const int threads = c.nq <= 2 * s->num_sms ? 1024 : 512;
+    rescore_sort_kernel<<<c.nq, threads, smem, st>>>(p);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;

@@ -596,3 +596,24 @@ def test_sharded_searcher_from_file_and_in_process_shards_from_file(cldrd_lib, t
     assert r["ok"], r
     assert np.array_equal(D2, D.cpu().numpy()) and np.array_equal(I2, I.cpu().numpy())
     multi.close()
+
+
+@pytest.mark.parametrize("scan", ["f16", "tf32"])
+def test_embedding_like_distribution_stays_exact_and_seeded(cldrd_lib, scan):
+    """Encoder outputs are not white noise: a large mean vector shared by every passage and query and a
+    decaying spectrum, so all scores crowd into a narrow range far from zero (|q||b| is ~10x the spread
+    of the scores).  The filter band is wide relative to the score gaps here; results must still be exact,
+    with no query sent to the fallback."""
+    d, n, nq = 128, 1_200_000, 200
+    rng = np.random.Generator(np.random.PCG64(900))
+    mean = rng.standard_normal((d,), dtype=np.float32) * 0.8
+    spectrum = (1.0 / np.sqrt(1.0 + np.arange(d, dtype=np.float32))).astype(np.float32)
+    xb = (rng.standard_normal((n, d), dtype=np.float32) * spectrum[None, :] + mean[None, :]).astype(np.float32)
+    xq = (rng.standard_normal((nq, d), dtype=np.float32) * spectrum[None, :] + mean[None, :]).astype(np.float32)
+    gpu = _gpu_index(xb, None, scan)
+    D, _ = _check(gpu, xb, None, xq, 1000)
+    st = gpu.last_stats()
+    assert st["fallback_queries"] == 0, st
+    # the premise of the test: scores far from zero compared with their spread inside the top-k
+    assert (D[:, 0] - D[:, -1]).max() < 0.2 * D[:, -1].min()
+    gpu.close()
