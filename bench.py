@@ -223,7 +223,7 @@ def main():
         ms, nl = shard.scan_time()
         scan_ms_total += ms
         scan_launches += nl
-        launches += shard.stats()["launches"] + (1 if (world > 1 and rank == 0) else 0)
+        launches += shard.stats()["launches"] + (2 if world > 1 else 0)   # + merge and verify of this rank's slice
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -320,7 +320,11 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"configs[1]: synthetic {n_rows}x{d} fp32 index, {nq} queries, top-{k}",
                        "scan": shard.scan, "results": "exact fp32 (proven filter band + fp32 rescore)",
-                       "parallelism": f"index rows sharded over {world} GPU(s), NCCL gather + GPU merge",
+                       "parallelism": (f"index rows sharded over {world} GPU(s); " +
+                                       ("single shard" if world == 1 else
+                                        "re-score kernel stores lists into the merging rank's HBM over NVLink (peer memory), "
+                                        "slice-wise merge kernels store into rank 0" if getattr(searcher, "_px", None) is not None
+                                        else "NCCL all-to-all + slice-wise merge + NCCL gather")),
                        "l2": f"inputs larger than L2: each pass streams {scan_bytes / 1e9:.1f} GB of index rows per GPU",
                        "chunks_per_pass": stats["chunks"], "rescored_per_query": stats["rescored"] / max(nq, 1),
                        "survivors_per_query": stats["survivors"] / max(nq, 1), "fallback_queries": stats["fallback_queries"]},

@@ -12,6 +12,8 @@ SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "
               "bf16": SCAN_TC_BF16}
 MAX_K = 2048
 SEED_J = 32
+MAX_PEERS = 16            # CLDRD_MAX_PEERS
+PEER_HANDLE_BYTES = 72    # CLDRD_PEER_HANDLE_BYTES
 
 E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
 
@@ -55,12 +57,20 @@ SIGNATURES = {
     "cldrd_seed_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "cldrd_search_dev_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_verify_seed": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_search_dev_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "cldrd_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "cldrd_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "cldrd_peer_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cldrd_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "cldrd_peer_copy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cldrd_shard_norm_bound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cldrd_shard_set_norm_bound": (C.c_int, [C.c_void_p, C.c_float]),
     "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cldrd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "cldrd_host_free": (None, [C.c_void_p]),
     "cldrd_merge_w": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_merge_planes": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_merge": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_shard_last_stats": (C.c_int, [C.c_void_p, _c_i64p]),
     "cldrd_shard_wait_cycles": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),

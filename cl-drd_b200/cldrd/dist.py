@@ -60,6 +60,90 @@ def merge_candidates(allD: torch.Tensor, allI: torch.Tensor, id_map: Optional[to
     return outD, outI
 
 
+class _PeerExchange:
+    """Exchange buffers of one node's ranks, mapped into every rank (CUDA IPC over NVLink / NVSwitch).
+
+    Every rank owns  xD float32 [world][slice][k]  and  xI int64 [world][slice][k]  (plane p is written
+    by rank p's re-score kernel: `cldrd_search_dev_scatter`); rank 0 also owns the result buffers
+    oD / oI [world*slice][k] that every rank's merge kernel writes its slice into.  Sized for
+    `cap_elems` = world*slice*k entries; rebuilt (collectively) when a search needs more."""
+
+    def __init__(self, device: int, rank: int, world: int, cap_elems: int, group):
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.cap_elems = cap_elems
+        self.own = []          # pointers from cldrd_peer_alloc
+        self.opened = []       # pointers from cldrd_peer_open
+        self.xD = [None] * world
+        self.xI = [None] * world
+        self.oD = self.oI = None
+        elems = cap_elems
+        sizes = [elems * 4, elems * 8] + ([elems * 4, elems * 8] if rank == 0 else [])
+        handles = torch.zeros((4, _lib.PEER_HANDLE_BYTES), dtype=torch.uint8)
+        ok = True
+        try:
+            for i, nbytes in enumerate(sizes):
+                ptr = C.c_void_p()
+                buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+                check(lib().cldrd_peer_alloc(device, nbytes, C.byref(ptr), buf))
+                self.own.append(ptr.value)
+                handles[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+        except Exception:
+            ok = False
+        dev = torch.device("cuda", device)
+        allh = torch.empty((world, 4, _lib.PEER_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, handles.to(dev), group=group)
+        allh = allh.cpu()
+        if ok:
+            try:
+                for r in range(world):
+                    for i in range(4 if r == 0 else 2):
+                        if r == rank:
+                            ptr_v = self.own[i]
+                        else:
+                            ptr = C.c_void_p()
+                            hb = (C.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(bytes(allh[r, i].tolist()))
+                            check(lib().cldrd_peer_open(device, hb, C.byref(ptr)))
+                            self.opened.append(ptr.value)
+                            ptr_v = ptr.value
+                        if i == 0:
+                            self.xD[r] = ptr_v
+                        elif i == 1:
+                            self.xI[r] = ptr_v
+                        elif i == 2:
+                            self.oD = ptr_v
+                        else:
+                            self.oI = ptr_v
+            except Exception:
+                ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(flag.item())
+        if self.ok:
+            self.c_xD = (C.c_void_p * world)(*self.xD)
+            self.c_xI = (C.c_void_p * world)(*self.xI)
+        else:
+            self.close()
+
+    def fits(self, slice_rows: int, k: int) -> bool:
+        return self.ok and self.world * slice_rows * k <= self.cap_elems
+
+    def close(self):
+        # every rank unmaps before anybody frees
+        for p in self.opened:
+            lib().cldrd_peer_close(self.device, C.c_void_p(p))
+        self.opened = []
+        if dist.is_initialized():
+            try:
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+            except Exception:
+                pass
+        for p in self.own:
+            lib().cldrd_peer_free(self.device, C.c_void_p(p))
+        self.own = []
+        self.ok = False
+
+
 class ShardedSearcher:
     """rank-local shard + the gather/merge step.  Build with `from_rows` (device rows already in
     HBM, zero copy) or `from_file` (each rank preads only its own row range)."""
@@ -149,6 +233,94 @@ class ShardedSearcher:
             return D, I
         return D[:, :w].contiguous(), I[:, :w].contiguous()
 
+    def _peer_exchange(self, n: int, k: int):
+        """The node-local peer-memory exchange for an [n, k] search, or None when it is unavailable
+        (CLDRD_DIST_P2P=0, CPU process group, IPC / peer access refused): then NCCL moves the lists."""
+        if os.environ.get("CLDRD_DIST_P2P", "1") == "0" or self.world > _lib.MAX_PEERS or n == 0:
+            return None
+        if getattr(self, "_px_disabled", False):
+            return None
+        sl = (n + self.world - 1) // self.world
+        px = getattr(self, "_px", None)
+        if px is not None and px.fits(sl, k):
+            return px
+        cap = self.world * sl * k
+        if px is not None:
+            cap = max(cap, px.cap_elems)
+            px.close()
+        self._px = _PeerExchange(self.shard.device, self.rank, self.world, cap, self.group)
+        if not self._px.ok:
+            self._px = None
+            self._px_disabled = True   # agreed by all ranks (all-reduce MIN): nobody retries
+        return self._px
+
+    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, seed, seeded: bool, mark, marks, prof):
+        """Seeded search whose re-score kernel stores every query's list in the merging rank's memory
+        (NVLink peer stores), slice-wise merge + verify on every rank, merge kernels store into rank 0's
+        result buffer.  Two tiny all-reduces are the only collectives after the seed: they are the
+        barriers between the three kernels' peer accesses."""
+        n, world, dev = q.shape[0], self.world, q.device
+        sl = (n + world - 1) // world
+        st = torch.cuda.current_stream(dev).cuda_stream
+        eps2 = torch.empty((n,), dtype=torch.float32, device=dev)
+        token = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with self.local._lock:
+            check(lib().cldrd_search_dev_scatter(self.shard.handle, C.c_void_p(q.data_ptr()), n, int(k),
+                                                 C.c_void_p(seed.data_ptr()) if seed is not None else None,
+                                                 world, self.rank, sl, px.c_xD, px.c_xI, C.c_void_p(eps2.data_ptr()),
+                                                 C.c_void_p(st)))
+        mark("seeded search + scatter")
+        dist.all_reduce(token, group=self.group)            # every plane of my buffers is written
+        if os.environ.get("CLDRD_DIST_DEBUG") == "1":
+            torch.cuda.synchronize()
+            print(f"[rank {self.rank}] scatter + barrier ok: n={n} k={k} sl={sl} cap={px.cap_elems}", flush=True)
+        lo = self.rank * sl
+        n_mine = max(0, min(sl, n - lo))
+        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
+        fail_sl = torch.zeros((sl,), dtype=torch.int32, device=dev)
+        if n_mine > 0:
+            outD = px.oD + lo * k * 4
+            outI = px.oI + lo * k * 8
+            check(lib().cldrd_merge_planes(dev.index, C.c_void_p(px.xD[self.rank]), C.c_void_p(px.xI[self.rank]), world, sl,
+                                           n_mine, k, k, None, C.c_void_p(outD), C.c_void_p(outI), C.c_void_p(st)))
+            if seeded:
+                check(lib().cldrd_verify_seed(dev.index, C.c_void_p(outD), n_mine, k,
+                                              C.c_void_p(seed[lo:lo + n_mine].contiguous().data_ptr()),
+                                              C.c_void_p(eps2[lo:lo + n_mine].contiguous().data_ptr()),
+                                              C.c_void_p(fail_sl.data_ptr()), C.c_void_p(st)))
+                nfail[0] = fail_sl[:n_mine].sum()
+        mark("merge+verify")
+        dist.all_reduce(nfail, op=dist.ReduceOp.SUM, group=self.group)   # also: every slice is in rank 0's buffer
+        outD_t = outI_t = None
+        if self.rank == 0:
+            outD_t = torch.empty((n, k), dtype=torch.float32, device=dev)
+            outI_t = torch.empty((n, k), dtype=torch.int64, device=dev)
+            check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outD_t.data_ptr()), C.c_void_p(px.oD), n * k * 4, C.c_void_p(st)))
+            check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outI_t.data_ptr()), C.c_void_p(px.oI), n * k * 8, C.c_void_p(st)))
+        mark("result")
+        misses = int(nfail.item()) if seeded else 0
+        if misses > 0:   # rare: the seed sat above the true k-th score for these queries
+            fail_all = torch.empty((world, sl), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(fail_all, fail_sl, group=self.group)
+            idx = torch.nonzero(fail_all.view(-1)[:n]).flatten()
+            D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
+            D2, I2 = self._trim(D2, I2)
+            allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
+            if self.rank == 0:
+                pD, pI = merge_candidates(allD2, allI2, None, k)
+                outD_t[idx] = pD
+                outI_t[idx] = pI
+        self.last_seed_misses = misses
+        mark("miss broadcast")
+        if prof:
+            torch.cuda.synchronize()
+            self.last_phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
+        if self.rank != 0:
+            return None, None
+        if self.id_map is not None:
+            outI_t = torch.where(outI_t >= 0, self.id_map[outI_t.clamp_min(0)], outI_t)
+        return outD_t, outI_t
+
     def search(self, q: torch.Tensor, k: int):
         """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
         if self.world == 1:
@@ -171,6 +343,9 @@ class ShardedSearcher:
         seeded = self.ntotal >= self.SEED_MIN_ROWS and n > 0
         seed = self._seed(q, k) if seeded else None
         mark("sample+allgather+seed")
+        px = self._peer_exchange(n, k)
+        if px is not None:
+            return self._search_p2p(px, q, k, seed, seeded, mark, marks, prof)
         D, I, eps2 = self.local.search_device_seeded(q, k, seed)
         mark("seeded search")
         D, I = self._trim(D, I)

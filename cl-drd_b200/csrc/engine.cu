@@ -10,6 +10,8 @@
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common_host.h"
@@ -163,6 +165,15 @@ struct cldrd_shard {
     size_t d_out_elems = 0;
 
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // scatter mode of the current search (cldrd_search_dev_scatter): results go to peer buffers
+    struct {
+        int world = 0, rank = 0;
+        int64_t slice = 0;
+        int64_t q0 = 0;   // first query of the current batch within the search
+        float* scores[CLDRD_MAX_PEERS];
+        int64_t* rows[CLDRD_MAX_PEERS];
+    } sc;
 
     // optional per-kernel timing of the scan launches (bench roofline): event pairs on the
     // launching stream, summed after the search's final synchronisation
@@ -539,12 +550,22 @@ int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool transl
     p.row0 = s->row0;
     p.ids = (translate && s->ids) ? s->ids : nullptr;
     const size_t ooff = out_index ? 0 : size_t(c.qoff) * c.k;
-    p.out_scores = out_scores + ooff;
-    p.out_ids = out_ids + ooff;
+    p.out_scores = out_scores ? out_scores + ooff : nullptr;   // NULL in scatter mode
+    p.out_ids = out_ids ? out_ids + ooff : nullptr;
     p.out_index = out_index;
     p.fail = fail_flags ? fail_flags + c.qoff : nullptr;
     p.fail_set = fail_flags ? fail_flags + c.qoff : nullptr;
     p.stats = s->w_stats;
+    p.sc_world = s->sc.world;
+    if (s->sc.world > 0) {
+        p.sc_rank = s->sc.rank;
+        p.sc_slice = s->sc.slice;
+        p.q_base = s->sc.q0 + (out_index ? 0 : c.qoff);
+        for (int i = 0; i < s->sc.world; ++i) {
+            p.sc_scores[i] = s->sc.scores[i];
+            p.sc_rows[i] = s->sc.rows[i];
+        }
+    }
     const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
     // few queries (the reference's batch=128 loop): one CTA per query leaves most SMs with a single
     // CTA, so give it twice the warps to keep the row gather's loads in flight; the per-row result
@@ -1072,7 +1093,7 @@ int64_t cldrd_shard_scan_bytes(const cldrd_shard* s) {
 static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
                          int seed_mode, const float* seed_dev, float* out_scores_dev, int64_t* out_ids_dev,
                          float* eps_out_dev, void* cuda_stream) {
-    if (!s || nq < 0 || (nq && (!q_dev || !out_scores_dev || !out_ids_dev)))
+    if (!s || nq < 0 || (nq && (!q_dev || (s->sc.world == 0 && (!out_scores_dev || !out_ids_dev)))))
         return fail(CLDRD_EINVAL, "search: NULL argument");
     if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "search: k=%d outside [1,%d]", k, CLDRD_MAX_K);
     if (!s->finalized) return fail(CLDRD_ESTATE, "search: shard not finalized");
@@ -1091,9 +1112,11 @@ static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t
     for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
         const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
         CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+        s->sc.q0 = q0;
         int rc = search_batch(s, q_dev + size_t(q0) * s->d, nb, k, translate_ids != 0, seed_mode,
-                              seed_dev ? seed_dev + q0 : nullptr, out_scores_dev + size_t(q0) * k,
-                              out_ids_dev + size_t(q0) * k, eps_out_dev ? eps_out_dev + q0 : nullptr, st, &totals);
+                              seed_dev ? seed_dev + q0 : nullptr, out_scores_dev ? out_scores_dev + size_t(q0) * k : nullptr,
+                              out_ids_dev ? out_ids_dev + size_t(q0) * k : nullptr, eps_out_dev ? eps_out_dev + q0 : nullptr,
+                              st, &totals);
         if (rc) return rc;
         for (int i = 0; i < ST_COUNT; ++i) {
             if (i == ST_MAX_LIST) tot[i] = std::max(tot[i], s->h_stats[i]);
@@ -1129,6 +1152,130 @@ int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int3
                             void* cuda_stream) {
     return search_common(s, q_dev, nq, k, translate_ids, seed_dev ? 2 : 0, seed_dev, out_scores_dev, out_ids_dev,
                          eps_out_dev, cuda_stream);
+}
+
+int cldrd_search_dev_scatter(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, const float* seed_dev,
+                             int32_t world, int32_t rank, int64_t slice, float* const* peer_scores,
+                             int64_t* const* peer_rows, float* eps_out_dev, void* cuda_stream) {
+    if (!s || !peer_scores || !peer_rows) return fail(CLDRD_EINVAL, "search_scatter: NULL argument");
+    if (world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || slice < 1 || nq > slice * world)
+        return fail(CLDRD_EINVAL, "search_scatter: world=%d rank=%d slice=%lld do not cover nq=%lld", world, rank,
+                    (long long)slice, (long long)nq);
+    for (int i = 0; i < world; ++i)
+        if (!peer_scores[i] || !peer_rows[i]) return fail(CLDRD_EINVAL, "search_scatter: NULL buffer of rank %d", i);
+    s->sc.world = world;
+    s->sc.rank = rank;
+    s->sc.slice = slice;
+    for (int i = 0; i < world; ++i) {
+        s->sc.scores[i] = peer_scores[i];
+        s->sc.rows[i] = peer_rows[i];
+    }
+    // the base pointers below are never dereferenced in scatter mode (only offset)
+    int rc = search_common(s, q_dev, nq, k, 0, seed_dev ? 2 : 0, seed_dev, nullptr, nullptr, eps_out_dev, cuda_stream);
+    s->sc.world = 0;
+    return rc;
+}
+
+// cudaMalloc may carve a small request out of a larger driver allocation; the IPC handle then names
+// the whole allocation and the peer's mapping starts at ITS base.  The handle we hand out therefore
+// carries the offset of our pointer inside that allocation (bytes 64..71).
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+static GetAddressRangeFn get_address_range_fn() {
+    static GetAddressRangeFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<GetAddressRangeFn>(p);
+    return fn;
+}
+static std::mutex g_peer_mu;
+static std::map<void*, void*> g_peer_base;   // pointer handed out by cldrd_peer_open -> mapping base
+
+int cldrd_peer_alloc(int device, int64_t nbytes, void** out_ptr, void* out_handle) {
+    if (!out_ptr || !out_handle || nbytes < 1) return fail(CLDRD_EINVAL, "peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(uint64_t) == CLDRD_PEER_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard g(device);
+    *out_ptr = nullptr;
+    // whole 2 MiB pages: smaller requests are carved out of a pool block that IPC would export as a whole
+    const size_t page = size_t(2) << 20;
+    const size_t alloc_bytes = (size_t(nbytes) + page - 1) / page * page;
+    cudaError_t e = cudaMalloc(out_ptr, alloc_bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CLDRD_ENOMEM : CLDRD_ECUDA, "peer_alloc: cudaMalloc(%lld): %s",
+                    (long long)nbytes, cudaGetErrorString(e));
+    }
+    // slice rows past the last query are merged too and nobody writes them: all-ones = row -1 = padding
+    cudaMemset(*out_ptr, 0xFF, alloc_bytes);
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, *out_ptr);
+    GetAddressRangeFn range = get_address_range_fn();
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const bool ranged = range && range(&base, &size, reinterpret_cast<CUdeviceptr>(*out_ptr)) == CUDA_SUCCESS;
+    if (e != cudaSuccess || !ranged) {
+        cudaGetLastError();
+        cudaFree(*out_ptr);
+        *out_ptr = nullptr;
+        return fail(CLDRD_ECUDA, "peer_alloc: %s", e != cudaSuccess ? cudaGetErrorString(e) : "cuMemGetAddressRange failed");
+    }
+    const uint64_t offset = uint64_t(reinterpret_cast<CUdeviceptr>(*out_ptr) - base);
+    memcpy(out_handle, &h, sizeof(h));
+    memcpy(static_cast<char*>(out_handle) + sizeof(h), &offset, sizeof(offset));
+    return CLDRD_OK;
+}
+
+int cldrd_peer_free(int device, void* ptr) {
+    if (!ptr) return CLDRD_OK;
+    DeviceGuard g(device);
+    CU_TRY(cudaFree(ptr));
+    return CLDRD_OK;
+}
+
+int cldrd_peer_open(int device, const void* handle, void** out_ptr) {
+    if (!handle || !out_ptr) return fail(CLDRD_EINVAL, "peer_open: bad argument");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    uint64_t offset = 0;
+    memcpy(&h, handle, sizeof(h));
+    memcpy(&offset, static_cast<const char*>(handle) + sizeof(h), sizeof(offset));
+    *out_ptr = nullptr;
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CLDRD_ECUDA, "peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    *out_ptr = static_cast<char*>(base) + offset;
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    g_peer_base[*out_ptr] = base;
+    return CLDRD_OK;
+}
+
+int cldrd_peer_close(int device, void* ptr) {
+    if (!ptr) return CLDRD_OK;
+    DeviceGuard g(device);
+    void* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_peer_mu);
+        auto it = g_peer_base.find(ptr);
+        if (it == g_peer_base.end()) return fail(CLDRD_EINVAL, "peer_close: not a pointer from cldrd_peer_open");
+        base = it->second;
+        g_peer_base.erase(it);
+    }
+    CU_TRY(cudaIpcCloseMemHandle(base));
+    return CLDRD_OK;
+}
+
+int cldrd_peer_copy(int device, void* dst, const void* src, int64_t nbytes, void* cuda_stream) {
+    if (nbytes < 0 || (nbytes && (!dst || !src))) return fail(CLDRD_EINVAL, "peer_copy: bad argument");
+    if (nbytes == 0) return CLDRD_OK;
+    DeviceGuard g(device);
+    CU_TRY(cudaMemcpyAsync(dst, src, size_t(nbytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
+    return CLDRD_OK;
 }
 
 int cldrd_sample_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, float* out_topj_dev, void* cuda_stream) {
@@ -1273,9 +1420,10 @@ void cldrd_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t w,
-                  int32_t k, const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
-    if (parts < 1 || nq < 0 || w < 1 || k < 1 || k > CLDRD_MAX_K ||
+int cldrd_merge_planes(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t plane_rows,
+                       int64_t nq, int32_t w, int32_t k, const int64_t* id_map_dev, float* out_scores_dev,
+                       int64_t* out_ids_dev, void* cuda_stream) {
+    if (parts < 1 || nq < 0 || nq > plane_rows || w < 1 || k < 1 || k > CLDRD_MAX_K ||
         (nq && (!scores_dev || !rows_dev || !out_scores_dev || !out_ids_dev)))
         return fail(CLDRD_EINVAL, "merge: bad argument");
     if (nq == 0) return CLDRD_OK;
@@ -1286,9 +1434,15 @@ int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, 
     DeviceGuard g(device);
     CU_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     merge_kernel<<<unsigned(nq), 512, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-        scores_dev, rows_dev, parts, nq, w, k, k_pad, id_map_dev, out_scores_dev, out_ids_dev);
+        scores_dev, rows_dev, parts, plane_rows, w, k, k_pad, id_map_dev, out_scores_dev, out_ids_dev);
     CU_TRY(cudaGetLastError());
     return CLDRD_OK;
+}
+
+int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t w,
+                  int32_t k, const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream) {
+    return cldrd_merge_planes(device, scores_dev, rows_dev, parts, nq, nq, w, k, id_map_dev, out_scores_dev, out_ids_dev,
+                              cuda_stream);
 }
 
 int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t nq, int32_t k,

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "cldrd.h"
 #include "device_common.cuh"
 
 namespace cldrd {
@@ -283,6 +284,14 @@ struct RescoreParams {
     const int* fail;      // skip failed queries (nullptr = none)
     int* fail_set;        // a list longer than n_pad (reduced-shared-memory launch) flags the query here
     unsigned long long* stats;
+    // scatter mode (sc_world > 0): output row r of this launch is query q_base + r of the search; it
+    // goes to plane [sc_rank], row Q % sc_slice of the buffers of rank Q / sc_slice (peer memory)
+    int sc_world;
+    int sc_rank;
+    long long sc_slice;
+    long long q_base;
+    float* sc_scores[CLDRD_MAX_PEERS];
+    int64_t* sc_rows[CLDRD_MAX_PEERS];
 };
 
 // One CTA per query: exact fp32 score of every listed row, sort, emit the k best.
@@ -317,8 +326,18 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     if (tid == 0) atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)L);
     block_bitonic_desc(keys, n_pad);
     const size_t orow = p.out_index ? size_t(p.out_index[q]) : size_t(q);
-    float* os = p.out_scores + orow * p.k;
-    int64_t* oi = p.out_ids + orow * p.k;
+    float* os;
+    int64_t* oi;
+    if (p.sc_world > 0) {
+        const long long Q = p.q_base + (long long)orow;
+        const int dest = int(Q / p.sc_slice);
+        const size_t at = (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * p.k;
+        os = p.sc_scores[dest] + at;
+        oi = p.sc_rows[dest] + at;
+    } else {
+        os = p.out_scores + orow * p.k;
+        oi = p.out_ids + orow * p.k;
+    }
     for (int i = tid; i < p.k; i += blockDim.x) {
         if (i < L) {
             uint64_t key = keys[i];
@@ -333,13 +352,13 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Multi-shard merge: [parts][nq][w] (score, global row; -1 = padding) -> [nq][k], same key order
+// Multi-shard merge: [parts][plane_rows][w] (score, global row; -1 = padding) -> [grid][k], same key order
 // as the single-shard search, so the result is bit-identical to it.  One CTA per query:
 // compact the valid entries, radix-select the k-th key, sort only the k survivors.
 // dyn smem: keys[parts*w] u64 | top[k_pad] u64
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) merge_kernel(const float* scores, const int64_t* rows,
-                                                    int parts, int64_t nq, int w, int k, int k_pad,
+                                                    int parts, int64_t plane_rows, int w, int k, int k_pad,
                                                     const int64_t* id_map, float* out_scores,
                                                     int64_t* out_ids) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -359,7 +378,7 @@ __global__ void __launch_bounds__(512) merge_kernel(const float* scores, const i
     __syncthreads();
     for (int i = tid; i < n_in; i += blockDim.x) {
         const int part = i / w, j = i - part * w;
-        const size_t off = (size_t(part) * nq + q) * w + j;
+        const size_t off = (size_t(part) * plane_rows + q) * w + j;
         const int64_t r = rows[off];
         if (r >= 0) keys[atomicAdd(&s_n, 1)] = make_key(scores[off], uint32_t(r));
     }
@@ -370,7 +389,10 @@ __global__ void __launch_bounds__(512) merge_kernel(const float* scores, const i
         const uint64_t kth = block_radix_select<64>(keys, n, k, hist, bcast);   // keys are distinct
         for (int i = tid; i < n; i += blockDim.x) {
             const uint64_t key = keys[i];
-            if (key >= kth) top[atomicAdd(&s_out, 1)] = key;
+            if (key >= kth) {
+                const int slot = atomicAdd(&s_out, 1);
+                if (slot < k) top[slot] = key;   // duplicate keys (malformed input) must not overrun `top`
+            }
         }
         m = k;
     } else {

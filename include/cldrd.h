@@ -154,6 +154,33 @@ int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int3
 int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k,
                       const float* seed_dev, const float* eps2_dev, int32_t* fail_dev,
                       void* cuda_stream);
+/* Step 3 fused with the exchange (one process per GPU on ONE node, NVLink / NVSwitch peer memory):
+ * the same seeded search, but the re-score kernel stores each query's list straight into the
+ * exchange buffer of the rank that will merge that query, instead of a local array that an NCCL
+ * all-to-all would then move.  Query Q (0 <= Q < nq) belongs to rank Q / slice; in that rank's buffers
+ * (peer_scores[dest], float32, and peer_rows[dest], int64 GLOBAL rows, both laid out
+ * [world][slice][k]) this shard fills plane [rank], row Q % slice, all k columns (-FLT_MAX / -1
+ * padded).  peer_scores / peer_rows are HOST arrays of `world` device pointers valid in this
+ * process (cldrd_peer_open of the owners' handles; the own entry is the own allocation).  After a
+ * barrier over the ranks, each rank merges its planes with cldrd_merge_planes(parts=world, w=k).
+ * world <= CLDRD_MAX_PEERS.  seed_dev NULL = unseeded (retry of seed misses). */
+#define CLDRD_MAX_PEERS 16
+int cldrd_search_dev_scatter(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
+                             const float* seed_dev, int32_t world, int32_t rank, int64_t slice,
+                             float* const* peer_scores, int64_t* const* peer_rows,
+                             float* eps2_out_dev, void* cuda_stream);
+/* Exchange buffers for the call above: device memory that other processes of the node can map.
+ * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
+ * cldrd.dist sends them through its process group); cldrd_peer_open maps a peer's handle into this process
+ * (`device` = the opening process' GPU; needs peer access between the two GPUs);
+ * cldrd_peer_copy is a stream-ordered device-to-device copy between any two such pointers. */
+#define CLDRD_PEER_HANDLE_BYTES 72
+int cldrd_peer_alloc(int device, int64_t nbytes, void** out_ptr, void* out_handle);
+int cldrd_peer_free(int device, void* ptr);
+int cldrd_peer_open(int device, const void* handle, void** out_ptr);
+int cldrd_peer_close(int device, void* ptr);
+int cldrd_peer_copy(int device, void* dst, const void* src, int64_t nbytes, void* cuda_stream);
+
 /* The error band uses the largest row norm of the index: shards of one index must agree on it
  * (all-reduce MAX of cldrd_shard_norm_bound, then cldrd_shard_set_norm_bound on every shard). */
 int cldrd_shard_norm_bound(const cldrd_shard* s, float* out);
@@ -183,6 +210,14 @@ int cldrd_merge(int device, const float* scores_dev, const int64_t* rows_dev, in
 int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
                   int64_t nq, int32_t w, int32_t k, const int64_t* id_map_dev,
                   float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
+
+/* Same with planes that hold more rows than are merged: input [parts][plane_rows][w], the first
+ * nq <= plane_rows rows of every plane are merged (the exchange buffers of cldrd_search_dev_scatter:
+ * plane_rows = slice, nq = the queries this rank owns). */
+int cldrd_merge_planes(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
+                       int64_t plane_rows, int64_t nq, int32_t w, int32_t k,
+                       const int64_t* id_map_dev, float* out_scores_dev, int64_t* out_ids_dev,
+                       void* cuda_stream);
 
 /* Per-search statistics of the last cldrd_search_* call on this shard (for tests / bench):
  * stats[0] kernel launches, [1] index chunks scanned, [2] queries sent to the dense fallback,

@@ -25,7 +25,11 @@ def main():
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
     res = {}
-    for name, n, d, nq, k in [("small", 50_000, 64, 70, 100), ("big", 1_300_000, 64, 70, 100)]:
+    # (name, rows, d, queries, k, seed bias): "manyq" crosses the 8192-query batch of the engine and is not a
+    # multiple of the world size; "miss" pushes every seed above every score so that all queries take the retry
+    cases = [("small", 50_000, 64, 71, 100, None), ("big", 1_300_000, 64, 71, 100, None),
+             ("manyq", 60_000, 64, 8301, 10, None), ("miss", 1_300_000, 64, 33, 50, "1e6")]
+    for name, n, d, nq, k, bias in cases:
         rng = np.random.Generator(np.random.PCG64(300))
         xb = rng.standard_normal((n, d), dtype=np.float32)
         xq = rng.standard_normal((nq, d), dtype=np.float32)
@@ -34,19 +38,32 @@ def main():
         rows = torch.from_numpy(xb[rr.start:rr.stop]).to(dev)
         q = torch.from_numpy(xq).to(dev)
         id_map = torch.from_numpy(ids).to(dev) if rank == 0 else None
+        os.environ["CLDRD_SEED_BIAS"] = bias or "0"
         s = CD.ShardedSearcher.from_rows(rows, rr.start, n, scan="f16", id_map=id_map)
-        D, I = s.search(q, k)
+        os.environ["CLDRD_SEED_BIAS"] = "0"
+        out = {}
+        for transport in ("p2p", "nccl"):      # peer-memory scatter (default) and the NCCL all-to-all path
+            os.environ["CLDRD_DIST_P2P"] = "1" if transport == "p2p" else "0"
+            out[transport] = s.search(q, k)
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] {name}/{transport} done", file=sys.stderr, flush=True)
+            if transport == "p2p":
+                res[f"p2p_used_{name}"] = getattr(s, "_px", None) is not None
+                res[f"seed_misses_{name}"] = getattr(s, "last_seed_misses", None)
+        os.environ["CLDRD_DIST_P2P"] = "1"
         if rank == 0:
             full = torch.from_numpy(xb).to(dev)
             one = CD.ShardedSearcher.from_rows(full, 0, n, scan="f16", id_map=id_map)
             one.world, one.rank = 1, 0
             D1, I1 = one.search(q, k)
-            res[f"bit_equal_{name}"] = bool(torch.equal(D, D1) and torch.equal(I, I1))
+            for transport, (D, I) in out.items():
+                res[f"bit_equal_{name}_{transport}"] = bool(torch.equal(D, D1) and torch.equal(I, I1))
             if name == "big":
+                D, I = out["p2p"]
                 D_ref, I_ref = O.search(xb, ids, xq, k)
                 r = O.compare_topk(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, *O.search(xb, ids, xq, k + 16, dtype=np.float64))
                 res["oracle_ok"] = bool(r["ok"])
-                res["seed_misses"] = getattr(s, "last_seed_misses", None)
+            one.shard.close()
         dist.barrier()
     if rank == 0:
         with open(args.out, "w") as f:

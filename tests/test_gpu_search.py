@@ -453,7 +453,8 @@ def _norm_bound(searcher):
 
 
 def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
-    """One process per GPU over NCCL (needs 2 GPUs): sharded result == single-GPU result, bit for bit."""
+    """One process per GPU (needs 2 GPUs): sharded result == single-GPU result, bit for bit, through the
+    peer-memory scatter (default) and through the NCCL all-to-all path."""
     import subprocess
     import sys
     import torch
@@ -464,10 +465,14 @@ def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tests", "dist_worker.py"), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-8000:]
     import json
     res = json.loads(out.read_text())
-    assert res["bit_equal_small"] and res["bit_equal_big"] and res["oracle_ok"], res
+    for name in ("small", "big", "manyq", "miss"):
+        assert res[f"bit_equal_{name}_p2p"] and res[f"bit_equal_{name}_nccl"], res
+        assert res[f"p2p_used_{name}"], res          # the peer-memory exchange is the path that ran
+    assert res["oracle_ok"], res
+    assert res["seed_misses_miss"] == 33 and res["seed_misses_big"] == 0, res
 
 
 def test_more_queries_than_one_batch(cldrd_lib):
