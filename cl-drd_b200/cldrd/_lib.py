@@ -13,6 +13,7 @@ SCAN_NAMES = {"simt": SCAN_SIMT_F32, "tf32": SCAN_TC_TF32, "f16": SCAN_TC_F16, "
 MAX_K = 2048
 SEED_J = 32
 MAX_PEERS = 16            # CLDRD_MAX_PEERS
+QUERY_BATCH = 8192        # CLDRD_QUERY_BATCH
 PEER_HANDLE_BYTES = 72    # CLDRD_PEER_HANDLE_BYTES
 
 E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
@@ -59,6 +60,10 @@ SIGNATURES = {
     "cldrd_verify_seed": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_search_dev_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "cldrd_levels_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cldrd_scatter_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_scatter_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "cldrd_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "cldrd_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cldrd_peer_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -208,18 +208,19 @@ class ShardedSearcher:
         check(lib().cldrd_shard_set_norm_bound(self.shard.handle, C.c_float(float(t.item()))))
         self._norm_synced = True
 
-    def _seed(self, q: torch.Tensor, k: int) -> torch.Tensor:
-        """Steps 1+2: sample every shard, all-gather the per-shard sample scores (NCCL), take the
-        global SEED_J-th best as the scan-score threshold of each query."""
+    def _levels(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        """Steps 1+2: sample every shard, all-gather the per-shard sample scores (NCCL), keep the SEED_J best
+        of the union per query, best first.  The last column is the seed (a scan-score threshold near rank
+        3.5k of the whole index); the columns before it are the levels the shards count against."""
         n = q.shape[0]
         topj = self.local.sample_device(q, k)
         allj = torch.empty((self.world,) + tuple(topj.shape), dtype=topj.dtype, device=topj.device)
         dist.all_gather_into_tensor(allj, topj, group=self.group)
-        seed = torch.empty((n,), dtype=torch.float32, device=q.device)
+        levels = torch.empty((n, _lib.SEED_J), dtype=torch.float32, device=q.device)
         st = torch.cuda.current_stream(q.device).cuda_stream
-        check(lib().cldrd_seed_from_samples(q.device.index, C.c_void_p(allj.data_ptr()), self.world, n,
-                                            C.c_void_p(seed.data_ptr()), C.c_void_p(st)))
-        return seed
+        check(lib().cldrd_levels_from_samples(q.device.index, C.c_void_p(allj.data_ptr()), self.world, n,
+                                              C.c_void_p(levels.data_ptr()), C.c_void_p(st)))
+        return levels
 
     def _trim(self, D: torch.Tensor, I: torch.Tensor):
         """A seeded shard returns far fewer than k valid rows per query (about 3.5k / world): agree
@@ -254,21 +255,34 @@ class ShardedSearcher:
             self._px_disabled = True   # agreed by all ranks (all-reduce MIN): nobody retries
         return self._px
 
-    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, seed, seeded: bool, mark, marks, prof):
-        """Seeded search whose re-score kernel stores every query's list in the merging rank's memory
-        (NVLink peer stores), slice-wise merge + verify on every rank, merge kernels store into rank 0's
-        result buffer.  Two tiny all-reduces are the only collectives after the seed: they are the
-        barriers between the three kernels' peer accesses."""
+    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, levels, seed, mark, marks, prof):
+        """Per batch of <= 8192 queries: scan + select with the seed and count the candidates above every
+        sample level; all-reduce the counts (32 ints per query) so that every shard knows a threshold that k
+        rows of the WHOLE index reach, and re-scores only what lies above it (about k / world rows per query);
+        the re-score kernel stores every query's list in the merging rank's memory (NVLink peer stores).
+        Then slice-wise merge + verify on every rank, the merge kernels storing into rank 0's result buffer.
+        Two scalar all-reduces are the barriers between the kernels' peer accesses."""
         n, world, dev = q.shape[0], self.world, q.device
+        seeded = levels is not None
         sl = (n + world - 1) // world
         st = torch.cuda.current_stream(dev).cuda_stream
         eps2 = torch.empty((n,), dtype=torch.float32, device=dev)
         token = torch.zeros((1,), dtype=torch.int32, device=dev)
         with self.local._lock:
-            check(lib().cldrd_search_dev_scatter(self.shard.handle, C.c_void_p(q.data_ptr()), n, int(k),
-                                                 C.c_void_p(seed.data_ptr()) if seed is not None else None,
-                                                 world, self.rank, sl, px.c_xD, px.c_xI, C.c_void_p(eps2.data_ptr()),
-                                                 C.c_void_p(st)))
+            for b0 in range(0, n, _lib.QUERY_BATCH):
+                nb = min(_lib.QUERY_BATCH, n - b0)
+                qb = q[b0:b0 + nb]
+                lv = levels[b0:b0 + nb] if seeded else None
+                counts = torch.empty((nb, _lib.SEED_J), dtype=torch.int32, device=dev)
+                check(lib().cldrd_scatter_begin(self.shard.handle, C.c_void_p(qb.data_ptr()), nb, int(k),
+                                                C.c_void_p(lv.data_ptr()) if seeded else None,
+                                                C.c_void_p(counts.data_ptr()), C.c_void_p(eps2[b0:].data_ptr()),
+                                                C.c_void_p(st)))
+                if seeded:
+                    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+                check(lib().cldrd_scatter_finish(self.shard.handle, C.c_void_p(counts.data_ptr()),
+                                                 C.c_void_p(lv.data_ptr()) if seeded else None, world, self.rank, sl, b0,
+                                                 px.c_xD, px.c_xI, C.c_void_p(st)))
         mark("seeded search + scatter")
         dist.all_reduce(token, group=self.group)            # every plane of my buffers is written
         if os.environ.get("CLDRD_DIST_DEBUG") == "1":
@@ -341,11 +355,12 @@ class ShardedSearcher:
 
         mark("start")
         seeded = self.ntotal >= self.SEED_MIN_ROWS and n > 0
-        seed = self._seed(q, k) if seeded else None
+        levels = self._levels(q, k) if seeded else None
+        seed = levels[:, _lib.SEED_J - 1].contiguous() if seeded else None
         mark("sample+allgather+seed")
         px = self._peer_exchange(n, k)
         if px is not None:
-            return self._search_p2p(px, q, k, seed, seeded, mark, marks, prof)
+            return self._search_p2p(px, q, k, levels, seed, mark, marks, prof)
         D, I, eps2 = self.local.search_device_seeded(q, k, seed)
         mark("seeded search")
         D, I = self._trim(D, I)

@@ -166,6 +166,16 @@ struct cldrd_shard {
 
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+    // two-phase sharded search (cldrd_scatter_begin / cldrd_scatter_finish): the batch between the calls
+    struct {
+        bool active = false;
+        const float* q = nullptr;
+        int nq = 0, k = 0;
+        bool seeded = false;
+        int64_t launches = 0, chunks = 0;
+    } pend;
+    float* w_cut = nullptr;       // [kQueryBatch] re-score cut of the pending batch
+
     // scatter mode of the current search (cldrd_search_dev_scatter): results go to peer buffers
     struct {
         int world = 0, rank = 0;
@@ -213,6 +223,8 @@ void free_workspace(cldrd_shard* s) {
     s->w_unit_ctr = nullptr;
     cudaFree(s->w_fail);
     cudaFree(s->w_fail_index);
+    cudaFree(s->w_cut);
+    s->w_cut = nullptr;
     cudaFree(s->w_list);
     cudaFree(s->w_surv);
     cudaFree(s->w_dense);
@@ -249,6 +261,7 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMemset(s->w_wait, 0, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->w_cut, Q * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
     CU_TRY(cudaMalloc(&s->w_surv, kSurvTotal * sizeof(uint64_t)));
     CU_TRY(cudaMalloc(&s->w_dense, Q * kDensePiece * sizeof(float)));
@@ -535,7 +548,7 @@ int launch_prep(BatchCtx& c) {
 // at most that many entries (so that the CTAs fit next to a running scan CTA); longer lists are
 // flagged as failed and redone by the fallback.
 int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool translate, const int* out_index,
-                   int* fail_flags, cudaStream_t st, int n_pad_small = 0) {
+                   int* fail_flags, cudaStream_t st, int n_pad_small = 0, const float* cut = nullptr) {
     cldrd_shard* s = c.s;
     RescoreParams p{};
     p.xb = s->xb;
@@ -556,6 +569,7 @@ int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool transl
     p.fail = fail_flags ? fail_flags + c.qoff : nullptr;
     p.fail_set = fail_flags ? fail_flags + c.qoff : nullptr;
     p.stats = s->w_stats;
+    p.cut = cut ? cut + c.qoff : nullptr;
     p.sc_world = s->sc.world;
     if (s->sc.world > 0) {
         p.sc_rank = s->sc.rank;
@@ -1193,6 +1207,146 @@ static GetAddressRangeFn get_address_range_fn() {
 }
 static std::mutex g_peer_mu;
 static std::map<void*, void*> g_peer_base;   // pointer handed out by cldrd_peer_open -> mapping base
+
+static_assert(kQueryBatch == CLDRD_QUERY_BATCH, "header and engine disagree on the query batch");
+
+int cldrd_levels_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq, float* levels_out_dev,
+                              void* cuda_stream) {
+    if (!topj_dev || !levels_out_dev || parts < 1 || parts > CLDRD_MAX_PEERS || nq < 1)
+        return fail(CLDRD_EINVAL, "levels_from_samples: bad argument");
+    DeviceGuard g(device);
+    levels_from_samples_kernel<<<unsigned(nq), 128, size_t(parts) * CLDRD_SEED_J * sizeof(float),
+                                 static_cast<cudaStream_t>(cuda_stream)>>>(topj_dev, parts, int(nq), CLDRD_SEED_J,
+                                                                           levels_out_dev);
+    CU_TRY(cudaGetLastError());
+    return CLDRD_OK;
+}
+
+int cldrd_scatter_begin(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, const float* levels_dev,
+                        int32_t* counts_out_dev, float* eps_out_dev, void* cuda_stream) {
+    if (!s || !q_dev || !counts_out_dev || nq < 1 || nq > kQueryBatch)
+        return fail(CLDRD_EINVAL, "scatter_begin: bad argument (1 <= nq <= %d)", kQueryBatch);
+    if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "scatter_begin: k=%d outside [1,%d]", k, CLDRD_MAX_K);
+    if (!s->finalized) return fail(CLDRD_ESTATE, "scatter_begin: shard not finalized");
+    if (s->pend.active) return fail(CLDRD_ESTATE, "scatter_begin: the previous batch was not finished");
+    if (reinterpret_cast<uintptr_t>(q_dev) % 16 && is_tc(s->scan_eff))
+        return fail(CLDRD_EINVAL, "search: query buffer must be 16-byte aligned");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    s->ev_used = 0;
+    s->scan_ms = 0.0;
+    s->scan_launches = 0;
+    s->ev_rows.clear();
+    s->ev_ms.clear();
+    CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+    BatchCtx c{};
+    c.s = s;
+    c.st = st;
+    c.q = q_dev;
+    c.nq = int(nq);
+    c.k = k;
+    int rc = launch_prep(c);
+    if (rc) return rc;
+    const bool seeded = levels_dev != nullptr;
+    if (seeded) {
+        const SamplePlan sp = sample_plan(s, k);
+        const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
+        c.seed_rank = double(CLDRD_SEED_J) / frac;
+        // the seed is the last level: gather column J-1 into the workspace
+        CU_TRY(cudaMemcpy2DAsync(s->w_seed_in, sizeof(float), levels_dev + (CLDRD_SEED_J - 1), CLDRD_SEED_J * sizeof(float),
+                                 sizeof(float), size_t(nq), cudaMemcpyDeviceToDevice, st));
+        if ((rc = apply_seed(c, s->w_seed_in))) return rc;
+    }
+    if ((rc = run_chunks(c, seeded ? PASS_SEEDED : PASS_PROGRESSIVE))) return rc;
+    if (seeded) {
+        count_levels_kernel<<<unsigned(nq), 256, 0, st>>>(s->w_list, s->w_list_len, s->ws_keep_cap, s->w_fail, levels_dev,
+                                                          CLDRD_SEED_J, counts_out_dev);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+    } else {
+        CU_TRY(cudaMemsetAsync(counts_out_dev, 0, size_t(nq) * CLDRD_SEED_J * sizeof(int32_t), st));
+    }
+    if (eps_out_dev)
+        CU_TRY(cudaMemcpyAsync(eps_out_dev, s->w_band, size_t(nq) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s->pend.active = true;
+    s->pend.q = q_dev;
+    s->pend.nq = int(nq);
+    s->pend.k = k;
+    s->pend.seeded = seeded;
+    s->pend.launches = c.launches;
+    s->pend.chunks = c.chunks;
+    return CLDRD_OK;
+}
+
+int cldrd_scatter_finish(cldrd_shard* s, const int32_t* counts_dev, const float* levels_dev, int32_t world, int32_t rank,
+                         int64_t slice, int64_t q_base, float* const* peer_scores, int64_t* const* peer_rows,
+                         void* cuda_stream) {
+    if (!s || !peer_scores || !peer_rows) return fail(CLDRD_EINVAL, "scatter_finish: NULL argument");
+    if (!s->pend.active) return fail(CLDRD_ESTATE, "scatter_finish: no batch pending (call cldrd_scatter_begin)");
+    const int nq = s->pend.nq, k = s->pend.k;
+    s->pend.active = false;
+    if (world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || slice < 1 || q_base < 0 ||
+        q_base + nq > slice * world)
+        return fail(CLDRD_EINVAL, "scatter_finish: world=%d rank=%d slice=%lld do not cover queries [%lld, %lld)", world,
+                    rank, (long long)slice, (long long)q_base, (long long)(q_base + nq));
+    if (s->pend.seeded && (!counts_dev || !levels_dev)) return fail(CLDRD_EINVAL, "scatter_finish: NULL counts / levels");
+    for (int i = 0; i < world; ++i)
+        if (!peer_scores[i] || !peer_rows[i]) return fail(CLDRD_EINVAL, "scatter_finish: NULL buffer of rank %d", i);
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    BatchCtx c{};
+    c.s = s;
+    c.st = st;
+    c.q = s->pend.q;
+    c.nq = nq;
+    c.k = k;
+    const float* cut = nullptr;
+    if (s->pend.seeded) {
+        cut_from_counts_kernel<<<(nq + 255) / 256, 256, 0, st>>>(counts_dev, levels_dev, s->w_band, nq, CLDRD_SEED_J, k, s->w_cut);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+        cut = s->w_cut;
+    }
+    s->sc.world = world;
+    s->sc.rank = rank;
+    s->sc.slice = slice;
+    s->sc.q0 = q_base;
+    for (int i = 0; i < world; ++i) {
+        s->sc.scores[i] = peer_scores[i];
+        s->sc.rows[i] = peer_rows[i];
+    }
+    SearchTotals totals;
+    totals.launches = s->pend.launches;
+    totals.chunks = s->pend.chunks;
+    int rc = launch_rescore(c, nullptr, nullptr, false, nullptr, s->w_fail, st, 0, cut);
+    if (!rc) rc = read_stats(s, st);
+    totals.launches += c.launches;
+    if (!rc && s->h_stats[ST_RANGE_ERR])
+        rc = fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
+    unsigned long long first[ST_COUNT];
+    memcpy(first, s->h_stats, sizeof(first));
+    if (!rc && s->h_stats[ST_FAILED] != 0)
+        rc = run_fallbacks(s, s->pend.q, nq, k, false, nullptr, nullptr, st, s->pend.seeded, &totals);
+    s->sc.world = 0;
+    if (rc) return rc;
+    if (s->profile) {
+        for (size_t i = 0; i + 1 < s->ev_used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->scan_ms += ms;
+            s->ev_ms.push_back(ms);
+            s->scan_launches++;
+        }
+    }
+    s->stats[0] = totals.launches;
+    s->stats[1] = totals.chunks;
+    s->stats[2] = totals.fallback_queries;
+    s->stats[3] = int64_t(first[ST_RESCORED]);
+    s->stats[4] = int64_t(first[ST_SURVIVORS]);
+    s->stats[5] = int64_t(first[ST_MAX_LIST]);
+    s->stats[6] = int64_t(first[ST_TILES]);
+    s->stats[7] = int64_t(first[ST_EXACT_COMPACT]);
+    return CLDRD_OK;
+}
 
 int cldrd_peer_alloc(int device, int64_t nbytes, void** out_ptr, void* out_handle) {
     if (!out_ptr || !out_handle || nbytes < 1) return fail(CLDRD_EINVAL, "peer_alloc: bad argument");

@@ -284,6 +284,9 @@ struct RescoreParams {
     const int* fail;      // skip failed queries (nullptr = none)
     int* fail_set;        // a list longer than n_pad (reduced-shared-memory launch) flags the query here
     unsigned long long* stats;
+    // optional [nq]: list entries whose SCAN score is below cut[q] are dropped unscored (sharded search:
+    // the shards agreed that such rows cannot be in the global top-k)
+    const float* cut;
     // scatter mode (sc_world > 0): output row r of this launch is query q_base + r of the search; it
     // goes to plane [sc_rank], row Q % sc_slice of the buffers of rank Q / sc_slice (peer memory)
     int sc_world;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     if (p.fail && p.fail[q]) return;
-    const int L = p.list_len[q];
+    int L = p.list_len[q];
     if (L > p.n_pad) {   // only possible when launched with less shared memory than keep_cap needs
         if (tid == 0 && p.fail_set) {
             p.fail_set[q] = 1;
@@ -315,14 +318,27 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     int n_pad = 2;
     while (n_pad < L) n_pad <<= 1;
     for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
+    __shared__ int s_kept;
+    if (tid == 0) s_kept = 0;
     __syncthreads();
     const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const uint32_t cut_ord = p.cut ? f2ord(p.cut[q]) : 0u;
+    int kept = 0;
     for (int i = warp; i < L; i += nwarps) {
-        const uint32_t row = key_row(my_list[i]);
+        const uint64_t cand = my_list[i];
+        if (key_ord(cand) < cut_ord) {   // warp-uniform
+            if (lane == 0) keys[i] = 0;
+            continue;
+        }
+        const uint32_t row = key_row(cand);
         float s = exact_dot_warp(q_s, p.xb + size_t(row) * p.d, p.d, p.vec4 != 0, lane);
         if (lane == 0) keys[i] = make_key(s, row);
+        ++kept;
     }
+    if (lane == 0 && kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    L = s_kept;                      // dropped entries are zero keys: they sort behind the kept ones
     if (tid == 0) atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)L);
     block_bitonic_desc(keys, n_pad);
     const size_t orow = p.out_index ? size_t(p.out_index[q]) : size_t(q);
@@ -594,6 +610,81 @@ __global__ void seed_from_samples_kernel(const float* topj, int parts, int nq, i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) seed[q] = best;
+}
+
+// levels[q][0..j) = the j best of the parts*j sample scores gathered from all shards, best first
+// (levels[q][j-1] is the seed of seed_from_samples_kernel).  One CTA per query; dyn smem parts*j floats.
+__global__ void levels_from_samples_kernel(const float* topj, int parts, int nq, int j, float* levels) {
+    extern __shared__ float lv_s[];
+    const int q = blockIdx.x;
+    const int n = parts * j;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const int part = c / j, i = c - part * j;
+        lv_s[c] = topj[(size_t(part) * nq + q) * j + i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const float v = lv_s[c];
+        int r = 0;
+        for (int t = 0; t < n; ++t) {
+            const float x = lv_s[t];
+            r += (x > v) || (x == v && t < c);
+        }
+        if (r < j) levels[size_t(q) * j + r] = v;
+    }
+}
+
+// counts[q][b] = how many entries of this shard's candidate list have a scan score >= levels[q][b]
+// (levels descending, j <= 64).  Failed queries (redone by the fallback) count nothing, which is safe:
+// the counts only have to be lower bounds.
+__global__ void count_levels_kernel(const uint64_t* list, const int* list_len, int keep_cap, const int* fail,
+                                    const float* levels, int j, int* counts) {
+    __shared__ int hist[64];
+    __shared__ float lv[64];
+    const int q = blockIdx.x;
+    if (threadIdx.x < j) {
+        hist[threadIdx.x] = 0;
+        lv[threadIdx.x] = levels[size_t(q) * j + threadIdx.x];
+    }
+    __syncthreads();
+    const int L = (fail && fail[q]) ? 0 : list_len[q];
+    const uint64_t* my = list + size_t(q) * keep_cap;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float sc = ord2f(key_ord(my[i]));
+        int lo = 0, hi = j;            // smallest b with lv[b] <= sc
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (lv[mid] <= sc) hi = mid;
+            else lo = mid + 1;
+        }
+        if (lo < j) atomicAdd(&hist[lo], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < j; ++b) {
+            acc += hist[b];
+            counts[size_t(q) * j + b] = acc;
+        }
+    }
+}
+
+// cut[q] = T - 2*eps for the highest level T that at least k rows of the WHOLE index reach in scan score
+// (counts summed over the shards), -inf if no level does.  Why it is safe: k rows with scan score >= T
+// have exact score >= T - eps, so the exact k-th best is >= T - eps, and a row of the top-k has scan
+// score >= T - 2*eps.
+__global__ void cut_from_counts_kernel(const int* counts, const float* levels, const float* band, int nq, int j,
+                                       int k, float* cut) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float c = -INFINITY;
+    for (int b = 0; b < j; ++b) {
+        if (counts[size_t(q) * j + b] >= k) {
+            c = levels[size_t(q) * j + b] - band[q];
+            break;
+        }
+    }
+    cut[q] = c;
 }
 
 // After the exact re-score: fail[q] = 1 unless the k-th returned score clears seed + eps.

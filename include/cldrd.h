@@ -169,7 +169,30 @@ int cldrd_search_dev_scatter(cldrd_shard* s, const float* q_dev, int64_t nq, int
                              const float* seed_dev, int32_t world, int32_t rank, int64_t slice,
                              float* const* peer_scores, int64_t* const* peer_rows,
                              float* eps2_out_dev, void* cuda_stream);
-/* Exchange buffers for the call above: device memory that other processes of the node can map.
+/* The same in two calls per batch of at most CLDRD_QUERY_BATCH queries, with one more exchange in
+ * between, so that a shard re-scores only what can still reach the GLOBAL top-k (about k / world rows
+ * per query instead of everything above the seed):
+ *   cldrd_levels_from_samples: levels[q][0..J) = the J best sample scores of the all-gathered samples,
+ *       best first (J = CLDRD_SEED_J; levels[q][J-1] is the seed of cldrd_seed_from_samples).
+ *   cldrd_scatter_begin: scan + select with that seed; counts_out[q][b] = how many candidates of this
+ *       shard have a scan score >= levels[q][b].  levels_dev NULL = unseeded (counts are zeroed).
+ *   (caller: all-reduce SUM of the counts over the shards)
+ *   cldrd_scatter_finish: T = the highest level that >= k rows of the whole index reach; candidates with
+ *       scan score < T - 2*eps are dropped (k rows with scan score >= T put the exact k-th score above
+ *       T - eps, so a top-k row scans above T - 2*eps); the rest are re-scored and stored as in
+ *       cldrd_search_dev_scatter, batch query i being query q_base + i of the search.
+ * One batch in flight per shard; q_dev must stay valid until cldrd_scatter_finish returns. */
+#define CLDRD_QUERY_BATCH 8192
+int cldrd_levels_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq,
+                              float* levels_out_dev, void* cuda_stream);
+int cldrd_scatter_begin(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
+                        const float* levels_dev, int32_t* counts_out_dev, float* eps2_out_dev,
+                        void* cuda_stream);
+int cldrd_scatter_finish(cldrd_shard* s, const int32_t* counts_dev, const float* levels_dev,
+                         int32_t world, int32_t rank, int64_t slice, int64_t q_base,
+                         float* const* peer_scores, int64_t* const* peer_rows, void* cuda_stream);
+
+/* Exchange buffers for the calls above: device memory that other processes of the node can map.
  * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
  * cldrd.dist sends them through its process group); cldrd_peer_open maps a peer's handle into this process
  * (`device` = the opening process' GPU; needs peer access between the two GPUs);

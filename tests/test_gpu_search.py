@@ -622,3 +622,79 @@ def test_embedding_like_distribution_stays_exact_and_seeded(cldrd_lib, scan):
     # the premise of the test: scores far from zero compared with their spread inside the top-k
     assert (D[:, 0] - D[:, -1]).max() < 0.2 * D[:, -1].min()
     gpu.close()
+
+
+@pytest.mark.parametrize("k", [100, 1000])
+def test_two_phase_scatter_protocol_on_one_gpu(cldrd_lib, k):
+    """The sharded search of cldrd.dist without processes: 3 shards on one GPU, plain device buffers standing
+    in for the peers' exchange buffers.  levels -> scatter_begin -> sum of counts -> scatter_finish (re-score
+    only above the agreed cut, results stored plane-wise into the owner's buffers) -> merge_planes.  Must equal
+    the single-shard search bit for bit, and the cut must really cut."""
+    import torch
+    from cldrd import dist as CD
+    from cldrd._lib import check, lib, SEED_J
+    from cldrd.index import shard_ranges
+    xb, xq = _big(nq=70, seed=203)
+    N, nq, world = xb.shape[0], xq.shape[0], 3
+    rows = torch.from_numpy(xb).cuda()
+    q = torch.from_numpy(xq).cuda()
+    one = CD.ShardedSearcher.from_rows(rows, 0, N, scan="f16")
+    D1, I1 = one.local.search_device(q, k, translate_ids=False)
+    shards = [CD.ShardedSearcher.from_rows(rows[rr.start:rr.stop], rr.start, N, scan="f16") for rr in shard_ranges(N, world)]
+    bound = max(_norm_bound(s) for s in shards + [one])
+    for s in shards:
+        check(lib().cldrd_shard_set_norm_bound(s.shard.handle, C.c_float(bound)))
+    topj = torch.stack([s.local.sample_device(q, k) for s in shards])
+    levels = torch.empty((nq, SEED_J), dtype=torch.float32, device="cuda")
+    check(lib().cldrd_levels_from_samples(0, C.c_void_p(topj.data_ptr()), world, nq, C.c_void_p(levels.data_ptr()), None))
+    seed = torch.empty((nq,), dtype=torch.float32, device="cuda")
+    check(lib().cldrd_seed_from_samples(0, C.c_void_p(topj.data_ptr()), world, nq, C.c_void_p(seed.data_ptr()), None))
+    torch.cuda.synchronize()
+    lv = levels.cpu().numpy()
+    assert (np.diff(lv, axis=1) <= 0).all() and np.array_equal(lv[:, -1], seed.cpu().numpy())
+    sl = (nq + world - 1) // world
+    xD = [torch.full((world, sl, k), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+    xI = [torch.full((world, sl, k), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    c_xD = (C.c_void_p * world)(*[t.data_ptr() for t in xD])
+    c_xI = (C.c_void_p * world)(*[t.data_ptr() for t in xI])
+    counts = [torch.empty((nq, SEED_J), dtype=torch.int32, device="cuda") for _ in range(world)]
+    eps2 = torch.empty((nq,), dtype=torch.float32, device="cuda")
+    for r, s in enumerate(shards):
+        check(lib().cldrd_scatter_begin(s.shard.handle, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(levels.data_ptr()),
+                                        C.c_void_p(counts[r].data_ptr()), C.c_void_p(eps2.data_ptr()), None))
+    # a second begin without finish is a state error, not a silent overwrite
+    rc = lib().cldrd_scatter_begin(shards[0].shard.handle, C.c_void_p(q.data_ptr()), nq, k, None,
+                                   C.c_void_p(counts[0].data_ptr()), None, None)
+    assert rc != 0
+    total = torch.stack(counts).sum(dim=0).to(torch.int32).contiguous()
+    tc = total.cpu().numpy()
+    assert (np.diff(tc, axis=1) >= 0).all() and (tc[:, -1] >= k).all()      # counts grow level by level; the seed level clears k
+    rescored = 0
+    for r, s in enumerate(shards):
+        check(lib().cldrd_scatter_finish(s.shard.handle, C.c_void_p(total.data_ptr()), C.c_void_p(levels.data_ptr()), world, r, sl,
+                                         0, c_xD, c_xI, None))
+        st = s.shard.stats()
+        assert st["fallback_queries"] == 0, st
+        rescored += st["rescored"]
+    D = torch.empty((world * sl, k), dtype=torch.float32, device="cuda")
+    I = torch.empty((world * sl, k), dtype=torch.int64, device="cuda")
+    for r in range(world):
+        n_mine = max(0, min(sl, nq - r * sl))
+        check(lib().cldrd_merge_planes(0, C.c_void_p(xD[r].data_ptr()), C.c_void_p(xI[r].data_ptr()), world, sl, n_mine, k, k, None,
+                                       C.c_void_p(D[r * sl:].data_ptr()), C.c_void_p(I[r * sl:].data_ptr()), None))
+    fail = torch.ones((nq,), dtype=torch.int32, device="cuda")
+    check(lib().cldrd_verify_seed(0, C.c_void_p(D.data_ptr()), nq, k, C.c_void_p(seed.data_ptr()), C.c_void_p(eps2.data_ptr()),
+                                  C.c_void_p(fail.data_ptr()), None))
+    torch.cuda.synchronize()
+    ok = (fail == 0)
+    assert int(ok.sum()) >= nq - 2
+    assert torch.equal(D[:nq][ok], D1[ok]) and torch.equal(I[:nq][ok], I1[ok])
+    # without the cut every shard re-scores all it collected above the seed (~3.5k rows per query over the
+    # shards); with it, about k plus one level step plus the error band
+    assert rescored / nq < 1.6 * k + 400, (rescored / nq, k)
+    # finish without begin
+    rc = lib().cldrd_scatter_finish(shards[0].shard.handle, C.c_void_p(total.data_ptr()), C.c_void_p(levels.data_ptr()), world, 0, sl,
+                                    0, c_xD, c_xI, None)
+    assert rc != 0
+    for s in shards + [one]:
+        s.shard.close()
