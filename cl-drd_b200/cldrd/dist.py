@@ -3,12 +3,15 @@ reference's `index_cpu_to_gpu_multiple(..., shard=True)` (retriever/retrieval_ut
 
 rank r keeps passage rows shard_ranges(N, G)[r] resident in its HBM; queries are replicated.
 Per query batch: every rank scans a small sample of its rows, the sample scores are
-all-gathered (NCCL) and turned into one global filter seed per query; every rank then runs the
-fused scan + filter + fp32 re-score over its shard with that seed and emits [nq, k] (score,
-GLOBAL row); one NCCL gather over NVLink brings the lists to rank 0, where the merge kernel (same
-u64 key order as the single-GPU search, so results are bit-identical), the seed verification and
-the id_map gather finish the job.  torch.distributed is plumbing only; no collective touches
-the index.
+all-gathered (NCCL) and turned into 32 levels per query, the last of which is the global filter seed;
+every rank runs the fused scan + filter over its shard with that seed and counts its candidates above
+each level; an all-reduce of those counts tells every rank which candidates can still reach the global
+top-k, and only those are re-scored in fp32.  The re-score kernel stores each query's list straight
+into the HBM of the rank that merges that query (peer memory over NVLink, mapped with CUDA IPC); every
+rank merges and verifies its slice of the queries (same u64 key order as the single-GPU search, so
+results are bit-identical) and stores it into rank 0's result buffer, where the id_map gather finishes
+the job.  Without peer mapping an NCCL all-to-all and a gather move the lists.  torch.distributed is
+plumbing only; no collective touches the index.
 """
 from __future__ import annotations
 

@@ -131,7 +131,8 @@ int cldrd_search_dev(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
                      int32_t translate_ids, float* out_scores_dev, int64_t* out_ids_dev,
                      void* cuda_stream);
 
-/* Sharded search, three steps per query batch; each rank owns one shard:
+/* Sharded search; each rank owns one shard.  The NCCL-transport form, three steps per
+ * query batch (the peer-memory form follows below):
  *   1. cldrd_sample_dev: dense scan of a small strided sample of this shard's rows; writes each
  *      query's best CLDRD_SEED_J sample scan scores to out_topj_dev [nq][CLDRD_SEED_J].
  *   2. all-gather those to [parts][nq][CLDRD_SEED_J] (NCCL, by the caller) and call
