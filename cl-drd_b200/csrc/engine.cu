@@ -1122,6 +1122,7 @@ static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t
     s->scan_launches = 0;
     s->ev_rows.clear();
     s->ev_ms.clear();
+    s->pend.active = false;   // a plain search abandons a two-phase batch that was never finished
     if (seed_mode == 1 && (s->nrows < kSeedMinRows || s->no_seed)) seed_mode = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
         const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));

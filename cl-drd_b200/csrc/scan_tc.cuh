@@ -20,7 +20,11 @@
 //                 segments: one per group while groups are few, one per CTA otherwise.  A
 //                 segment is written by exactly one thread at a time; its cursor is carried in
 //                 a register across a unit and parked in seg_cnt between units (no atomics, no
-//                 shared counters), and the survivors spread evenly over the segments.
+//                 shared counters), and the survivors spread evenly over the segments.  The last
+//                 quarter of the slice is an overflow pool shared by all segments of the query
+//                 (atomic cursor, out-of-line filter_group_generic): a segment that fills up -
+//                 rows one query likes stored next to each other - spills there instead of
+//                 sending the query to the fallback.
 #pragma once
 #include "device_common.cuh"
 #include "scan_simt.cuh"  // ScanParams
