@@ -234,20 +234,13 @@ def main():
 
     # ---- end-to-end loop with host buffers: `e2e` ---------------------------------------------------
     q_np = q_host.numpy()
-    out_D = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    out_I = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-    q_stage = torch.empty_like(q_dev)
 
     def step_e2e():
         if world == 1:
             return searcher.local.search(q_np, k)          # numpy in -> numpy out (cldrd_search_host)
-        q_stage.copy_(q_host, non_blocking=True)            # H2D from pinned memory, every step
-        D, I = searcher.search(q_stage, k)
-        if rank == 0:
-            out_D.copy_(D, non_blocking=True)
-            out_I.copy_(I, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out_D, out_I
+        # every rank uploads its replica of the queries from pinned memory and writes its slice of the
+        # result into one shared page-locked block over its own PCIe link; rank 0 gets numpy views
+        return searcher.search_host(q_host, k)
 
     for _ in range(2):
         step_e2e()
@@ -332,7 +325,7 @@ def main():
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3 / args.steps,
                     "api": "GpuIndexFlat.search(numpy) -> cldrd_search_host" if world == 1 else
-                           "pinned host -> ShardedSearcher.search -> pinned host"},
+                           "pinned host -> ShardedSearcher.search_host -> shared page-locked host block (numpy views on rank 0)"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

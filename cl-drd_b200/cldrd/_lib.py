@@ -73,6 +73,8 @@ SIGNATURES = {
     "cldrd_shard_set_norm_bound": (C.c_int, [C.c_void_p, C.c_float]),
     "cldrd_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cldrd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "cldrd_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cldrd_host_unregister": (C.c_int, [C.c_void_p]),
     "cldrd_host_free": (None, [C.c_void_p]),
     "cldrd_merge_w": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_merge_planes": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

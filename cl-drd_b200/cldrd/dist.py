@@ -147,6 +147,67 @@ class _PeerExchange:
         self.ok = False
 
 
+class _SharedHostResult:
+    """[rows, k] float32 scores + int64 ids in ONE shared-memory mapping that every rank of the node has
+    page-locked (cldrd_host_register): each rank copies its merged slice device -> host over its own PCIe
+    link, rank 0 reads the whole result as numpy arrays without any further copy."""
+
+    def __init__(self, rank: int, rows: int, k: int, group):
+        import mmap
+        self.rank, self.group = rank, group
+        self.cap_elems = rows * k
+        self.nbytes = self.cap_elems * 12 + 64
+        name = [None]
+        if rank == 0:
+            name[0] = f"/dev/shm/cldrd_{os.getpid()}_{id(self) & 0xFFFFFF:x}"
+            fd = os.open(name[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        dist.broadcast_object_list(name, src=0, group=group)
+        if rank != 0:
+            fd = os.open(name[0], os.O_RDWR)
+        self.mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(name[0])            # the mappings keep it alive; nothing is left behind on a crash
+        self.base = C.addressof(C.c_char.from_buffer(self.mm))
+        ok = lib().cldrd_host_register(C.c_void_p(self.base), self.nbytes) == 0
+        if not ok:
+            self.base = 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(flag.item())
+        if not self.ok:
+            self.close()
+
+    def fits(self, rows: int, k: int) -> bool:
+        return rows * k <= self.cap_elems
+
+    def views(self, n: int, k: int, rows_alloc: int):
+        """numpy views: D [n,k] at byte 0, I [n,k] behind the score block of rows_alloc rows."""
+        import numpy as np
+        D = np.frombuffer(self.mm, dtype=np.float32, count=n * k, offset=0).reshape(n, k)
+        I = np.frombuffer(self.mm, dtype=np.int64, count=n * k, offset=self.ids_offset(rows_alloc, k)).reshape(n, k)
+        return D, I
+
+    @staticmethod
+    def ids_offset(rows_alloc: int, k: int) -> int:
+        return (rows_alloc * k * 4 + 63) // 64 * 64
+
+    def close(self):
+        if self.base:
+            lib().cldrd_host_unregister(C.c_void_p(self.base))
+            self.base = 0
+
+    def __del__(self):
+        # the page-lock must go before the mapping does: a later mapping at the same address could not be
+        # registered otherwise
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedSearcher:
     """rank-local shard + the gather/merge step.  Build with `from_rows` (device rows already in
     HBM, zero copy) or `from_file` (each rank preads only its own row range)."""
@@ -258,7 +319,7 @@ class ShardedSearcher:
             self._px_disabled = True   # agreed by all ranks (all-reduce MIN): nobody retries
         return self._px
 
-    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, levels, seed, mark, marks, prof):
+    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, levels, seed, mark, marks, prof, host=None):
         """Per batch of <= 8192 queries: scan + select with the seed and count the candidates above every
         sample level; all-reduce the counts (32 ints per query) so that every shard knows a threshold that k
         rows of the WHOLE index reach, and re-scores only what lies above it (about k / world rows per query);
@@ -296,10 +357,23 @@ class ShardedSearcher:
         nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
         fail_sl = torch.zeros((sl,), dtype=torch.int32, device=dev)
         if n_mine > 0:
-            outD = px.oD + lo * k * 4
-            outI = px.oI + lo * k * 8
+            if host is None:      # merged slice -> rank 0's device buffer (peer stores by the merge kernel)
+                outD = px.oD + lo * k * 4
+                outI = px.oI + lo * k * 8
+                idm = None
+            else:                 # merged slice (external ids applied) stays here, then goes to the shared host block
+                mD = torch.empty((n_mine, k), dtype=torch.float32, device=dev)
+                mI = torch.empty((n_mine, k), dtype=torch.int64, device=dev)
+                outD, outI = mD.data_ptr(), mI.data_ptr()
+                idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
             check(lib().cldrd_merge_planes(dev.index, C.c_void_p(px.xD[self.rank]), C.c_void_p(px.xI[self.rank]), world, sl,
-                                           n_mine, k, k, None, C.c_void_p(outD), C.c_void_p(outI), C.c_void_p(st)))
+                                           n_mine, k, k, idm, C.c_void_p(outD), C.c_void_p(outI), C.c_void_p(st)))
+            if host is not None:
+                rows_alloc = world * sl
+                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(host.base + lo * k * 4), C.c_void_p(outD), n_mine * k * 4,
+                                            C.c_void_p(st)))
+                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(host.base + host.ids_offset(rows_alloc, k) + lo * k * 8), C.c_void_p(outI),
+                                            n_mine * k * 8, C.c_void_p(st)))
             if seeded:
                 check(lib().cldrd_verify_seed(dev.index, C.c_void_p(outD), n_mine, k,
                                               C.c_void_p(seed[lo:lo + n_mine].contiguous().data_ptr()),
@@ -308,6 +382,8 @@ class ShardedSearcher:
                 nfail[0] = fail_sl[:n_mine].sum()
         mark("merge+verify")
         dist.all_reduce(nfail, op=dist.ReduceOp.SUM, group=self.group)   # also: every slice is in rank 0's buffer
+        if host is not None:
+            return self._finish_host(host, q, k, n, sl, seeded, nfail, fail_sl, mark, marks, prof)
         outD_t = outI_t = None
         if self.rank == 0:
             outD_t = torch.empty((n, k), dtype=torch.float32, device=dev)
@@ -337,6 +413,102 @@ class ShardedSearcher:
         if self.id_map is not None:
             outI_t = torch.where(outI_t >= 0, self.id_map[outI_t.clamp_min(0)], outI_t)
         return outD_t, outI_t
+
+    def _finish_host(self, host, q, k, n, sl, seeded, nfail, fail_sl, mark, marks, prof):
+        """Tail of the host-result search: every rank's slice is in the shared block once the miss-count
+        all-reduce (already issued, stream-ordered behind the copies) has completed."""
+        world, dev = self.world, q.device
+        misses = int(nfail.item()) if seeded else 0      # synchronises this rank's stream
+        if not seeded:
+            torch.cuda.current_stream(dev).synchronize()
+        D = I = None
+        if self.rank == 0:
+            D, I = host.views(n, k, world * sl)
+        mark("result")
+        if misses > 0:
+            fail_all = torch.empty((world, sl), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(fail_all, fail_sl, group=self.group)
+            idx = torch.nonzero(fail_all.view(-1)[:n]).flatten()
+            D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
+            D2, I2 = self._trim(D2, I2)
+            allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
+            if self.rank == 0:
+                pD, pI = merge_candidates(allD2, allI2, self.id_map, k)
+                rows = idx.cpu().numpy()
+                D[rows] = pD.cpu().numpy()
+                I[rows] = pI.cpu().numpy()
+        self.last_seed_misses = misses
+        mark("miss broadcast")
+        if prof:
+            torch.cuda.synchronize()
+            self.last_phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
+        return D, I
+
+    def _id_map_everywhere(self):
+        """The host-result path applies external ids inside every rank's merge: replicate rank 0's table once."""
+        if getattr(self, "_id_map_synced", False):
+            return
+        dev = torch.device("cuda", self.shard.device)
+        has = torch.tensor([1 if (self.rank == 0 and self.id_map is not None) else 0], dtype=torch.int32, device=dev)
+        dist.broadcast(has, src=0, group=self.group)
+        if int(has.item()):
+            if self.rank != 0:
+                self.id_map = torch.empty((self.ntotal,), dtype=torch.int64, device=dev)
+            dist.broadcast(self.id_map, src=0, group=self.group)
+        self._id_map_synced = True
+
+    def search_host(self, q_host, k: int):
+        """Host buffers in, host buffers out (the shape of the reference's `index.search(x, k)`).
+
+        q_host: the replicated float32 [nq, d] queries in host memory (numpy array or CPU tensor; page-locked
+        memory makes the upload asynchronous).  Returns numpy (D, I) on rank 0, (None, None) elsewhere.  On one
+        node the ranks write their slices of the result into one shared page-locked block, each over its own
+        PCIe link, and rank 0 returns views of that block: they are valid until the next search_host call."""
+        qh = torch.as_tensor(q_host)
+        assert qh.dtype == torch.float32 and qh.dim() == 2 and qh.shape[1] == self.d
+        n = qh.shape[0]
+        dev = torch.device("cuda", self.shard.device)
+        stage = getattr(self, "_q_stage", None)
+        if stage is None or stage.shape[0] < n:
+            stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
+        q = stage[:n]
+        q.copy_(qh, non_blocking=True)
+        if self.world == 1 or n == 0:
+            D, I = self.search(q, k)
+            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
+        self._sync_norm_bound()
+        px = self._peer_exchange(n, k)
+        if px is None:          # no peer mapping: device result on rank 0, one copy down
+            D, I = self.search(q, k)
+            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
+        self._id_map_everywhere()
+        sl = (n + self.world - 1) // self.world
+        host = getattr(self, "_host", None)
+        if not getattr(self, "_host_disabled", False) and (host is None or not host.fits(self.world * sl, k)):
+            if host is not None:
+                host.close()
+            host = self._host = _SharedHostResult(self.rank, self.world * sl, k, self.group)
+            if not host.ok:           # agreed by all ranks
+                host = self._host = None
+                self._host_disabled = True
+        if host is None:
+            D, I = self.search(q, k)
+            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
+        prof = os.environ.get("CLDRD_DIST_PROFILE") == "1"
+        marks = []
+
+        def mark(name):
+            if prof:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        seeded = self.ntotal >= self.SEED_MIN_ROWS
+        levels = self._levels(q, k) if seeded else None
+        seed = levels[:, _lib.SEED_J - 1].contiguous() if seeded else None
+        mark("sample+allgather+seed")
+        return self._search_p2p(px, q, k, levels, seed, mark, marks, prof, host=host)
 
     def search(self, q: torch.Tensor, k: int):
         """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""

@@ -1429,7 +1429,7 @@ int cldrd_peer_copy(int device, void* dst, const void* src, int64_t nbytes, void
     if (nbytes < 0 || (nbytes && (!dst || !src))) return fail(CLDRD_EINVAL, "peer_copy: bad argument");
     if (nbytes == 0) return CLDRD_OK;
     DeviceGuard g(device);
-    CU_TRY(cudaMemcpyAsync(dst, src, size_t(nbytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
+    CU_TRY(cudaMemcpyAsync(dst, src, size_t(nbytes), cudaMemcpyDefault, static_cast<cudaStream_t>(cuda_stream)));
     return CLDRD_OK;
 }
 
@@ -1573,6 +1573,26 @@ int cldrd_host_alloc(void** out, int64_t nbytes) {
 
 void cldrd_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int cldrd_host_register(void* p, int64_t nbytes) {
+    if (!p || nbytes < 1) return fail(CLDRD_EINVAL, "host_register: bad argument");
+    cudaError_t e = cudaHostRegister(p, size_t(nbytes), cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CLDRD_ECUDA, "cudaHostRegister(%lld) failed: %s", (long long)nbytes, cudaGetErrorString(e));
+    }
+    return CLDRD_OK;
+}
+
+int cldrd_host_unregister(void* p) {
+    if (!p) return CLDRD_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CLDRD_ECUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
+    return CLDRD_OK;
 }
 
 int cldrd_merge_planes(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts, int64_t plane_rows,

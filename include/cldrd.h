@@ -197,7 +197,8 @@ int cldrd_scatter_finish(cldrd_shard* s, const int32_t* counts_dev, const float*
  * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
  * cldrd.dist sends them through its process group); cldrd_peer_open maps a peer's handle into this process
  * (`device` = the opening process' GPU; needs peer access between the two GPUs);
- * cldrd_peer_copy is a stream-ordered device-to-device copy between any two such pointers. */
+ * cldrd_peer_copy is a stream-ordered copy between any two pointers CUDA knows (own or mapped device
+ * memory, page-locked host memory). */
 #define CLDRD_PEER_HANDLE_BYTES 72
 int cldrd_peer_alloc(int device, int64_t nbytes, void** out_ptr, void* out_handle);
 int cldrd_peer_free(int device, void* ptr);
@@ -220,6 +221,10 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
  * an internal pinned staging buffer plus one memcpy. */
 int  cldrd_host_alloc(void** out, int64_t nbytes);
 void cldrd_host_free(void* p);
+/* Page-lock memory the caller already owns (e.g. a shared-memory mapping that several ranks of one
+ * node write their slice of the results into, each over its own PCIe link). */
+int  cldrd_host_register(void* p, int64_t nbytes);
+int  cldrd_host_unregister(void* p);
 
 /* Merge per-shard candidate lists (replaces faiss IndexShards' CPU merge_knn_results behind
  * retriever/retrieval_utils.py:176-182).  Inputs are [parts][nq][k] device arrays of scores and

@@ -51,13 +51,17 @@ def main():
                 res[f"p2p_used_{name}"] = getattr(s, "_px", None) is not None
                 res[f"seed_misses_{name}"] = getattr(s, "last_seed_misses", None)
         os.environ["CLDRD_DIST_P2P"] = "1"
+        Dh, Ih = s.search_host(xq, k)          # host in, host out: slices land in one shared page-locked block
+        res[f"host_shared_{name}"] = getattr(s, "_host", None) is not None
         if rank == 0:
+            Dh, Ih = Dh.copy(), Ih.copy()
             full = torch.from_numpy(xb).to(dev)
             one = CD.ShardedSearcher.from_rows(full, 0, n, scan="f16", id_map=id_map)
             one.world, one.rank = 1, 0
             D1, I1 = one.search(q, k)
             for transport, (D, I) in out.items():
                 res[f"bit_equal_{name}_{transport}"] = bool(torch.equal(D, D1) and torch.equal(I, I1))
+            res[f"bit_equal_{name}_host"] = bool(np.array_equal(Dh, D1.cpu().numpy()) and np.array_equal(Ih, I1.cpu().numpy()))
             if name == "big":
                 D, I = out["p2p"]
                 D_ref, I_ref = O.search(xb, ids, xq, k)

@@ -471,6 +471,7 @@ def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
     for name in ("small", "big", "manyq", "miss"):
         assert res[f"bit_equal_{name}_p2p"] and res[f"bit_equal_{name}_nccl"], res
         assert res[f"p2p_used_{name}"], res          # the peer-memory exchange is the path that ran
+        assert res[f"bit_equal_{name}_host"] and res[f"host_shared_{name}"], res
     assert res["oracle_ok"], res
     assert res["seed_misses_miss"] == 33 and res["seed_misses_big"] == 0, res
 
