@@ -152,33 +152,66 @@ class _SharedHostResult:
     page-locked (cldrd_host_register): each rank copies its merged slice device -> host over its own PCIe
     link, rank 0 reads the whole result as numpy arrays without any further copy."""
 
-    def __init__(self, rank: int, rows: int, k: int, group):
+    _serial = 0
+
+    def __init__(self, rank: int, rows: int, k: int, group, register: bool = True):
         import mmap
         self.rank, self.group = rank, group
         self.cap_elems = rows * k
         self.nbytes = self.cap_elems * 12 + 64
-        name = [None]
+        self.mm, self.base, self.ok = None, 0, False
+        # every step below ends in a collective that all ranks reach whatever failed locally
+        name, fd = [None], -1
         if rank == 0:
-            name[0] = f"/dev/shm/cldrd_{os.getpid()}_{id(self) & 0xFFFFFF:x}"
-            fd = os.open(name[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-            os.ftruncate(fd, self.nbytes)
+            try:
+                _SharedHostResult._serial += 1
+                path = f"/dev/shm/cldrd_{os.getpid()}_{_SharedHostResult._serial}"
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                name[0] = path
+                os.ftruncate(fd, self.nbytes)
+            except OSError:
+                if fd >= 0:
+                    os.close(fd)
+                    fd = -1
+                if name[0] is not None:
+                    try:
+                        os.unlink(name[0])
+                    except OSError:
+                        pass
+                name[0] = None
         dist.broadcast_object_list(name, src=0, group=group)
-        if rank != 0:
-            fd = os.open(name[0], os.O_RDWR)
-        self.mm = mmap.mmap(fd, self.nbytes)
-        os.close(fd)
-        dist.barrier(group=group)
-        if rank == 0:
-            os.unlink(name[0])            # the mappings keep it alive; nothing is left behind on a crash
-        self.base = C.addressof(C.c_char.from_buffer(self.mm))
-        ok = lib().cldrd_host_register(C.c_void_p(self.base), self.nbytes) == 0
-        if not ok:
-            self.base = 0
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        self.ok = bool(flag.item())
-        if not self.ok:
+        good = name[0] is not None
+        if good:
+            try:
+                if rank != 0:
+                    fd = os.open(name[0], os.O_RDWR)
+                self.mm = mmap.mmap(fd, self.nbytes)
+            except (OSError, ValueError):
+                good = False
+        if fd >= 0:
+            os.close(fd)
+        good = self._all_ok(good)         # also the barrier: everybody has mapped it (or given up)
+        if rank == 0 and name[0] is not None:
+            try:
+                os.unlink(name[0])        # the mappings keep it alive; nothing is left behind on a crash
+            except OSError:
+                pass
+        if good and register:
+            self.base = C.addressof(C.c_char.from_buffer(self.mm))
+            reg = lib().cldrd_host_register(C.c_void_p(self.base), self.nbytes) == 0
+            if not reg:
+                self.base = 0
+            good = self._all_ok(reg)
+        self.ok = good
+        if not good:
             self.close()
+
+    def _all_ok(self, mine: bool) -> bool:
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        flag = torch.tensor([1 if mine else 0], dtype=torch.int32,
+                            device=torch.device("cuda", torch.cuda.current_device()) if on_gpu else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
 
     def fits(self, rows: int, k: int) -> bool:
         return rows * k <= self.cap_elems

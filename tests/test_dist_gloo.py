@@ -50,6 +50,48 @@ def test_gather_candidates_gloo_world2(tmp_path):
     assert torch.load(out)["ok"]
 
 
+def _shared_block_worker(rank, world, port, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "cl-drd_b200")]
+    from cldrd import dist as CD
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = {}
+    before = set(os.listdir("/dev/shm"))
+    # (1) the mapping is really shared: every rank writes its slice, rank 0 reads all of them
+    n, k, sl = 7, 5, 4                                            # 7 queries, slices of 4 rows, 2 ranks
+    blk = CD._SharedHostResult(rank, world * sl, k, None, register=False)
+    res["mapped"] = blk.ok
+    D, I = blk.views(world * sl, k, world * sl)
+    lo = rank * sl
+    D[lo:lo + sl] = float(rank + 1)
+    I[lo:lo + sl] = 100 * (rank + 1) + np.arange(k)
+    dist.barrier()
+    if rank == 0:
+        res["shared"] = bool((D[:sl] == 1).all() and (D[sl:] == 2).all() and (I[sl:, 0] == 200).all())
+        res["ids_aligned"] = CD._SharedHostResult.ids_offset(world * sl, k) % 8 == 0 and I.ctypes.data % 8 == 0
+    dist.barrier()
+    # (2) without CUDA the page-lock is refused: all ranks must agree on ok == False, nobody hangs
+    blk2 = CD._SharedHostResult(rank, world * sl, k, None, register=True)
+    res["register_refused_everywhere"] = (not blk2.ok) and blk2.base == 0
+    res["no_files_left"] = set(os.listdir("/dev/shm")) <= before
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_host_result_block_gloo_world2(tmp_path):
+    """cldrd.dist._SharedHostResult (the block ShardedSearcher.search_host writes its slices into): shared
+    between the ranks, unlinked at once, and a refused cudaHostRegister (no GPU here) is agreed on collectively."""
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("the refusal path needs a box without CUDA")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_shared_block_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert all(res.values()), res
+
+
 def test_shard_ranges_cover_rows_exactly():
     sys.path[:0] = [os.path.join(ROOT, "cl-drd_b200")]
     from cldrd.index import shard_ranges
