@@ -3,12 +3,15 @@
 
 metric   : queries/s for top-1000 over a synthetic 8 841 823 x 768 fp32 index (configs[1],
            MS MARCO-dev shape, 6 980 queries), at --gpus N B200s of one box.
-step     : one search of all 6 980 queries over the whole index (every rank scans its row shard,
-           NCCL gather of the per-shard top-k lists to rank 0, merge kernel, id translation).
+step     : one search of all 6 980 queries over the whole index.  N>1: every rank scans its row shard
+           (seed and re-score cut agreed through an NCCL all-gather of sample scores and an all-reduce
+           of 32 counts per query), the re-score kernel stores the lists into the merging rank's HBM
+           over NVLink, slice-wise merge kernels, result on rank 0.
 value    : device-resident throughput (queries already in HBM), CUDA events, max over ranks.
 e2e      : the same through the reference-facing call with HOST buffers: `index.search(x, k)`
-           with numpy in / numpy out at N=1 (cldrd_search_host), pinned-host -> device ->
-           gather/merge -> pinned-host at N>1; copies inside the timed region.
+           with numpy in / numpy out at N=1 (cldrd_search_host); at N>1 ShardedSearcher.search_host:
+           every rank uploads the queries from pinned memory and copies its merged slice into one
+           shared page-locked host block, rank 0 reads numpy views; copies inside the timed region.
 roofline : scan kernel (tcgen05 tiles + fused filter): algorithmic FLOPs 2*Q*N_shard*d per pass
            divided by the summed device time of the scan launches (CUDA events on the launching
            stream, recorded inside libcldrd), against MEASURED_PEAKS.json's sustained bf16 peak.

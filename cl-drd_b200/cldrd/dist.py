@@ -242,8 +242,9 @@ class _SharedHostResult:
 
 
 class ShardedSearcher:
-    """rank-local shard + the gather/merge step.  Build with `from_rows` (device rows already in
-    HBM, zero copy) or `from_file` (each rank preads only its own row range)."""
+    """rank-local shard + this rank's part of the sharded protocol.  Build with `from_rows` (device rows
+    already in HBM, zero copy) or `from_file` (each rank preads only its own row range); `search` takes and
+    returns CUDA tensors, `search_host` host arrays."""
 
     def __init__(self, shard: _Shard, ntotal: int, d: int, id_map: Optional[torch.Tensor], group=None):
         self.shard = shard
