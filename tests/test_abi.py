@@ -64,3 +64,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.lower() or "oracle" in f, f"{f} mentions the oracle"
+
+
+def test_sharded_entry_points_validate_arguments(cldrd_lib):
+    """The peer-memory / two-phase entry points reject bad arguments with a code and a message, GPU or not."""
+    from cldrd import _lib
+    p = C.c_void_p()
+    handle = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+    assert cldrd_lib.cldrd_peer_alloc(0, 0, C.byref(p), handle) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_peer_open(0, None, C.byref(p)) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_peer_close(0, C.c_void_p(0x1000)) == _lib.E_INVAL          # not a pointer we handed out
+    assert b"cldrd_peer_open" in cldrd_lib.cldrd_last_error()
+    assert cldrd_lib.cldrd_peer_close(0, None) == 0 and cldrd_lib.cldrd_peer_free(0, None) == 0
+    assert cldrd_lib.cldrd_peer_copy(0, None, None, 16, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_host_register(None, 0) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_host_unregister(None) == 0
+    assert cldrd_lib.cldrd_scatter_begin(None, None, 1, 10, None, None, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_scatter_finish(None, None, None, 2, 0, 4, 0, None, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_search_dev_scatter(None, None, 1, 10, None, 2, 0, 4, None, None, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_levels_from_samples(0, None, 2, 4, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_merge_planes(0, None, None, 2, 4, 5, 10, 10, None, None, None, None) == _lib.E_INVAL   # nq > plane_rows
+    assert _lib.MAX_PEERS == 16 and _lib.QUERY_BATCH == 8192 and _lib.PEER_HANDLE_BYTES == 72
+
+
+def test_header_constants_match_python_side():
+    import re
+    from cldrd import _lib
+    text = open(os.path.join(ROOT, "include", "cldrd.h")).read()
+    consts = dict(re.findall(r"#define\s+(CLDRD_[A-Z_0-9]+)\s+(-?\d+)", text))
+    assert int(consts["CLDRD_MAX_K"]) == _lib.MAX_K
+    assert int(consts["CLDRD_SEED_J"]) == _lib.SEED_J
+    assert int(consts["CLDRD_MAX_PEERS"]) == _lib.MAX_PEERS
+    assert int(consts["CLDRD_QUERY_BATCH"]) == _lib.QUERY_BATCH
+    assert int(consts["CLDRD_PEER_HANDLE_BYTES"]) == _lib.PEER_HANDLE_BYTES
