@@ -164,6 +164,9 @@ class _SharedHostResult:
         name, fd = [None], -1
         if rank == 0:
             try:
+                vfs = os.statvfs("/dev/shm")
+                if vfs.f_bavail * vfs.f_frsize < self.nbytes + (16 << 20):
+                    raise OSError("not enough room in /dev/shm")   # pinning would hit SIGBUS, not an error code
                 _SharedHostResult._serial += 1
                 path = f"/dev/shm/cldrd_{os.getpid()}_{_SharedHostResult._serial}"
                 fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
