@@ -1,6 +1,10 @@
 """Query search entry point: same flags, prints and run file as the reference's
 retriever/retrieve_top_passages.py (:28-109).  The search runs on the B200 kernels; the regroup and
-writer loops are one native call."""
+writer loops are one native call.
+
+Launched under torchrun (`torchrun --nproc-per-node G retrieve_top_passages.py ...`) it is the one-process-per-GPU
+form: every rank loads only its row shard of the index file, encodes the queries, and takes part in the sharded
+search (cldrd.dist.ShardedSearcher.search_host); rank 0 writes the run file."""
 import argparse
 import os
 import sys
@@ -44,6 +48,15 @@ def check_paths(queries_path, output_path):
 def main(args, is_query_side=True, header="# unique query"):
     from transformers import AutoTokenizer
     check_paths(args.queries_path, args.output_path)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        own_group = not dist.is_initialized()
+        if own_group:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     model = DualEncoder(args.model_name_or_path, share_weights=args.share_weights)
     print("************************* share weights = {} *************************".format(args.share_weights))
     if args.resume:
@@ -56,6 +69,21 @@ def main(args, is_query_side=True, header="# unique query"):
     query_embs, query_ids = get_embeddings_from_scratch(model, loader, use_fp16=True, is_query=is_query_side,
                                                         show_progress_bar=True)
     os.environ.setdefault("CLDRD_SCAN", args.precision)
+    if world > 1:
+        import numpy as np
+        import torch.distributed as dist
+        from cldrd.dist import ShardedSearcher
+        searcher = ShardedSearcher.from_file(args.index_path, device=torch.cuda.current_device(), scan=args.precision)
+        nn_scores, nn_doc_ids = searcher.search_host(np.ascontiguousarray(query_embs, dtype=np.float32), args.top_k)
+        if rank == 0:
+            print(f"{header} = {len(set(query_ids))}")
+            avg = cldrd.write_run_file(args.output_path, query_ids, nn_doc_ids, nn_scores)
+            print(f"average ranks per query = {avg}")
+        dist.barrier()
+        searcher.shard.close()
+        if own_group:
+            dist.destroy_process_group()
+        return
     index = cldrd.read_index(args.index_path)                      # headers only; rows stream file -> HBM
     devs = [int(x) for x in str(args.gpus).split(",")]
     index = convert_index_to_gpu(index, devs if len(devs) > 1 else devs[0], False)

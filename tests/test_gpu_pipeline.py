@@ -92,3 +92,41 @@ def test_index_text_then_retrieve_top_passages(cldrd_lib, tmp_path):
     s2 = np.array([float(ln[3]) for ln in l2]).reshape(300, 5)
     assert (np.diff(s2, axis=1) <= 0).all()
     assert set(int(ln[1]) for ln in l2) <= set(pids.tolist())
+
+
+def test_retrieve_top_passages_under_torchrun_equals_single_process(cldrd_lib, tmp_path):
+    """The CLI in its one-process-per-GPU form (needs 2 GPUs): same run file, byte for byte, as the single-process run."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "cl-drd_b200"))
+    from retriever import index_text, retrieve_top_passages
+    model_dir = _tiny_model_dir(tmp_path)
+    rng = np.random.default_rng(5)
+    coll, quer = tmp_path / "collection.tsv", tmp_path / "queries.dev.tsv"
+    pids = rng.permutation(5000)[:400] + 7_000_000
+    with open(coll, "w") as f:
+        for pid in pids:
+            f.write(f"{pid}\t{' '.join(rng.choice(WORDS, size=rng.integers(5, 30)))}\n")
+    qids = rng.permutation(1000)[:31] + 1_048_000
+    with open(quer, "w") as f:
+        for qid in qids:
+            f.write(f"{qid}\t{' '.join(rng.choice(WORDS, size=rng.integers(2, 8)))}\n")
+    index_dir = str(tmp_path / "index") + "/"
+    a = index_text.get_args(["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir, "--passages_path", str(coll),
+                             "--index_dir", index_dir, "--index_name", "checkpoint_1", "--share_weights", "--batch_size", "64"])
+    index_path = index_text.main(a)
+    common = ["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir, "--queries_path", str(quer),
+              "--index_path", index_path, "--top_k", "20", "--share_weights"]
+    run1 = tmp_path / "runs" / "dev.one.run"
+    retrieve_top_passages.main(retrieve_top_passages.get_args(common + ["--output_path", str(run1)]))
+    run2 = tmp_path / "runs" / "dev.two.run"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(root, "cl-drd_b200", "retriever", "retrieve_top_passages.py")] + common + \
+          ["--output_path", str(run2)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
+    assert run2.read_bytes() == run1.read_bytes()
+
