@@ -86,6 +86,7 @@ SIGNATURES = {
     "cldrd_shard_last_scan_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _c_i64p, C.c_int32]),
     "cldrd_scan_dense_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "cldrd_write_run": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _c_i64p]),
+    "cldrd_write_run_mt": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _c_i64p]),
     "cldrd_format_score": (C.c_int, [C.c_float, C.c_char_p]),
 }
 

@@ -18,12 +18,13 @@ def format_score(s: float) -> str:
     return buf.raw[:n].decode()
 
 
-def write_run_file(path, query_ids, nn_ids, nn_scores, append: bool = False) -> float:
+def write_run_file(path, query_ids, nn_ids, nn_scores, append: bool = False, threads: int = 0) -> float:
     """query_ids [n], nn_ids [n,k] int64, nn_scores [n,k] float32 -> "qid\\tdocid\\trank\\tscore\\n".
 
     Mirrors the reference: creates the parent directory if missing (:99-100); a query id that
     occurs more than once keeps its first position and its later hits continue the same rank
     sequence (the dict regroup of :90-96).  Returns the average ranks per query it prints (:109).
+    threads: formatting threads (0 = CLDRD_WRITER_THREADS or every host core); the bytes do not depend on it.
     """
     qids = np.ascontiguousarray(np.asarray(query_ids, dtype=np.int64))
     I = np.ascontiguousarray(np.asarray(nn_ids, dtype=np.int64))
@@ -40,6 +41,6 @@ def write_run_file(path, query_ids, nn_ids, nn_scores, append: bool = False) -> 
         order = np.argsort(np.array([first_of[q] for q in qids.tolist()], dtype=np.int64), kind="stable")
         qids, I, D = qids[order], np.ascontiguousarray(I[order]), np.ascontiguousarray(D[order])
     lines = C.c_int64()
-    check(lib().cldrd_write_run(str(path).encode(), ptr(qids), ptr(D), ptr(I), n, k, 1 if append else 0,
-                                C.byref(lines)))
+    check(lib().cldrd_write_run_mt(str(path).encode(), ptr(qids), ptr(D), ptr(I), n, k, 1 if append else 0,
+                                   int(threads), C.byref(lines)))
     return lines.value / max(uniq.shape[0], 1)

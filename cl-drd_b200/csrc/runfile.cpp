@@ -13,6 +13,11 @@
 #include <fcntl.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common_host.h"
@@ -124,62 +129,122 @@ int cldrd_format_score(float s, char* buf) {
     return py_repr_double(double(s), buf);
 }
 
-int cldrd_write_run(const char* path, const int64_t* qids, const float* scores, const int64_t* ids,
-                    int64_t nq, int32_t k, int32_t append, int64_t* lines_written) {
+// One formatted line per hit.  `rank` is the 1-based rank of the first hit of this row.
+static inline char* format_row(char* p, int64_t qid, const float* s, const int64_t* d, int32_t k, int64_t rank) {
+    char qbuf[24];
+    const int qlen = int(put_i64(qbuf, qid) - qbuf);
+    for (int32_t j = 0; j < k; ++j) {
+        memcpy(p, qbuf, qlen);
+        p += qlen;
+        *p++ = '\t';
+        p = put_i64(p, d[j]);
+        *p++ = '\t';
+        p = put_i64(p, rank + j);
+        *p++ = '\t';
+        p += py_repr_double(double(s[j]), p);
+        *p++ = '\n';
+    }
+    return p;
+}
+
+// longest line: 20 (qid) + 20 (docid) + 20 (rank) + 24 (score) + 4 separators
+static constexpr size_t kMaxLine = 96;
+
+static int pwrite_all(int fd, const char* q, size_t n, off_t off, const char* path) {
+    while (n) {
+        ssize_t w = pwrite(fd, q, n, off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return cldrd::fail(CLDRD_EIO, "write to '%s' failed: %s", path, strerror(errno));
+        }
+        q += w;
+        off += w;
+        n -= size_t(w);
+    }
+    return CLDRD_OK;
+}
+
+int cldrd_write_run_mt(const char* path, const int64_t* qids, const float* scores, const int64_t* ids,
+                       int64_t nq, int32_t k, int32_t append, int32_t threads, int64_t* lines_written) {
     if (!path || nq < 0 || k < 0 || (nq && k && (!qids || !scores || !ids)))
         return cldrd::fail(CLDRD_EINVAL, "write_run: bad argument");
-    int fd = open(path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    // explicit offsets instead of O_APPEND: the formatting threads pwrite their pieces in place
+    int fd = open(path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
     if (fd < 0) return cldrd::fail(CLDRD_EIO, "cannot open run file '%s': %s", path, strerror(errno));
-    const size_t kBuf = size_t(8) << 20;
-    std::vector<char> buf(kBuf + 256);
-    char* p = buf.data();
-    int64_t lines = 0;
-    int64_t rank = 0;
-    int rc = CLDRD_OK;
-    auto flush = [&]() {
-        const char* q = buf.data();
-        size_t n = size_t(p - buf.data());
-        while (n) {
-            ssize_t w = write(fd, q, n);
-            if (w < 0) {
-                if (errno == EINTR) continue;
-                rc = cldrd::fail(CLDRD_EIO, "write to '%s' failed: %s", path, strerror(errno));
-                return;
-            }
-            q += w;
-            n -= size_t(w);
-        }
-        p = buf.data();
-    };
-    for (int64_t i = 0; i < nq && !rc; ++i) {
-        // the reference's dict regroup: a qid seen again continues its rank sequence; callers
-        // pass rows grouped so that equal qids are consecutive.
-        if (i == 0 || qids[i] != qids[i - 1]) rank = 0;
-        char qbuf[24];
-        int qlen = int(put_i64(qbuf, qids[i]) - qbuf);
-        const float* s = scores + i * int64_t(k);
-        const int64_t* d = ids + i * int64_t(k);
-        for (int32_t j = 0; j < k; ++j) {
-            memcpy(p, qbuf, qlen);
-            p += qlen;
-            *p++ = '\t';
-            p = put_i64(p, d[j]);
-            *p++ = '\t';
-            p = put_i64(p, ++rank);
-            *p++ = '\t';
-            p += py_repr_double(double(s[j]), p);
-            *p++ = '\n';
-            ++lines;
-            if (size_t(p - buf.data()) >= kBuf) {
-                flush();
-                if (rc) break;
-            }
+    off_t base = 0;
+    if (append) {
+        base = lseek(fd, 0, SEEK_END);
+        if (base < 0) {
+            int rc = cldrd::fail(CLDRD_EIO, "cannot seek '%s': %s", path, strerror(errno));
+            close(fd);
+            return rc;
         }
     }
-    if (!rc) flush();
+    // the reference's dict regroup: a qid seen again continues its rank sequence; callers pass rows
+    // grouped so that equal qids are consecutive.  first_rank[i] = rank of row i's first hit.
+    std::vector<int64_t> first_rank(size_t(nq), 1);
+    for (int64_t i = 1; i < nq; ++i)
+        if (qids[i] == qids[i - 1]) first_rank[size_t(i)] = first_rank[size_t(i - 1)] + k;
+    int T = threads;
+    if (T <= 0) {
+        if (const char* e = getenv("CLDRD_WRITER_THREADS")) T = atoi(e);
+        if (T <= 0) T = int(std::thread::hardware_concurrency());
+    }
+    // Pieces of ~2 MiB of text are handed out in file order.  A worker formats its piece into its own buffer,
+    // learns the piece's file offset from its predecessor (start[i+1] = start[i] + length, published as soon as the
+    // length is known, before the write), and writes it in place with pwrite: formatting and writing of different
+    // pieces overlap, the bytes land exactly where the single-threaded loop would have put them.
+    const int64_t piece = std::max<int64_t>(1, (int64_t(2) << 20) / std::max<int64_t>(1, int64_t(k) * 48));
+    const int64_t npieces = (nq + piece - 1) / piece;
+    T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(T, 256), npieces)));
+    std::vector<std::atomic<int64_t>> start(size_t(npieces) + 1);
+    for (auto& x : start) x.store(-1, std::memory_order_relaxed);
+    start[0].store(int64_t(base), std::memory_order_release);
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    std::vector<int> rcs(size_t(T), CLDRD_OK);
+    std::vector<std::string> errs{size_t(T)};
+    auto worker = [&](int t) {
+        std::vector<char> buf(size_t(piece) * size_t(std::max(k, 1)) * kMaxLine + 64);
+        for (;;) {
+            const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= npieces) break;
+            const int64_t lo = i * piece, hi = std::min<int64_t>(nq, lo + piece);
+            char* p = buf.data();
+            if (!failed.load(std::memory_order_relaxed))
+                for (int64_t r = lo; r < hi; ++r)
+                    p = format_row(p, qids[r], scores + r * int64_t(k), ids + r * int64_t(k), k, first_rank[size_t(r)]);
+            const int64_t len = int64_t(p - buf.data());
+            int64_t at;
+            while ((at = start[size_t(i)].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+            start[size_t(i) + 1].store(at + len, std::memory_order_release);
+            if (len && !failed.load(std::memory_order_relaxed)) {
+                const int wrc = pwrite_all(fd, buf.data(), size_t(len), off_t(at), path);
+                if (wrc) {
+                    rcs[size_t(t)] = wrc;
+                    errs[size_t(t)] = cldrd_last_error();   // the message is thread-local
+                    failed.store(1, std::memory_order_relaxed);
+                }
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+    }
+    int rc = CLDRD_OK;
+    for (int t = 0; t < T && !rc; ++t)
+        if (rcs[size_t(t)]) rc = cldrd::fail(rcs[size_t(t)], "%s", errs[size_t(t)].c_str());
     if (close(fd) != 0 && !rc) rc = cldrd::fail(CLDRD_EIO, "close '%s' failed: %s", path, strerror(errno));
-    if (lines_written) *lines_written = lines;
+    if (lines_written) *lines_written = rc ? 0 : nq * int64_t(k);
     return rc;
+}
+
+int cldrd_write_run(const char* path, const int64_t* qids, const float* scores, const int64_t* ids,
+                    int64_t nq, int32_t k, int32_t append, int64_t* lines_written) {
+    return cldrd_write_run_mt(path, qids, scores, ids, nq, k, append, 0, lines_written);
 }
 
 }  // extern "C"

@@ -120,6 +120,34 @@ def test_run_writer_bytes_equal_reference_loop(cldrd_lib, tmp_path):
     assert a.read_bytes() == gold
 
 
+def test_run_writer_threads_do_not_change_the_bytes(cldrd_lib, tmp_path):
+    """Many ~2 MiB pieces formatted by 1, 3 and 8 threads, written with pwrite at prefix-summed offsets:
+    identical files; equal qids that straddle a piece boundary keep one rank sequence; append continues
+    behind the existing bytes (retrieve_top_passages.py:90-109 is the loop all of this replaces)."""
+    import cldrd
+    rng = np.random.default_rng(5)
+    n, k = 3000, 200                     # ~27 MB of text: a dozen pieces
+    D = (rng.standard_normal((n, k)) * 30 + 80).astype(np.float32)
+    I = rng.integers(0, 8_841_823, (n, k), dtype=np.int64)
+    qids = np.repeat(rng.permutation(10 ** 7)[: n // 3].astype(np.int64), 3)[:n]    # runs of three equal qids
+    files = []
+    for t in (1, 3, 8):
+        f = tmp_path / f"t{t}.tsv"
+        avg = cldrd.write_run_file(str(f), qids, I, D, threads=t)
+        assert avg == 3 * k
+        files.append(f.read_bytes())
+    assert files[0] == files[1] == files[2]
+    ref = tmp_path / "ref.tsv"
+    O.write_run(str(ref), qids[:300].tolist(), I[:300], D[:300])
+    assert files[0].startswith(ref.read_bytes())
+    assert files[0].count(b"\n") == n * k
+    # append in two halves == one call (the halves are cut between two qid runs)
+    f2 = tmp_path / "halves.tsv"
+    cldrd.write_run_file(str(f2), qids[:1500], I[:1500], D[:1500], threads=4)
+    cldrd.write_run_file(str(f2), qids[1500:], I[1500:], D[1500:], append=True, threads=4)
+    assert f2.read_bytes() == files[0]
+
+
 def test_score_text_matches_python_repr(cldrd_lib):
     import cldrd
     rng = np.random.default_rng(1)
