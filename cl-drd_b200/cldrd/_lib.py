@@ -58,12 +58,18 @@ SIGNATURES = {
     "cldrd_seed_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "cldrd_search_dev_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_verify_seed": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cldrd_search_dev_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
-                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
-    "cldrd_levels_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
-    "cldrd_scatter_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cldrd_scatter_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
-                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "cldrd_node_block_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "cldrd_node_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32]),
+    "cldrd_node_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cldrd_node_block": (C.c_void_p, [C.c_void_p]),
+    "cldrd_node_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "cldrd_node_detach": (C.c_int, [C.c_void_p]),
+    "cldrd_node_destroy": (None, [C.c_void_p]),
+    "cldrd_node_result_ptrs": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cldrd_node_search_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_node_search_end": (C.c_int, [C.c_void_p, C.c_void_p, _c_i32p, _c_i32p, C.c_int32]),
+    "cldrd_node_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cldrd_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "cldrd_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cldrd_peer_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -75,6 +81,7 @@ SIGNATURES = {
     "cldrd_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "cldrd_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
     "cldrd_host_unregister": (C.c_int, [C.c_void_p]),
+    "cldrd_host_device_ptr": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cldrd_host_free": (None, [C.c_void_p]),
     "cldrd_merge_w": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_merge_planes": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

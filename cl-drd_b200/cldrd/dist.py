@@ -2,15 +2,14 @@
 reference's `index_cpu_to_gpu_multiple(..., shard=True)` (retriever/retrieval_utils.py:174-182).
 
 rank r keeps passage rows shard_ranges(N, G)[r] resident in its HBM; queries are replicated.
-Per query batch: every rank scans a small sample of its rows, the sample scores are
-all-gathered (NCCL) and turned into 32 levels per query, the last of which is the global filter seed;
-every rank runs the fused scan + filter over its shard with that seed and counts its candidates above
-each level; an all-reduce of those counts tells every rank which candidates can still reach the global
-top-k, and only those are re-scored in fp32.  The re-score kernel stores each query's list straight
-into the HBM of the rank that merges that query (peer memory over NVLink, mapped with CUDA IPC); every
-rank merges and verifies its slice of the queries (same u64 key order as the single-GPU search, so
-results are bit-identical) and stores it into rank 0's result buffer, where the id_map gather finishes
-the job.  Without peer mapping an NCCL all-to-all and a gather move the lists.  torch.distributed is
+Per query batch (include/cldrd.h "Sharded search on one node") every rank makes ONE asynchronous
+call: sample scan -> sample scores stored into every rank's block -> flag barrier -> levels and the global filter
+seed -> fused scan + filter -> candidates counted against the levels, counts stored into every rank's block ->
+barrier -> only what can still reach the global top-k is re-scored in fp32 and stored straight into the HBM of
+the rank that merges the query (peer memory over NVLink, mapped with CUDA IPC) -> barrier -> every rank merges
+and verifies its slice (same u64 key order as the single-GPU search: bit-identical results) and stores it where
+the result is wanted: rank 0's HBM or a shared page-locked host block.  No NCCL call and no host synchronisation
+inside a batch.  Without peer mapping NCCL moves the lists (all-gather, all-to-all, gather).  torch.distributed is
 plumbing only; no collective touches the index.
 """
 from __future__ import annotations
@@ -23,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import CldrdError, check, lib
 from .index import GpuIndexFlat, _Shard, shard_ranges
 
 
@@ -63,87 +62,79 @@ def merge_candidates(allD: torch.Tensor, allI: torch.Tensor, id_map: Optional[to
     return outD, outI
 
 
-class _PeerExchange:
-    """Exchange buffers of one node's ranks, mapped into every rank (CUDA IPC over NVLink / NVSwitch).
+def _coll_dev(group) -> torch.device:
+    """Where tensors of the (setup-time) collectives live: the GPU under NCCL, host memory under gloo (the
+    CPU tests, and two ranks sharing one GPU, which NCCL refuses)."""
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
 
-    Every rank owns  xD float32 [world][slice][k]  and  xI int64 [world][slice][k]  (plane p is written
-    by rank p's re-score kernel: `cldrd_search_dev_scatter`); rank 0 also owns the result buffers
-    oD / oI [world*slice][k] that every rank's merge kernel writes its slice into.  Sized for
-    `cap_elems` = world*slice*k entries; rebuilt (collectively) when a search needs more."""
 
-    def __init__(self, device: int, rank: int, world: int, cap_elems: int, group):
+def _all_ok(mine: bool, group) -> bool:
+    flag = torch.tensor([1 if mine else 0], dtype=torch.int32, device=_coll_dev(group))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
+class _NodeExchange:
+    """This rank's cldrd_node: its exchange block plus the blocks of the node's other ranks mapped into this
+    process (CUDA IPC handles travel through the process group once, at construction).  Everything a search
+    exchanges afterwards is stored by kernels into these blocks (include/cldrd.h, "Sharded search on one node")."""
+
+    def __init__(self, device: int, rank: int, world: int, max_k: int, group):
         self.device, self.rank, self.world, self.group = device, rank, world, group
-        self.cap_elems = cap_elems
-        self.own = []          # pointers from cldrd_peer_alloc
-        self.opened = []       # pointers from cldrd_peer_open
-        self.xD = [None] * world
-        self.xI = [None] * world
-        self.oD = self.oI = None
-        elems = cap_elems
-        sizes = [elems * 4, elems * 8] + ([elems * 4, elems * 8] if rank == 0 else [])
-        handles = torch.zeros((4, _lib.PEER_HANDLE_BYTES), dtype=torch.uint8)
+        self.max_k = max_k
+        self.handle = C.c_void_p()
         ok = True
+        mine = torch.zeros((_lib.PEER_HANDLE_BYTES,), dtype=torch.uint8)
         try:
-            for i, nbytes in enumerate(sizes):
-                ptr = C.c_void_p()
-                buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
-                check(lib().cldrd_peer_alloc(device, nbytes, C.byref(ptr), buf))
-                self.own.append(ptr.value)
-                handles[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+            check(lib().cldrd_node_create(C.byref(self.handle), device, world, rank, max_k))
+            buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+            check(lib().cldrd_node_handle(self.handle, buf))
+            mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
         except Exception:
             ok = False
-        dev = torch.device("cuda", device)
-        allh = torch.empty((world, 4, _lib.PEER_HANDLE_BYTES), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allh, handles.to(dev), group=group)
-        allh = allh.cpu()
+        cdev = _coll_dev(group)
+        allh = torch.empty((world * _lib.PEER_HANDLE_BYTES,), dtype=torch.uint8, device=cdev)   # flat: gloo insists
+        dist.all_gather_into_tensor(allh, mine.to(cdev), group=group)
+        allh = allh.cpu().view(world, _lib.PEER_HANDLE_BYTES)
+        ok = _all_ok(ok, group)           # nobody maps a block whose owner failed to create it
         if ok:
             try:
                 for r in range(world):
-                    for i in range(4 if r == 0 else 2):
-                        if r == rank:
-                            ptr_v = self.own[i]
-                        else:
-                            ptr = C.c_void_p()
-                            hb = (C.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(bytes(allh[r, i].tolist()))
-                            check(lib().cldrd_peer_open(device, hb, C.byref(ptr)))
-                            self.opened.append(ptr.value)
-                            ptr_v = ptr.value
-                        if i == 0:
-                            self.xD[r] = ptr_v
-                        elif i == 1:
-                            self.xI[r] = ptr_v
-                        elif i == 2:
-                            self.oD = ptr_v
-                        else:
-                            self.oI = ptr_v
+                    if r != rank:
+                        hb = (C.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(bytes(allh[r].tolist()))
+                        check(lib().cldrd_node_attach(self.handle, r, hb, None, -1))
             except Exception:
                 ok = False
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        self.ok = bool(flag.item())
-        if self.ok:
-            self.c_xD = (C.c_void_p * world)(*self.xD)
-            self.c_xI = (C.c_void_p * world)(*self.xI)
-        else:
+            ok = _all_ok(ok, group)
+        self.ok = ok
+        if not ok:
             self.close()
 
-    def fits(self, slice_rows: int, k: int) -> bool:
-        return self.ok and self.world * slice_rows * k <= self.cap_elems
+    def result_ptrs(self, owner: int):
+        d, i = C.c_void_p(), C.c_void_p()
+        check(lib().cldrd_node_result_ptrs(self.handle, owner, C.byref(d), C.byref(i)))
+        return d.value, i.value
+
+    def phase_ms(self) -> dict:
+        arr = (C.c_double * 5)()
+        check(lib().cldrd_node_phase_ms(self.handle, arr))
+        return dict(zip(["sample+barrier+levels", "scan+select", "counts+barrier+rescore", "barrier+merge+store",
+                         "barrier+status"], list(arr)))
 
     def close(self):
-        # every rank unmaps before anybody frees
-        for p in self.opened:
-            lib().cldrd_peer_close(self.device, C.c_void_p(p))
-        self.opened = []
+        """Collective: every rank unmaps its peers before anybody frees."""
+        if self.handle:
+            lib().cldrd_node_detach(self.handle)
         if dist.is_initialized():
             try:
-                torch.cuda.synchronize(self.device)
                 dist.barrier(group=self.group)
             except Exception:
                 pass
-        for p in self.own:
-            lib().cldrd_peer_free(self.device, C.c_void_p(p))
-        self.own = []
+        if self.handle:
+            lib().cldrd_node_destroy(self.handle)
+            self.handle = C.c_void_p()
         self.ok = False
 
 
@@ -154,12 +145,13 @@ class _SharedHostResult:
 
     _serial = 0
 
-    def __init__(self, rank: int, rows: int, k: int, group, register: bool = True):
+    def __init__(self, rank: int, rows: int, k: int, group, register: bool = True, device: int = 0):
         import mmap
         self.rank, self.group = rank, group
         self.cap_elems = rows * k
         self.nbytes = self.cap_elems * 12 + 64
         self.mm, self.base, self.ok = None, 0, False
+        self.dev_base = 0        # the block as this rank's kernels address it
         # every step below ends in a collective that all ranks reach whatever failed locally
         name, fd = [None], -1
         if rank == 0:
@@ -204,17 +196,17 @@ class _SharedHostResult:
             reg = lib().cldrd_host_register(C.c_void_p(self.base), self.nbytes) == 0
             if not reg:
                 self.base = 0
+            else:
+                dp = C.c_void_p()
+                reg = lib().cldrd_host_device_ptr(device, C.c_void_p(self.base), C.byref(dp)) == 0
+                self.dev_base = dp.value or 0
             good = self._all_ok(reg)
         self.ok = good
         if not good:
             self.close()
 
     def _all_ok(self, mine: bool) -> bool:
-        on_gpu = dist.get_backend(self.group) == "nccl"
-        flag = torch.tensor([1 if mine else 0], dtype=torch.int32,
-                            device=torch.device("cuda", torch.cuda.current_device()) if on_gpu else "cpu")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        return bool(flag.item())
+        return _all_ok(mine, self.group)
 
     def fits(self, rows: int, k: int) -> bool:
         return rows * k <= self.cap_elems
@@ -234,6 +226,7 @@ class _SharedHostResult:
         if self.base:
             lib().cldrd_host_unregister(C.c_void_p(self.base))
             self.base = 0
+            self.dev_base = 0
 
     def __del__(self):
         # the page-lock must go before the mapping does: a later mapping at the same address could not be
@@ -249,14 +242,25 @@ class ShardedSearcher:
     already in HBM, zero copy) or `from_file` (each rank preads only its own row range); `search` takes and
     returns CUDA tensors, `search_host` host arrays."""
 
+    SEED_MIN_ROWS = 1 << 20   # below this the per-shard progressive scheme is already cheap
+    RING = 3                  # batches of one search in flight (cldrd_node allows 4)
+
     def __init__(self, shard: _Shard, ntotal: int, d: int, id_map: Optional[torch.Tensor], group=None):
         self.shard = shard
         self.local = GpuIndexFlat(shard, shard.nrows, d)
         self.ntotal, self.d = ntotal, d
-        self.id_map = id_map  # int64 [ntotal] on rank 0's device, or None
+        self.id_map = id_map  # int64 [ntotal] on rank 0's device (replicated on first sharded use), or None
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._nx: Optional[_NodeExchange] = None
+        self._nx_disabled = False
+        self._host: Optional[_SharedHostResult] = None
+        self._host_disabled = False
+        self._setup_done = False
+        self._id_map_synced = False
+        self.last_seed_misses = 0
+        self.last_phase_ms = None
 
     @classmethod
     def from_rows(cls, rows: torch.Tensor, row0: int, ntotal: int, scan: str = "auto",
@@ -296,32 +300,226 @@ class ShardedSearcher:
             id_map = torch.from_numpy(ids).to(f"cuda:{device}")
         return cls(sh, n.value, d.value, id_map, group)
 
-    SEED_MIN_ROWS = 1 << 20   # below this the per-shard progressive scheme is already cheap
+    # ---- one-time agreements between the shards of one index ---------------------------------------------
 
-    def _sync_norm_bound(self):
-        """Shards of one index must use the same row-norm bound in their error band."""
-        if self.world == 1 or getattr(self, "_norm_synced", False):
+    def _setup(self):
+        """The error band every decision of the protocol uses (filter cut, counted cut, seed check) must be the
+        SAME on all shards: same scan precision (eps coefficient) and same row-norm bound.  scan="auto" picks f16
+        or tf32 per shard from that shard's own value range, so the ranks settle on the coarsest one here."""
+        if self.world == 1 or self._setup_done:
             return
+        cdev = _coll_dev(self.group)
+        order = {"f16": 0, "tf32": 1, "bf16": 2, "simt": 3}
+        mode = torch.tensor([order[self.shard.scan], -order[self.shard.scan]], dtype=torch.int32, device=cdev)
+        dist.all_reduce(mode, op=dist.ReduceOp.MAX, group=self.group)
+        hi, lo = int(mode[0].item()), -int(mode[1].item())
+        if hi != lo:
+            if self.shard.scan_request != "auto" or hi != order["tf32"]:
+                raise CldrdError(_lib.E_INVAL, f"the shards of one index use different scan modes ({lo} .. {hi}): "
+                                               "pass the same scan= on every rank")
+            if order[self.shard.scan] != hi:      # some other shard does not fit fp16: everybody scans in tf32
+                self.shard.refill("tf32")
         b = C.c_float()
         check(lib().cldrd_shard_norm_bound(self.shard.handle, C.byref(b)))
-        t = torch.tensor([b.value], dtype=torch.float32, device=f"cuda:{self.shard.device}")
+        t = torch.tensor([b.value], dtype=torch.float32, device=cdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         check(lib().cldrd_shard_set_norm_bound(self.shard.handle, C.c_float(float(t.item()))))
-        self._norm_synced = True
+        self._setup_done = True
 
-    def _levels(self, q: torch.Tensor, k: int) -> torch.Tensor:
-        """Steps 1+2: sample every shard, all-gather the per-shard sample scores (NCCL), keep the SEED_J best
-        of the union per query, best first.  The last column is the seed (a scan-score threshold near rank
-        3.5k of the whole index); the columns before it are the levels the shards count against."""
+    def _id_map_everywhere(self):
+        """Every rank's merge kernel applies the external ids to its slice: replicate rank 0's table once."""
+        if self._id_map_synced:
+            return
+        dev = torch.device("cuda", self.shard.device)
+        cdev = _coll_dev(self.group)
+        has = torch.tensor([1 if (self.rank == 0 and self.id_map is not None) else 0], dtype=torch.int32, device=cdev)
+        dist.broadcast(has, src=0, group=self.group)
+        if int(has.item()):
+            if self.rank != 0:
+                self.id_map = torch.empty((self.ntotal,), dtype=torch.int64, device=dev)
+            if cdev.type == "cuda":
+                dist.broadcast(self.id_map, src=0, group=self.group)
+            else:
+                t = self.id_map.cpu()
+                dist.broadcast(t, src=0, group=self.group)
+                self.id_map.copy_(t)
+        self._id_map_synced = True
+
+    def _node(self, k: int) -> Optional[_NodeExchange]:
+        """The node-local peer-memory exchange, or None when it is unavailable (CLDRD_DIST_P2P=0, IPC / peer
+        access refused -- agreed by all ranks): then NCCL moves the lists."""
+        if os.environ.get("CLDRD_DIST_P2P", "1") == "0" or self.world > _lib.MAX_PEERS or self._nx_disabled:
+            return None
+        nx = self._nx
+        if nx is not None and k <= nx.max_k:
+            return nx
+        if nx is not None:
+            nx.close()
+        self._nx = _NodeExchange(self.shard.device, self.rank, self.world, int(k), self.group)
+        if not self._nx.ok:
+            self._nx = None
+            self._nx_disabled = True
+        return self._nx
+
+    # ---- the node-wide search ------------------------------------------------------------------------------
+
+    def _end_batch(self, nx: _NodeExchange, b0: int):
+        nfail = C.c_int32()
+        idx = (C.c_int32 * _lib.QUERY_BATCH)()
+        check(lib().cldrd_node_search_end(self.shard.handle, nx.handle, C.byref(nfail), idx, _lib.QUERY_BATCH))
+        return [b0 + idx[i] for i in range(nfail.value)]
+
+    def _run_node(self, nx: _NodeExchange, q: torch.Tensor, k: int, seeded: bool, out_of_batch, out_rows=None,
+                  after_batch=None):
+        """Queue the batches of one search (at most RING in flight), return the queries (indices into q) that
+        have to be searched again -- the same list on every rank.  out_of_batch(b0, nb) -> (scores ptr, ids ptr)
+        of the batch's output rows; out_rows: optional int32 device tensor, output row of every query."""
         n = q.shape[0]
-        topj = self.local.sample_device(q, k)
-        allj = torch.empty((self.world,) + tuple(topj.shape), dtype=topj.dtype, device=topj.device)
-        dist.all_gather_into_tensor(allj, topj, group=self.group)
-        levels = torch.empty((n, _lib.SEED_J), dtype=torch.float32, device=q.device)
         st = torch.cuda.current_stream(q.device).cuda_stream
-        check(lib().cldrd_levels_from_samples(q.device.index, C.c_void_p(allj.data_ptr()), self.world, n,
-                                              C.c_void_p(levels.data_ptr()), C.c_void_p(st)))
-        return levels
+        idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
+        inflight, again = [], []
+        with self.local._lock:
+            for b0 in range(0, n, _lib.QUERY_BATCH):
+                nb = min(_lib.QUERY_BATCH, n - b0)
+                if len(inflight) >= self.RING:
+                    again += self._end_batch(nx, inflight.pop(0))
+                oD, oI = out_of_batch(b0, nb)
+                rows = C.c_void_p(out_rows[b0:b0 + nb].data_ptr()) if out_rows is not None else None
+                check(lib().cldrd_node_search_begin(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()), nb,
+                                                    int(k), 1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
+                                                    C.c_void_p(st)))
+                inflight.append(b0)
+                if after_batch is not None:
+                    after_batch(b0, nb)
+            while inflight:
+                again += self._end_batch(nx, inflight.pop(0))
+        self.last_phase_ms = nx.phase_ms()
+        return again
+
+    def _check_q(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 2 and
+                q.shape[1] == self.d):
+            raise TypeError(f"search: q must be a float32 CUDA tensor of shape [nq, {self.d}]")
+        if not 1 <= int(k) <= _lib.MAX_K:
+            raise RuntimeError(f"search: k={k} outside [1, {_lib.MAX_K}]")
+        return q.contiguous()
+
+    def search(self, q: torch.Tensor, k: int):
+        """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
+        q = self._check_q(q, k)
+        k = int(k)
+        if self.world == 1:
+            D, I = self.local.search_device(q, k, translate_ids=False)
+            if self.id_map is not None:
+                return merge_candidates(D.unsqueeze(0), I.unsqueeze(0), self.id_map)
+            return D, I
+        self._setup()
+        n, dev = q.shape[0], q.device
+        nx = self._node(k) if n > 0 else None
+        if nx is None:
+            return self._search_nccl(q, k)
+        self._id_map_everywhere()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        resD, resI = nx.result_ptrs(0)     # rank 0's result buffer, as this rank addresses it
+        outD = outI = None
+        if self.rank == 0:
+            outD = torch.empty((n, k), dtype=torch.float32, device=dev)
+            outI = torch.empty((n, k), dtype=torch.int64, device=dev)
+
+        def collect(b0, nb):               # rank 0: batch rows out of the result buffer before the next batch lands
+            if self.rank == 0:
+                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outD[b0:].data_ptr()), C.c_void_p(resD), nb * k * 4, C.c_void_p(st)))
+                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outI[b0:].data_ptr()), C.c_void_p(resI), nb * k * 8, C.c_void_p(st)))
+
+        again = self._run_node(nx, q, k, self.ntotal >= self.SEED_MIN_ROWS, lambda b0, nb: (resD, resI), None, collect)
+        self.last_seed_misses = len(again)
+        if again:    # rare: the seed sat above the true k-th score, or a survivor buffer overflowed: unseeded retry
+            idx = torch.tensor(again, dtype=torch.int64, device=dev)
+            q2 = q[idx].contiguous()
+            tmpD = torch.empty((len(again), k), dtype=torch.float32, device=dev) if self.rank == 0 else None
+            tmpI = torch.empty((len(again), k), dtype=torch.int64, device=dev) if self.rank == 0 else None
+
+            def collect2(b0, nb):
+                if self.rank == 0:
+                    check(lib().cldrd_peer_copy(dev.index, C.c_void_p(tmpD[b0:].data_ptr()), C.c_void_p(resD), nb * k * 4, C.c_void_p(st)))
+                    check(lib().cldrd_peer_copy(dev.index, C.c_void_p(tmpI[b0:].data_ptr()), C.c_void_p(resI), nb * k * 8, C.c_void_p(st)))
+
+            left = self._run_node(nx, q2, k, False, lambda b0, nb: (resD, resI), None, collect2)
+            assert not left, "an unseeded batch cannot raise queries"
+            if self.rank == 0:
+                outD[idx] = tmpD
+                outI[idx] = tmpI
+        return (outD, outI) if self.rank == 0 else (None, None)
+
+    def search_host(self, q_host, k: int, copy: bool = False):
+        """Host buffers in, host buffers out (the shape of the reference's `index.search(x, k)`,
+        retriever/retrieval_utils.py:135).
+
+        q_host: the replicated float32 [nq, d] queries in host memory (numpy array or CPU tensor; page-locked
+        memory makes the upload asynchronous).  Returns numpy (D, I) on rank 0, (None, None) elsewhere.  On one
+        node every rank's merge kernel stores its slice of the result straight into one shared page-locked block
+        over its own PCIe link; rank 0 returns views of that block (valid until the next search_host call) or,
+        with copy=True, fresh arrays."""
+        qh = torch.as_tensor(q_host)
+        assert qh.dtype == torch.float32 and qh.dim() == 2 and qh.shape[1] == self.d
+        if not 1 <= int(k) <= _lib.MAX_K:
+            raise RuntimeError(f"search: k={k} outside [1, {_lib.MAX_K}]")
+        k = int(k)
+        n = qh.shape[0]
+        dev = torch.device("cuda", self.shard.device)
+        stage = getattr(self, "_q_stage", None)
+        if stage is None or stage.shape[0] < n:
+            stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
+        q = stage[:n]
+        q.copy_(qh, non_blocking=True)
+
+        def via_device():
+            D, I = self.search(q, k)
+            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
+
+        if self.world == 1 or n == 0:
+            return via_device()
+        self._setup()
+        nx = self._node(k)
+        if nx is None:          # no peer mapping: device result on rank 0, one copy down
+            return via_device()
+        self._id_map_everywhere()
+        host = self._host
+        if not self._host_disabled and (host is None or not host.fits(n, k)):
+            if host is not None:
+                host.close()
+            host = self._host = _SharedHostResult(self.rank, n, k, self.group, device=dev.index)
+            if not host.ok:           # agreed by all ranks
+                host = self._host = None
+                self._host_disabled = True
+        if host is None:
+            return via_device()
+        baseD = host.dev_base
+        baseI = host.dev_base + host.ids_offset(n, k)
+        again = self._run_node(nx, q, k, self.ntotal >= self.SEED_MIN_ROWS,
+                               lambda b0, nb: (baseD + b0 * k * 4, baseI + b0 * k * 8))
+        self.last_seed_misses = len(again)
+        if again:
+            rows = torch.tensor(again, dtype=torch.int32, device=dev)
+            q2 = q[rows.long()].contiguous()
+            left = self._run_node(nx, q2, k, False, lambda b0, nb: (baseD, baseI), rows)
+            assert not left, "an unseeded batch cannot raise queries"
+        if self.rank != 0:
+            return None, None
+        D, I = host.views(n, k, n)
+        return (D.copy(), I.copy()) if copy else (D, I)
+
+    def close(self):
+        """Collective: releases the exchange block, the shared host block and the shard."""
+        if self._nx is not None:
+            self._nx.close()
+            self._nx = None
+        if self._host is not None:
+            self._host.close()
+            self._host = None
+        self.shard.close()
+
+    # ---- NCCL transport (no peer mapping available) ------------------------------------------------------------
 
     def _trim(self, D: torch.Tensor, I: torch.Tensor):
         """A seeded shard returns far fewer than k valid rows per query (about 3.5k / world): agree
@@ -335,226 +533,10 @@ class ShardedSearcher:
             return D, I
         return D[:, :w].contiguous(), I[:, :w].contiguous()
 
-    def _peer_exchange(self, n: int, k: int):
-        """The node-local peer-memory exchange for an [n, k] search, or None when it is unavailable
-        (CLDRD_DIST_P2P=0, CPU process group, IPC / peer access refused): then NCCL moves the lists."""
-        if os.environ.get("CLDRD_DIST_P2P", "1") == "0" or self.world > _lib.MAX_PEERS or n == 0:
-            return None
-        if getattr(self, "_px_disabled", False):
-            return None
-        sl = (n + self.world - 1) // self.world
-        px = getattr(self, "_px", None)
-        if px is not None and px.fits(sl, k):
-            return px
-        cap = self.world * sl * k
-        if px is not None:
-            cap = max(cap, px.cap_elems)
-            px.close()
-        self._px = _PeerExchange(self.shard.device, self.rank, self.world, cap, self.group)
-        if not self._px.ok:
-            self._px = None
-            self._px_disabled = True   # agreed by all ranks (all-reduce MIN): nobody retries
-        return self._px
-
-    def _search_p2p(self, px: "_PeerExchange", q: torch.Tensor, k: int, levels, seed, mark, marks, prof, host=None):
-        """Per batch of <= 8192 queries: scan + select with the seed and count the candidates above every
-        sample level; all-reduce the counts (32 ints per query) so that every shard knows a threshold that k
-        rows of the WHOLE index reach, and re-scores only what lies above it (about k / world rows per query);
-        the re-score kernel stores every query's list in the merging rank's memory (NVLink peer stores).
-        Then slice-wise merge + verify on every rank, the merge kernels storing into rank 0's result buffer.
-        Two scalar all-reduces are the barriers between the kernels' peer accesses."""
-        n, world, dev = q.shape[0], self.world, q.device
-        seeded = levels is not None
-        sl = (n + world - 1) // world
-        st = torch.cuda.current_stream(dev).cuda_stream
-        eps2 = torch.empty((n,), dtype=torch.float32, device=dev)
-        token = torch.zeros((1,), dtype=torch.int32, device=dev)
-        with self.local._lock:
-            for b0 in range(0, n, _lib.QUERY_BATCH):
-                nb = min(_lib.QUERY_BATCH, n - b0)
-                qb = q[b0:b0 + nb]
-                lv = levels[b0:b0 + nb] if seeded else None
-                counts = torch.empty((nb, _lib.SEED_J), dtype=torch.int32, device=dev)
-                check(lib().cldrd_scatter_begin(self.shard.handle, C.c_void_p(qb.data_ptr()), nb, int(k),
-                                                C.c_void_p(lv.data_ptr()) if seeded else None,
-                                                C.c_void_p(counts.data_ptr()), C.c_void_p(eps2[b0:].data_ptr()),
-                                                C.c_void_p(st)))
-                if seeded:
-                    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
-                check(lib().cldrd_scatter_finish(self.shard.handle, C.c_void_p(counts.data_ptr()),
-                                                 C.c_void_p(lv.data_ptr()) if seeded else None, world, self.rank, sl, b0,
-                                                 px.c_xD, px.c_xI, C.c_void_p(st)))
-        mark("seeded search + scatter")
-        dist.all_reduce(token, group=self.group)            # every plane of my buffers is written
-        if os.environ.get("CLDRD_DIST_DEBUG") == "1":
-            torch.cuda.synchronize()
-            print(f"[rank {self.rank}] scatter + barrier ok: n={n} k={k} sl={sl} cap={px.cap_elems}", flush=True)
-        lo = self.rank * sl
-        n_mine = max(0, min(sl, n - lo))
-        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
-        fail_sl = torch.zeros((sl,), dtype=torch.int32, device=dev)
-        if n_mine > 0:
-            if host is None:      # merged slice -> rank 0's device buffer (peer stores by the merge kernel)
-                outD = px.oD + lo * k * 4
-                outI = px.oI + lo * k * 8
-                idm = None
-            else:                 # merged slice (external ids applied) stays here, then goes to the shared host block
-                mD = torch.empty((n_mine, k), dtype=torch.float32, device=dev)
-                mI = torch.empty((n_mine, k), dtype=torch.int64, device=dev)
-                outD, outI = mD.data_ptr(), mI.data_ptr()
-                idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
-            check(lib().cldrd_merge_planes(dev.index, C.c_void_p(px.xD[self.rank]), C.c_void_p(px.xI[self.rank]), world, sl,
-                                           n_mine, k, k, idm, C.c_void_p(outD), C.c_void_p(outI), C.c_void_p(st)))
-            if host is not None:
-                rows_alloc = world * sl
-                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(host.base + lo * k * 4), C.c_void_p(outD), n_mine * k * 4,
-                                            C.c_void_p(st)))
-                check(lib().cldrd_peer_copy(dev.index, C.c_void_p(host.base + host.ids_offset(rows_alloc, k) + lo * k * 8), C.c_void_p(outI),
-                                            n_mine * k * 8, C.c_void_p(st)))
-            if seeded:
-                check(lib().cldrd_verify_seed(dev.index, C.c_void_p(outD), n_mine, k,
-                                              C.c_void_p(seed[lo:lo + n_mine].contiguous().data_ptr()),
-                                              C.c_void_p(eps2[lo:lo + n_mine].contiguous().data_ptr()),
-                                              C.c_void_p(fail_sl.data_ptr()), C.c_void_p(st)))
-                nfail[0] = fail_sl[:n_mine].sum()
-        mark("merge+verify")
-        dist.all_reduce(nfail, op=dist.ReduceOp.SUM, group=self.group)   # also: every slice is in rank 0's buffer
-        if host is not None:
-            return self._finish_host(host, q, k, n, sl, seeded, nfail, fail_sl, mark, marks, prof)
-        outD_t = outI_t = None
-        if self.rank == 0:
-            outD_t = torch.empty((n, k), dtype=torch.float32, device=dev)
-            outI_t = torch.empty((n, k), dtype=torch.int64, device=dev)
-            check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outD_t.data_ptr()), C.c_void_p(px.oD), n * k * 4, C.c_void_p(st)))
-            check(lib().cldrd_peer_copy(dev.index, C.c_void_p(outI_t.data_ptr()), C.c_void_p(px.oI), n * k * 8, C.c_void_p(st)))
-        mark("result")
-        misses = int(nfail.item()) if seeded else 0
-        if misses > 0:   # rare: the seed sat above the true k-th score for these queries
-            fail_all = torch.empty((world, sl), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(fail_all, fail_sl, group=self.group)
-            idx = torch.nonzero(fail_all.view(-1)[:n]).flatten()
-            D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
-            D2, I2 = self._trim(D2, I2)
-            allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
-            if self.rank == 0:
-                pD, pI = merge_candidates(allD2, allI2, None, k)
-                outD_t[idx] = pD
-                outI_t[idx] = pI
-        self.last_seed_misses = misses
-        mark("miss broadcast")
-        if prof:
-            torch.cuda.synchronize()
-            self.last_phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
-        if self.rank != 0:
-            return None, None
-        if self.id_map is not None:
-            outI_t = torch.where(outI_t >= 0, self.id_map[outI_t.clamp_min(0)], outI_t)
-        return outD_t, outI_t
-
-    def _finish_host(self, host, q, k, n, sl, seeded, nfail, fail_sl, mark, marks, prof):
-        """Tail of the host-result search: every rank's slice is in the shared block once the miss-count
-        all-reduce (already issued, stream-ordered behind the copies) has completed."""
-        world, dev = self.world, q.device
-        misses = int(nfail.item()) if seeded else 0      # synchronises this rank's stream
-        if not seeded:
-            torch.cuda.current_stream(dev).synchronize()
-        D = I = None
-        if self.rank == 0:
-            D, I = host.views(n, k, world * sl)
-        mark("result")
-        if misses > 0:
-            fail_all = torch.empty((world, sl), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(fail_all, fail_sl, group=self.group)
-            idx = torch.nonzero(fail_all.view(-1)[:n]).flatten()
-            D2, I2, _ = self.local.search_device_seeded(q[idx].contiguous(), k, None)
-            D2, I2 = self._trim(D2, I2)
-            allD2, allI2 = gather_candidates(D2, I2, dst=0, group=self.group)
-            if self.rank == 0:
-                pD, pI = merge_candidates(allD2, allI2, self.id_map, k)
-                rows = idx.cpu().numpy()
-                D[rows] = pD.cpu().numpy()
-                I[rows] = pI.cpu().numpy()
-        self.last_seed_misses = misses
-        mark("miss broadcast")
-        if prof:
-            torch.cuda.synchronize()
-            self.last_phase_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
-        return D, I
-
-    def _id_map_everywhere(self):
-        """The host-result path applies external ids inside every rank's merge: replicate rank 0's table once."""
-        if getattr(self, "_id_map_synced", False):
-            return
-        dev = torch.device("cuda", self.shard.device)
-        has = torch.tensor([1 if (self.rank == 0 and self.id_map is not None) else 0], dtype=torch.int32, device=dev)
-        dist.broadcast(has, src=0, group=self.group)
-        if int(has.item()):
-            if self.rank != 0:
-                self.id_map = torch.empty((self.ntotal,), dtype=torch.int64, device=dev)
-            dist.broadcast(self.id_map, src=0, group=self.group)
-        self._id_map_synced = True
-
-    def search_host(self, q_host, k: int):
-        """Host buffers in, host buffers out (the shape of the reference's `index.search(x, k)`).
-
-        q_host: the replicated float32 [nq, d] queries in host memory (numpy array or CPU tensor; page-locked
-        memory makes the upload asynchronous).  Returns numpy (D, I) on rank 0, (None, None) elsewhere.  On one
-        node the ranks write their slices of the result into one shared page-locked block, each over its own
-        PCIe link, and rank 0 returns views of that block: they are valid until the next search_host call."""
-        qh = torch.as_tensor(q_host)
-        assert qh.dtype == torch.float32 and qh.dim() == 2 and qh.shape[1] == self.d
-        n = qh.shape[0]
-        dev = torch.device("cuda", self.shard.device)
-        stage = getattr(self, "_q_stage", None)
-        if stage is None or stage.shape[0] < n:
-            stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
-        q = stage[:n]
-        q.copy_(qh, non_blocking=True)
-        if self.world == 1 or n == 0:
-            D, I = self.search(q, k)
-            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
-        self._sync_norm_bound()
-        px = self._peer_exchange(n, k)
-        if px is None:          # no peer mapping: device result on rank 0, one copy down
-            D, I = self.search(q, k)
-            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
-        self._id_map_everywhere()
-        sl = (n + self.world - 1) // self.world
-        host = getattr(self, "_host", None)
-        if not getattr(self, "_host_disabled", False) and (host is None or not host.fits(self.world * sl, k)):
-            if host is not None:
-                host.close()
-            host = self._host = _SharedHostResult(self.rank, self.world * sl, k, self.group)
-            if not host.ok:           # agreed by all ranks
-                host = self._host = None
-                self._host_disabled = True
-        if host is None:
-            D, I = self.search(q, k)
-            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
-        prof = os.environ.get("CLDRD_DIST_PROFILE") == "1"
-        marks = []
-
-        def mark(name):
-            if prof:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((name, e))
-
-        mark("start")
-        seeded = self.ntotal >= self.SEED_MIN_ROWS
-        levels = self._levels(q, k) if seeded else None
-        seed = levels[:, _lib.SEED_J - 1].contiguous() if seeded else None
-        mark("sample+allgather+seed")
-        return self._search_p2p(px, q, k, levels, seed, mark, marks, prof, host=host)
-
-    def search(self, q: torch.Tensor, k: int):
-        """q: replicated float32 [nq,d] CUDA tensor.  Returns (D, I) on rank 0, (None, None) elsewhere."""
-        if self.world == 1:
-            D, I = self.local.search_device(q, k, translate_ids=False)
-            if self.id_map is not None:
-                return merge_candidates(D.unsqueeze(0), I.unsqueeze(0), self.id_map)
-            return D, I
-        self._sync_norm_bound()
+    def _search_nccl(self, q: torch.Tensor, k: int):
+        """The same search with NCCL moving the data: all-gather of the sample scores -> seed; seeded search of
+        the shard; all-to-all so that rank j receives every shard's lists for the j-th slice of the queries,
+        merges and verifies that slice; only the merged [slice, k] results travel to rank 0 (gather)."""
         n = q.shape[0]
         prof = os.environ.get("CLDRD_DIST_PROFILE") == "1"
         marks = []
@@ -567,18 +549,19 @@ class ShardedSearcher:
 
         mark("start")
         seeded = self.ntotal >= self.SEED_MIN_ROWS and n > 0
-        levels = self._levels(q, k) if seeded else None
-        seed = levels[:, _lib.SEED_J - 1].contiguous() if seeded else None
+        seed = None
+        if seeded:
+            topj = self.local.sample_device(q, k)
+            allj = torch.empty((self.world,) + tuple(topj.shape), dtype=topj.dtype, device=topj.device)
+            dist.all_gather_into_tensor(allj, topj, group=self.group)
+            seed = torch.empty((n,), dtype=torch.float32, device=q.device)
+            st = torch.cuda.current_stream(q.device).cuda_stream
+            check(lib().cldrd_seed_from_samples(q.device.index, C.c_void_p(allj.data_ptr()), self.world, n,
+                                                C.c_void_p(seed.data_ptr()), C.c_void_p(st)))
         mark("sample+allgather+seed")
-        px = self._peer_exchange(n, k)
-        if px is not None:
-            return self._search_p2p(px, q, k, levels, seed, mark, marks, prof)
         D, I, eps2 = self.local.search_device_seeded(q, k, seed)
         mark("seeded search")
         D, I = self._trim(D, I)
-        # Distributed merge: all-to-all so that rank j receives every shard's lists for the j-th
-        # slice of the queries, merges and verifies that slice, and only the merged [slice, k]
-        # results travel to rank 0.  (A plain gather would make rank 0 receive and merge everything.)
         world, W = self.world, D.shape[1]
         sl = (n + world - 1) // world
         n_pad = sl * world
@@ -613,6 +596,7 @@ class ShardedSearcher:
             dist.gather(mD, None, dst=0, group=self.group)
             dist.gather(mI, None, dst=0, group=self.group)
         mark("gather")
+        self.last_seed_misses = 0
         if seeded:
             dist.all_reduce(nfail, op=dist.ReduceOp.SUM, group=self.group)
             if int(nfail.item()) > 0:   # rare: the seed sat above the true k-th score for these queries

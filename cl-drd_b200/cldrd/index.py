@@ -69,6 +69,20 @@ class _RowStore:
         return self.blocks[0]
 
 
+def _is_cuda_tensor(x) -> bool:
+    return (not isinstance(x, np.ndarray)) and getattr(x, "is_cuda", False) is True
+
+
+def _check_xd(x, d: int, what: str):
+    """Device-resident queries (extension): a float32 [n, d] CUDA tensor."""
+    import torch
+    if x.dtype != torch.float32:
+        raise TypeError(f"{what}: tensor must be float32, got {x.dtype}")
+    assert x.dim() == 2, f"{what}: expected a 2-D tensor"
+    assert x.shape[1] == d, f"{what}: dimension {x.shape[1]} != index dimension {d}"
+    return x.contiguous()
+
+
 def _check_x(x, d: int, what: str) -> np.ndarray:
     # faiss' SWIG wrapper asserts on shape and raises TypeError on dtype; same here
     if not isinstance(x, np.ndarray):
@@ -318,16 +332,21 @@ class _Shard:
     def fill(self, filler) -> None:
         """filler(shard) populates rows/ids; finalize, retrying with tf32 when "auto" picked fp16
         for values that do not fit fp16."""
+        self._filler = filler
         filler(self)
         try:
             check(lib().cldrd_shard_finalize(self.handle, None))
         except CldrdError as e:
             if self.scan_request != "auto" or e.code != _lib.E_INVAL:
                 raise
-            self.close()
-            self._create("tf32")
-            filler(self)
-            check(lib().cldrd_shard_finalize(self.handle, None))
+            self.refill("tf32")
+
+    def refill(self, scan: str) -> None:
+        """Rebuild the shard with another scan precision (rows are loaded / adopted again)."""
+        self.close()
+        self._create(scan)
+        self._filler(self)
+        check(lib().cldrd_shard_finalize(self.handle, None))
 
     def stats(self) -> dict:
         arr = (C.c_int64 * 8)()
@@ -405,8 +424,11 @@ class GpuIndexFlat:
         self._shard.close()
 
     def search(self, x, k):
+        """x: float32 [n, d] numpy array (the reference's call) or, as an extension, a CUDA tensor holding the
+        embeddings the encoder just produced (no host round trip on the way in).  Returns numpy (D, I)."""
         k = int(k)
-        x = _check_x(x, self.d, "search")
+        on_dev = _is_cuda_tensor(x)
+        x = _check_xd(x, self.d, "search") if on_dev else _check_x(x, self.d, "search")
         assert k > 0, "search: k must be positive"
         if k > _lib.MAX_K:
             raise RuntimeError(f"search: k={k} above the GPU limit {_lib.MAX_K} (same limit as faiss GpuIndexFlat)")
@@ -414,7 +436,14 @@ class GpuIndexFlat:
         # results land in page-locked arrays the caller owns: one DMA, no staging copy
         D = _lib.pinned_empty((n, k), np.float32)
         I = _lib.pinned_empty((n, k), np.int64)
-        if n:
+        if n and on_dev:
+            import torch
+            Dd, Id = self.search_device(x, k)
+            st = torch.cuda.current_stream(x.device)
+            check(lib().cldrd_peer_copy(x.device.index, ptr(D), C.c_void_p(Dd.data_ptr()), D.nbytes, C.c_void_p(st.cuda_stream)))
+            check(lib().cldrd_peer_copy(x.device.index, ptr(I), C.c_void_p(Id.data_ptr()), I.nbytes, C.c_void_p(st.cuda_stream)))
+            st.synchronize()
+        elif n:
             with self._lock:
                 check(lib().cldrd_search_host(self._shard.handle, ptr(x), n, k, ptr(D), ptr(I)))
         return D, I
@@ -487,68 +516,171 @@ def shard_ranges(ntotal: int, parts: int) -> List[range]:
 
 
 class GpuIndexShards:
-    """What index_cpu_to_gpu_multiple(..., shard=True) returns inside ONE process: the index
-    row-sharded over several GPUs; per-shard candidates are copied to the first device over
-    NVLink and merged there by the same kernel the NCCL path uses."""
+    """What index_cpu_to_gpu_multiple(..., shard=True) returns inside ONE process: the index row-sharded over
+    several GPUs.  A search is the node-wide protocol of include/cldrd.h ("Sharded search on one node") driven by
+    one host thread: one asynchronous cldrd_node_search_begin per shard and batch, the shards' kernels exchanging
+    sample scores, counts and re-scored lists through each other's HBM over NVLink, every shard's merge kernel
+    storing its slice of the result straight into the caller's page-locked arrays.  Results are bit-identical to
+    the single-GPU search."""
+
+    SEED_MIN_ROWS = 1 << 20
+    RING = 3
 
     def __init__(self, shards: List[_Shard], ids: Optional[np.ndarray], ntotal: int, d: int):
         import torch
+        self._torch = torch
         self._shards = shards
         self.ntotal, self.d = ntotal, d
-        self._torch = torch
-        self._dev0 = shards[0].device
-        self._id_map = None
+        self.metric_type = METRIC_INNER_PRODUCT
+        self.is_trained = True
+        self._lock = threading.Lock()
+        self._devs = [torch.device("cuda", sh.device) for sh in shards]
+        self._streams = [torch.cuda.Stream(device=dv) for dv in self._devs]
+        self._nodes: List[C.c_void_p] = []
+        self._node_k = 0
+        self._q = [None] * len(shards)
+        self.last_seed_misses = 0
+        # every decision of the protocol uses the same error band on all shards: same scan precision, same norm bound
+        if len({sh.scan for sh in shards}) > 1:
+            for sh in shards:
+                if sh.scan != "tf32":
+                    sh.refill("tf32")
+        bound = 0.0
+        for sh in shards:
+            b = C.c_float()
+            check(lib().cldrd_shard_norm_bound(sh.handle, C.byref(b)))
+            bound = max(bound, b.value)
+        for sh in shards:
+            check(lib().cldrd_shard_set_norm_bound(sh.handle, C.c_float(bound)))
+        self._id_maps = [None] * len(shards)
         if ids is not None:
-            self._id_map = torch.from_numpy(ids).to(f"cuda:{self._dev0}")
+            first = {}
+            for i, dv in enumerate(self._devs):      # one replica per device
+                if dv not in first:
+                    first[dv] = torch.from_numpy(ids).to(dv)
+                self._id_maps[i] = first[dv]
+
+    @property
+    def scan(self) -> str:
+        return self._shards[0].scan
+
+    def last_stats(self) -> List[dict]:
+        return [sh.stats() for sh in self._shards]
+
+    def _drop_nodes(self):
+        for n in self._nodes:
+            lib().cldrd_node_detach(n)
+        for n in self._nodes:
+            lib().cldrd_node_destroy(n)
+        self._nodes = []
+        self._node_k = 0
+
+    def _ensure_nodes(self, k: int):
+        if self._nodes and k <= self._node_k:
+            return
+        self._drop_nodes()
+        G = len(self._shards)
+        try:
+            for r, sh in enumerate(self._shards):
+                h = C.c_void_p()
+                check(lib().cldrd_node_create(C.byref(h), sh.device, G, r, int(k)))
+                self._nodes.append(h)
+            for r, sh in enumerate(self._shards):
+                for p, other in enumerate(self._shards):
+                    if p != r:
+                        blk = lib().cldrd_node_block(self._nodes[p])
+                        check(lib().cldrd_node_attach(self._nodes[r], p, None, C.c_void_p(blk), other.device))
+        except Exception:
+            self._drop_nodes()
+            raise
+        self._node_k = int(k)
 
     def close(self):
+        self._drop_nodes()
         for s in self._shards:
             s.close()
+
+    def _end_all(self, b0: int):
+        again = None
+        for sh, node in zip(self._shards, self._nodes):
+            nfail = C.c_int32()
+            idx = (C.c_int32 * _lib.QUERY_BATCH)()
+            check(lib().cldrd_node_search_end(sh.handle, node, C.byref(nfail), idx, _lib.QUERY_BATCH))
+            mine = [b0 + idx[i] for i in range(nfail.value)]
+            assert again is None or again == mine, "the shards disagree on the queries to search again"
+            again = mine
+        return again
+
+    def _run(self, qs, n: int, k: int, seeded: bool, outs, out_rows=None):
+        """qs[i]: the queries on shard i's device; outs[i]: (scores, ids) base addresses as shard i's device sees the
+        output arrays; out_rows[i]: optional int32 device tensor with the output row of every query."""
+        inflight, again = [], []
+        for b0 in range(0, n, _lib.QUERY_BATCH):
+            nb = min(_lib.QUERY_BATCH, n - b0)
+            if len(inflight) >= self.RING:
+                again += self._end_all(inflight.pop(0))
+            for i, (sh, node) in enumerate(zip(self._shards, self._nodes)):
+                oD, oI = outs[i]
+                if out_rows is None:
+                    oD, oI, rows = oD + b0 * k * 4, oI + b0 * k * 8, None
+                else:
+                    rows = C.c_void_p(out_rows[i][b0:b0 + nb].data_ptr())
+                idm = C.c_void_p(self._id_maps[i].data_ptr()) if self._id_maps[i] is not None else None
+                check(lib().cldrd_node_search_begin(sh.handle, node, C.c_void_p(qs[i][b0:b0 + nb].data_ptr()), nb, k,
+                                                    1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
+                                                    C.c_void_p(self._streams[i].cuda_stream)))
+            inflight.append(b0)
+        while inflight:
+            again += self._end_all(inflight.pop(0))
+        return again
 
     def search(self, x, k):
         torch = self._torch
         k = int(k)
-        x = _check_x(x, self.d, "search")
+        on_dev = _is_cuda_tensor(x)
+        x = _check_xd(x, self.d, "search") if on_dev else _check_x(x, self.d, "search")
+        assert k > 0, "search: k must be positive"
         if k > _lib.MAX_K:
             raise RuntimeError(f"search: k={k} above the GPU limit {_lib.MAX_K}")
         n = x.shape[0]
-        xt = torch.from_numpy(x)
-        Ds, Is = [], []
-        threads = []
-
-        def work(sh: _Shard, slot: int):
-            dev = torch.device("cuda", sh.device)
-            with torch.cuda.device(dev):
-                q = xt.to(dev, non_blocking=False)
-                D = torch.empty((n, k), dtype=torch.float32, device=dev)
-                I = torch.empty((n, k), dtype=torch.int64, device=dev)
-                st = torch.cuda.current_stream(dev)
-                check(lib().cldrd_search_dev(sh.handle, C.c_void_p(q.data_ptr()), n, k, 0, C.c_void_p(D.data_ptr()),
-                                             C.c_void_p(I.data_ptr()), C.c_void_p(st.cuda_stream)))
+        # results land in page-locked arrays the caller owns, written by the shards' merge kernels
+        D = _lib.pinned_empty((n, k), np.float32)
+        I = _lib.pinned_empty((n, k), np.int64)
+        if n == 0:
+            return D, I
+        with self._lock:
+            self._ensure_nodes(k)
+            # one upload (none for device-resident embeddings), then NVLink copies to the other shards
+            q0 = x.to(self._devs[0]) if on_dev else torch.from_numpy(x).to(self._devs[0])
+            torch.cuda.current_stream(q0.device).synchronize()
+            qs, outs = [], []
+            for i, dv in enumerate(self._devs):
+                with torch.cuda.stream(self._streams[i]):
+                    if dv == self._devs[0]:
+                        self._streams[i].wait_stream(torch.cuda.current_stream(dv))
+                        qi = q0
+                    else:
+                        qi = torch.empty_like(q0, device=dv)
+                        qi.copy_(q0, non_blocking=True)
+                    qs.append(qi)
+                pD, pI = C.c_void_p(), C.c_void_p()
+                check(lib().cldrd_host_device_ptr(dv.index, C.c_void_p(D.ctypes.data), C.byref(pD)))
+                check(lib().cldrd_host_device_ptr(dv.index, C.c_void_p(I.ctypes.data), C.byref(pI)))
+                outs.append((pD.value, pI.value))
+            again = self._run(qs, n, k, self.ntotal >= self.SEED_MIN_ROWS, outs)
+            self.last_seed_misses = len(again)
+            if again:   # rare: seed above the true k-th score, or a survivor buffer overflowed: unseeded retry
+                q2, rows = [], []
+                for i, dv in enumerate(self._devs):
+                    with torch.cuda.stream(self._streams[i]):
+                        idx = torch.tensor(again, dtype=torch.int64, device=dv)
+                        q2.append(qs[i][idx].contiguous())
+                        rows.append(idx.to(torch.int32))
+                left = self._run(q2, len(again), k, False, outs, rows)
+                assert not left, "an unseeded batch cannot raise queries"
+            for st in self._streams:
                 st.synchronize()
-                Ds[slot], Is[slot] = D, I
-
-        Ds = [None] * len(self._shards)
-        Is = [None] * len(self._shards)
-        for i, sh in enumerate(self._shards):
-            t = threading.Thread(target=work, args=(sh, i))
-            t.start()
-            threads.append(t)
-        for t in threads:
-            t.join()
-        dev0 = torch.device("cuda", self._dev0)
-        with torch.cuda.device(dev0):
-            allD = torch.stack([d_.to(dev0) for d_ in Ds]).contiguous()
-            allI = torch.stack([i_.to(dev0) for i_ in Is]).contiguous()
-            outD = torch.empty((n, k), dtype=torch.float32, device=dev0)
-            outI = torch.empty((n, k), dtype=torch.int64, device=dev0)
-            st = torch.cuda.current_stream(dev0)
-            check(lib().cldrd_merge(self._dev0, C.c_void_p(allD.data_ptr()), C.c_void_p(allI.data_ptr()),
-                                    len(self._shards), n, k,
-                                    C.c_void_p(self._id_map.data_ptr()) if self._id_map is not None else None,
-                                    C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()),
-                                    C.c_void_p(st.cuda_stream)))
-            return outD.cpu().numpy(), outI.cpu().numpy()
+        return D, I
 
 
 def index_cpu_to_gpu_multiple(vres, vdev: Sequence[int], index, co: Optional[GpuMultipleClonerOptions] = None):

@@ -38,7 +38,10 @@ def index_retrieve_arrays(index, query_embeddings, topk):
     the index for all queries instead of the reference's 128-query round trips."""
     print("Query Num", len(query_embeddings))
     start = timer()
-    D, I = index.search(np.ascontiguousarray(query_embeddings, dtype=np.float32), topk)
+    if not isinstance(query_embeddings, np.ndarray) and getattr(query_embeddings, "is_cuda", False):
+        D, I = index.search(query_embeddings, topk)          # device-resident embeddings: no host round trip
+    else:
+        D, I = index.search(np.ascontiguousarray(query_embeddings, dtype=np.float32), topk)
     elapsed_time = timer() - start
     print(f"Elapsed Time: {elapsed_time:.1f}s, Elapsed Time per query: "
           f"{1000 * elapsed_time / max(len(query_embeddings), 1):.1f}ms")
@@ -85,9 +88,13 @@ def construct_flatindex_from_embeddings(embeddings, ids):
     return index
 
 
-def get_embeddings_from_scratch(model, dataloader, use_fp16, is_query, show_progress_bar=False):
+def get_embeddings_from_scratch(model, dataloader, use_fp16, is_query, show_progress_bar=False, to_device=False):
     """retriever/retrieval_utils.py:30-58: encoder forward under autocast, CLS vectors gathered to
-    a float32 [N, hidden] ndarray + ids in file order.  The encoder stays a PyTorch module."""
+    a float32 [N, hidden] ndarray + ids in file order.  The encoder stays a PyTorch module.
+
+    to_device=True (extension) skips the reference's per-batch `.cpu().numpy()` round trip
+    (retriever/retrieval_utils.py:47): the [N, hidden] float32 embeddings stay in HBM as one torch tensor, which
+    `index.search` / `index_retrieve_arrays` accept directly."""
     import torch
     embeddings, embeddings_ids = [], []
     model.eval()
@@ -95,12 +102,17 @@ def get_embeddings_from_scratch(model, dataloader, use_fp16, is_query, show_prog
     for batch in dataloader:
         with torch.no_grad():
             with torch.autocast(device_type=dev.type, dtype=torch.float16, enabled=bool(use_fp16) and dev.type == "cuda"):
-                seq = {k: v.to(dev) for k, v in batch["seq"].items()}
+                seq = {k: v.to(dev, non_blocking=True) for k, v in batch["seq"].items()}
                 reps = model.query_embs(seq) if is_query else model.passage_embs(seq)
             text_ids = batch["id"]
-        embeddings.append(reps.float().cpu().numpy())
+        embeddings.append(reps.float() if to_device else reps.float().cpu().numpy())
         assert isinstance(text_ids, list)
         embeddings_ids.extend(text_ids)
+    if to_device:
+        embeddings = torch.cat(embeddings).contiguous() if embeddings else torch.empty((0, 0), device=dev)
+        assert len(embeddings_ids) == embeddings.shape[0]
+        print(f"# nan in embeddings: {int(torch.isnan(embeddings).sum().item())}")
+        return embeddings, embeddings_ids
     embeddings = np.concatenate(embeddings)
     assert len(embeddings_ids) == embeddings.shape[0]
     print(f"# nan in embeddings: {np.sum(np.isnan(embeddings))}")

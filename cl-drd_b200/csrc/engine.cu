@@ -12,6 +12,8 @@
 #include <unistd.h>
 #include <map>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common_host.h"
@@ -19,6 +21,7 @@
 #include "scan_tc.cuh"
 #include "scan_tc2.cuh"
 #include "select.cuh"
+#include "node.cuh"
 
 using namespace cldrd;
 
@@ -166,23 +169,16 @@ struct cldrd_shard {
 
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    // two-phase sharded search (cldrd_scatter_begin / cldrd_scatter_finish): the batch between the calls
-    struct {
-        bool active = false;
-        const float* q = nullptr;
-        int nq = 0, k = 0;
-        bool seeded = false;
-        int64_t launches = 0, chunks = 0;
-    } pend;
-    float* w_cut = nullptr;       // [kQueryBatch] re-score cut of the pending batch
+    float* w_levels = nullptr;    // [kQueryBatch][CLDRD_SEED_J] levels of the node-wide search (best first)
 
-    // scatter mode of the current search (cldrd_search_dev_scatter): results go to peer buffers
+    // scatter mode of the current re-score (node-wide search): lists go to the merging rank's key planes
     struct {
         int world = 0, rank = 0;
         int64_t slice = 0;
-        int64_t q0 = 0;   // first query of the current batch within the search
-        float* scores[CLDRD_MAX_PEERS];
-        int64_t* rows[CLDRD_MAX_PEERS];
+        int key_stride = 0;
+        bool raise_fail = false;
+        PeerPtrs keys;
+        PeerPtrs qfail;
     } sc;
 
     // optional per-kernel timing of the scan launches (bench roofline): event pairs on the
@@ -223,8 +219,8 @@ void free_workspace(cldrd_shard* s) {
     s->w_unit_ctr = nullptr;
     cudaFree(s->w_fail);
     cudaFree(s->w_fail_index);
-    cudaFree(s->w_cut);
-    s->w_cut = nullptr;
+    cudaFree(s->w_levels);
+    s->w_levels = nullptr;
     cudaFree(s->w_list);
     cudaFree(s->w_surv);
     cudaFree(s->w_dense);
@@ -261,7 +257,7 @@ int ensure_workspace(cldrd_shard* s) {
     CU_TRY(cudaMemset(s->w_wait, 0, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&s->w_fail, Q * sizeof(int)));
     CU_TRY(cudaMalloc(&s->w_fail_index, Q * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->w_cut, Q * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->w_levels, Q * CLDRD_SEED_J * sizeof(float)));
     CU_TRY(cudaMalloc(&s->w_list, Q * keep_cap * sizeof(uint64_t)));
     CU_TRY(cudaMalloc(&s->w_surv, kSurvTotal * sizeof(uint64_t)));
     CU_TRY(cudaMalloc(&s->w_dense, Q * kDensePiece * sizeof(float)));
@@ -277,6 +273,53 @@ int ensure_workspace(cldrd_shard* s) {
     }
     s->ws_keep_cap = keep_cap;
     return CLDRD_OK;
+}
+
+// CUDA loads a kernel's code on its first launch, and that load may synchronise the whole context.  The node-wide
+// search keeps flag barriers spinning on one stream while another stream of the same process still has kernels to
+// launch (several shards driven by one host thread): a first-time load behind a spinning barrier would wait for it
+// forever.  So every kernel of the library is loaded up front, once per device.
+template <typename F>
+void preload_one(F* fn) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, fn) != cudaSuccess) cudaGetLastError();
+}
+void preload_kernels(int device) {
+    static std::mutex mu;
+    static std::map<int, bool> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[device]) return;
+    done[device] = true;
+#define PRELOAD_TC(KIND)                          \
+    preload_one(scan_tc_kernel<KIND, TC_DENSE>);  \
+    preload_one(scan_tc_kernel<KIND, TC_MAXES>);  \
+    preload_one(scan_tc_kernel<KIND, TC_FILTER>); \
+    preload_one(scan_tc2_kernel<KIND, TC_DENSE>); \
+    preload_one(scan_tc2_kernel<KIND, TC_MAXES>); \
+    preload_one(scan_tc2_kernel<KIND, TC_FILTER>)
+    PRELOAD_TC(0);
+    PRELOAD_TC(1);
+    PRELOAD_TC(2);
+#undef PRELOAD_TC
+    preload_one(scan_simt_kernel<true, true>);
+    preload_one(scan_simt_kernel<true, false>);
+    preload_one(scan_simt_kernel<false, true>);
+    preload_one(scan_simt_kernel<false, false>);
+    preload_one(select_merge_kernel);
+    preload_one(rescore_sort_kernel);
+    preload_one(merge_kernel);
+    preload_one(query_prep_kernel);
+    preload_one(index_prep_kernel);
+    preload_one(sample_topj_kernel);
+    preload_one(seed_from_samples_kernel);
+    preload_one(verify_seed_kernel);
+    preload_one(apply_seed_kernel);
+    preload_one(gather_failed_kernel);
+    preload_one(node_barrier_kernel);
+    preload_one(levels_seed_kernel);
+    preload_one(count_levels_peers_kernel);
+    preload_one(merge_keys_kernel);
+    preload_one(node_tail_kernel);
 }
 
 // error-bound coefficients: eps = coef * |q| * max|b| + abs_coef * (|q| + max|b|)   
@@ -547,8 +590,15 @@ int launch_prep(BatchCtx& c) {
 // rows are scattered through out_index).  n_pad_small > 0: launch with shared memory for lists of
 // at most that many entries (so that the CTAs fit next to a running scan CTA); longer lists are
 // flagged as failed and redone by the fallback.
+struct CountedCut {
+    const int* planes = nullptr;   // [parts][stride] ints: counts the shards stored into this rank's block
+    size_t stride = 0;
+    int parts = 0;
+    const float* levels = nullptr;
+};
+
 int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool translate, const int* out_index,
-                   int* fail_flags, cudaStream_t st, int n_pad_small = 0, const float* cut = nullptr) {
+                   int* fail_flags, cudaStream_t st, int n_pad_small = 0, const CountedCut* cc = nullptr) {
     cldrd_shard* s = c.s;
     RescoreParams p{};
     p.xb = s->xb;
@@ -569,16 +619,24 @@ int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool transl
     p.fail = fail_flags ? fail_flags + c.qoff : nullptr;
     p.fail_set = fail_flags ? fail_flags + c.qoff : nullptr;
     p.stats = s->w_stats;
-    p.cut = cut ? cut + c.qoff : nullptr;
+    p.cut = nullptr;
+    if (cc) {
+        p.cnt_planes = cc->planes;
+        p.cnt_plane_stride = cc->stride;
+        p.cnt_parts = cc->parts;
+        p.levels = cc->levels;
+        p.lv_j = CLDRD_SEED_J;
+        p.band = s->w_band + c.qoff;
+    }
     p.sc_world = s->sc.world;
     if (s->sc.world > 0) {
         p.sc_rank = s->sc.rank;
         p.sc_slice = s->sc.slice;
-        p.q_base = s->sc.q0 + (out_index ? 0 : c.qoff);
-        for (int i = 0; i < s->sc.world; ++i) {
-            p.sc_scores[i] = s->sc.scores[i];
-            p.sc_rows[i] = s->sc.rows[i];
-        }
+        p.q_base = out_index ? 0 : c.qoff;
+        p.sc_key_stride = s->sc.key_stride;
+        p.sc_raise_fail = s->sc.raise_fail ? 1 : 0;
+        p.sc_keys = s->sc.keys;
+        p.sc_qfail = s->sc.qfail;
     }
     const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
     // few queries (the reference's batch=128 loop): one CTA per query leaves most SMs with a single
@@ -627,8 +685,9 @@ SamplePlan sample_plan(const cldrd_shard* s, int k) {
 }
 
 // Scan the shard's sample in one launch and leave each query's best CLDRD_SEED_J sample values
-// (best first, -inf padded) in out_topj [nq][CLDRD_SEED_J].  Uses the batch workspace.
-int run_sample(BatchCtx& c, float* out_topj) {
+// (best first, -inf padded) at element offset out_off of every buffer in outs, [nq][CLDRD_SEED_J].  Uses the batch
+// workspace.
+int run_sample(BatchCtx& c, const PeerPtrs& outs, int nouts, size_t out_off) {
     cldrd_shard* s = c.s;
     const SamplePlan sp = sample_plan(s, c.k);
     int cols = 0;
@@ -639,10 +698,17 @@ int run_sample(BatchCtx& c, float* out_topj) {
         cols = tc ? sp.tiles * (TC_BN / 32) : sp.tiles * TC_BN;
     }
     static_assert(CLDRD_SEED_J <= 64, "sample_topj_kernel sorts at most 64 values");
-    sample_topj_kernel<<<c.nq, 256, size_t(std::max(cols, 1)) * 8, c.st>>>(s->w_dense, kDensePiece, cols, CLDRD_SEED_J, out_topj);
+    sample_topj_kernel<<<c.nq, 256, size_t(std::max(cols, 1)) * 8, c.st>>>(s->w_dense, kDensePiece, cols, CLDRD_SEED_J, outs, nouts,
+                                                                           out_off);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;
+}
+
+int run_sample(BatchCtx& c, float* out_topj) {
+    PeerPtrs one{};
+    one.p[0] = out_topj;
+    return run_sample(c, one, 1, 0);
 }
 
 int apply_seed(BatchCtx& c, const float* seed_in) {
@@ -960,47 +1026,81 @@ int cldrd_shard_load_file(cldrd_shard* s, const char* path) {
     if (s->xb && !s->xb_owned) return fail(CLDRD_ESTATE, "shard_load_file: rows were adopted");
     DeviceGuard g(s->device);
     if ((rc = ensure_rows(s))) return rc;
-    // pread -> pinned double buffer -> cudaMemcpyAsync; the payload starts at an odd byte offset
-    // (82), so it is staged rather than mapped.
+    // pread -> page-locked ring -> cudaMemcpyAsync: the payload starts at an odd byte offset (82), so it is staged
+    // rather than mapped.  One reader is bound by a single core's page-cache copy (a few GB/s) while the PCIe link
+    // takes > 50 GB/s, so several readers each stream their own interleaved pieces through their own two buffers
+    // and their own stream.  Everything a reader owns is released on every path out of it.
     const size_t row_bytes = size_t(s->d) * 4;
-    const size_t piece_rows = std::max<size_t>(1, (size_t(64) << 20) / row_bytes);
-    char* pin[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    cudaStream_t st;
-    CU_TRY(cudaStreamCreate(&st));
-    for (int i = 0; i < 2; ++i) {
-        CU_TRY(cudaHostAlloc(&pin[i], piece_rows * row_bytes, cudaHostAllocDefault));
-        CU_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    }
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) rc = fail(CLDRD_EIO, "cannot open '%s'", path);
-    int b = 0;
-    for (int64_t r = 0; r < s->nrows && !rc; r += int64_t(piece_rows), b ^= 1) {
-        const size_t n = size_t(std::min<int64_t>(int64_t(piece_rows), s->nrows - r));
-        cudaEventSynchronize(ev[b]);
-        size_t want = n * row_bytes, got = 0;
-        off_t off = off_t(info.data_off) + off_t(s->row0 + r) * off_t(row_bytes);
-        while (got < want) {
-            ssize_t x = pread(fd, pin[b] + got, want - got, off + off_t(got));
-            if (x <= 0) {
-                rc = fail(CLDRD_EIO, "short read from '%s'", path);
+    const size_t piece_rows = std::max<size_t>(1, (size_t(32) << 20) / row_bytes);
+    const int64_t npieces = (s->nrows + int64_t(piece_rows) - 1) / int64_t(piece_rows);
+    int readers = 4;
+    if (const char* e = getenv("CLDRD_LOAD_THREADS")) readers = std::max(1, atoi(e));
+    readers = int(std::max<int64_t>(1, std::min<int64_t>(readers, npieces)));
+    std::vector<int> rcs(size_t(readers), CLDRD_OK);
+    std::vector<std::string> errs{size_t(readers)};
+    const int device = s->device;
+    auto reader = [&](int t) {
+        auto bail = [&](int code, const char* what, const char* detail) {
+            rcs[size_t(t)] = code;
+            errs[size_t(t)] = std::string(what) + (detail ? detail : "");
+        };
+        if (cudaSetDevice(device) != cudaSuccess) return bail(CLDRD_ECUDA, "cudaSetDevice failed", nullptr);
+        char* pin[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        int fd = -1;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaHostAlloc(&pin[i], piece_rows * row_bytes, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            bail(CLDRD_ECUDA, "staging buffers: ", cudaGetErrorString(e));
+        } else if ((fd = open(path, O_RDONLY)) < 0) {
+            bail(CLDRD_EIO, "cannot open ", path);
+        }
+        int b = 0;
+        for (int64_t p = t; p < npieces && !rcs[size_t(t)]; p += readers, b ^= 1) {
+            const int64_t r = p * int64_t(piece_rows);
+            const size_t n = size_t(std::min<int64_t>(int64_t(piece_rows), s->nrows - r));
+            cudaEventSynchronize(ev[b]);     // the copy that last used this buffer is done
+            const size_t want = n * row_bytes;
+            size_t got = 0;
+            const off_t off = off_t(info.data_off) + off_t(s->row0 + r) * off_t(row_bytes);
+            while (got < want) {
+                ssize_t x = pread(fd, pin[b] + got, want - got, off + off_t(got));
+                if (x <= 0) {
+                    bail(CLDRD_EIO, "short read from ", path);
+                    break;
+                }
+                got += size_t(x);
+            }
+            if (rcs[size_t(t)]) break;
+            if (cudaMemcpyAsync(reinterpret_cast<char*>(s->xb) + size_t(r) * row_bytes, pin[b], want, cudaMemcpyHostToDevice, st) !=
+                cudaSuccess) {
+                cudaGetLastError();
+                bail(CLDRD_ECUDA, "H2D copy failed", nullptr);
                 break;
             }
-            got += size_t(x);
+            cudaEventRecord(ev[b], st);
         }
-        if (rc) break;
-        if (cudaMemcpyAsync(reinterpret_cast<char*>(s->xb) + size_t(r) * row_bytes, pin[b], want, cudaMemcpyHostToDevice, st) != cudaSuccess)
-            rc = fail(CLDRD_ECUDA, "H2D copy failed");
-        cudaEventRecord(ev[b], st);
+        if (fd >= 0) close(fd);
+        if (st) cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        if (st) cudaStreamDestroy(st);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < readers; ++t) th.emplace_back(reader, t);
+        reader(0);
+        for (auto& x : th) x.join();
     }
-    if (fd >= 0) close(fd);
-    cudaStreamSynchronize(st);
-    for (int i = 0; i < 2; ++i) {
-        cudaFreeHost(pin[i]);
-        cudaEventDestroy(ev[i]);
-    }
-    cudaStreamDestroy(st);
-    if (rc) return rc;
+    for (int t = 0; t < readers; ++t)
+        if (rcs[size_t(t)]) return fail(rcs[size_t(t)], "shard_load_file: %s", errs[size_t(t)].c_str());
     if (info.has_ids) {
         std::vector<int64_t> ids(size_t(s->nrows));
         if ((rc = cldrd_index_read_ids(path, s->row0, s->nrows, ids.data()))) return rc;
@@ -1040,17 +1140,20 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
     if (lp && s->nrows) CU_TRY(cudaMalloc(&s->xlp, size_t(s->nrows) * s->d * 2));
     unsigned int* d_max = nullptr;
     CU_TRY(cudaMalloc(&d_max, 2 * sizeof(unsigned int)));
-    CU_TRY(cudaMemsetAsync(d_max, 0, 2 * sizeof(unsigned int), st));
-    if (s->nrows) {
-        const int threads = 256;
-        const int blocks = int(std::min<int64_t>((s->nrows * 32 + threads - 1) / threads, int64_t(s->num_sms) * 16));
-        index_prep_kernel<<<blocks, threads, 0, st>>>(s->xb, s->nrows, s->d, lp, s->xlp, d_max, d_max + 1);
-        CU_TRY(cudaGetLastError());
-    }
     unsigned int h_max[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_max);
+    {
+        cudaError_t e = cudaMemsetAsync(d_max, 0, 2 * sizeof(unsigned int), st);
+        if (e == cudaSuccess && s->nrows) {
+            const int threads = 256;
+            const int blocks = int(std::min<int64_t>((s->nrows * 32 + threads - 1) / threads, int64_t(s->num_sms) * 16));
+            index_prep_kernel<<<blocks, threads, 0, st>>>(s->xb, s->nrows, s->d, lp, s->xlp, d_max, d_max + 1);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_max);
+        if (e != cudaSuccess) return fail(CLDRD_ECUDA, "shard_finalize: index preparation pass failed: %s", cudaGetErrorString(e));
+    }
     float n2, mx;
     memcpy(&n2, &h_max[0], 4);
     memcpy(&mx, &h_max[1], 4);
@@ -1084,6 +1187,7 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
         CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<2, TC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
         CU_TRY(cudaFuncSetAttribute(scan_tc2_kernel<2, TC_MAXES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC2_SMEM_BYTES)));
     }
+    preload_kernels(s->device);
     int rc = ensure_workspace(s);
     if (rc) return rc;
     CU_TRY(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(select_smem(s))));
@@ -1107,7 +1211,7 @@ int64_t cldrd_shard_scan_bytes(const cldrd_shard* s) {
 static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, int32_t translate_ids,
                          int seed_mode, const float* seed_dev, float* out_scores_dev, int64_t* out_ids_dev,
                          float* eps_out_dev, void* cuda_stream) {
-    if (!s || nq < 0 || (nq && (!q_dev || (s->sc.world == 0 && (!out_scores_dev || !out_ids_dev)))))
+    if (!s || nq < 0 || (nq && (!q_dev || !out_scores_dev || !out_ids_dev)))
         return fail(CLDRD_EINVAL, "search: NULL argument");
     if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "search: k=%d outside [1,%d]", k, CLDRD_MAX_K);
     if (!s->finalized) return fail(CLDRD_ESTATE, "search: shard not finalized");
@@ -1122,12 +1226,10 @@ static int search_common(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t
     s->scan_launches = 0;
     s->ev_rows.clear();
     s->ev_ms.clear();
-    s->pend.active = false;   // a plain search abandons a two-phase batch that was never finished
     if (seed_mode == 1 && (s->nrows < kSeedMinRows || s->no_seed)) seed_mode = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += kQueryBatch) {
         const int nb = int(std::min<int64_t>(kQueryBatch, nq - q0));
         CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
-        s->sc.q0 = q0;
         int rc = search_batch(s, q_dev + size_t(q0) * s->d, nb, k, translate_ids != 0, seed_mode,
                               seed_dev ? seed_dev + q0 : nullptr, out_scores_dev ? out_scores_dev + size_t(q0) * k : nullptr,
                               out_ids_dev ? out_ids_dev + size_t(q0) * k : nullptr, eps_out_dev ? eps_out_dev + q0 : nullptr,
@@ -1169,28 +1271,6 @@ int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int3
                          eps_out_dev, cuda_stream);
 }
 
-int cldrd_search_dev_scatter(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, const float* seed_dev,
-                             int32_t world, int32_t rank, int64_t slice, float* const* peer_scores,
-                             int64_t* const* peer_rows, float* eps_out_dev, void* cuda_stream) {
-    if (!s || !peer_scores || !peer_rows) return fail(CLDRD_EINVAL, "search_scatter: NULL argument");
-    if (world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || slice < 1 || nq > slice * world)
-        return fail(CLDRD_EINVAL, "search_scatter: world=%d rank=%d slice=%lld do not cover nq=%lld", world, rank,
-                    (long long)slice, (long long)nq);
-    for (int i = 0; i < world; ++i)
-        if (!peer_scores[i] || !peer_rows[i]) return fail(CLDRD_EINVAL, "search_scatter: NULL buffer of rank %d", i);
-    s->sc.world = world;
-    s->sc.rank = rank;
-    s->sc.slice = slice;
-    for (int i = 0; i < world; ++i) {
-        s->sc.scores[i] = peer_scores[i];
-        s->sc.rows[i] = peer_rows[i];
-    }
-    // the base pointers below are never dereferenced in scatter mode (only offset)
-    int rc = search_common(s, q_dev, nq, k, 0, seed_dev ? 2 : 0, seed_dev, nullptr, nullptr, eps_out_dev, cuda_stream);
-    s->sc.world = 0;
-    return rc;
-}
-
 // cudaMalloc may carve a small request out of a larger driver allocation; the IPC handle then names
 // the whole allocation and the peer's mapping starts at ITS base.  The handle we hand out therefore
 // carries the offset of our pointer inside that allocation (bytes 64..71).
@@ -1210,144 +1290,6 @@ static std::mutex g_peer_mu;
 static std::map<void*, void*> g_peer_base;   // pointer handed out by cldrd_peer_open -> mapping base
 
 static_assert(kQueryBatch == CLDRD_QUERY_BATCH, "header and engine disagree on the query batch");
-
-int cldrd_levels_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq, float* levels_out_dev,
-                              void* cuda_stream) {
-    if (!topj_dev || !levels_out_dev || parts < 1 || parts > CLDRD_MAX_PEERS || nq < 1)
-        return fail(CLDRD_EINVAL, "levels_from_samples: bad argument");
-    DeviceGuard g(device);
-    levels_from_samples_kernel<<<unsigned(nq), 128, size_t(parts) * CLDRD_SEED_J * sizeof(float),
-                                 static_cast<cudaStream_t>(cuda_stream)>>>(topj_dev, parts, int(nq), CLDRD_SEED_J,
-                                                                           levels_out_dev);
-    CU_TRY(cudaGetLastError());
-    return CLDRD_OK;
-}
-
-int cldrd_scatter_begin(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k, const float* levels_dev,
-                        int32_t* counts_out_dev, float* eps_out_dev, void* cuda_stream) {
-    if (!s || !q_dev || !counts_out_dev || nq < 1 || nq > kQueryBatch)
-        return fail(CLDRD_EINVAL, "scatter_begin: bad argument (1 <= nq <= %d)", kQueryBatch);
-    if (k < 1 || k > CLDRD_MAX_K) return fail(CLDRD_EINVAL, "scatter_begin: k=%d outside [1,%d]", k, CLDRD_MAX_K);
-    if (!s->finalized) return fail(CLDRD_ESTATE, "scatter_begin: shard not finalized");
-    if (s->pend.active) return fail(CLDRD_ESTATE, "scatter_begin: the previous batch was not finished");
-    if (reinterpret_cast<uintptr_t>(q_dev) % 16 && is_tc(s->scan_eff))
-        return fail(CLDRD_EINVAL, "search: query buffer must be 16-byte aligned");
-    DeviceGuard g(s->device);
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    s->ev_used = 0;
-    s->scan_ms = 0.0;
-    s->scan_launches = 0;
-    s->ev_rows.clear();
-    s->ev_ms.clear();
-    CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
-    BatchCtx c{};
-    c.s = s;
-    c.st = st;
-    c.q = q_dev;
-    c.nq = int(nq);
-    c.k = k;
-    int rc = launch_prep(c);
-    if (rc) return rc;
-    const bool seeded = levels_dev != nullptr;
-    if (seeded) {
-        const SamplePlan sp = sample_plan(s, k);
-        const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
-        c.seed_rank = double(CLDRD_SEED_J) / frac;
-        // the seed is the last level: gather column J-1 into the workspace
-        CU_TRY(cudaMemcpy2DAsync(s->w_seed_in, sizeof(float), levels_dev + (CLDRD_SEED_J - 1), CLDRD_SEED_J * sizeof(float),
-                                 sizeof(float), size_t(nq), cudaMemcpyDeviceToDevice, st));
-        if ((rc = apply_seed(c, s->w_seed_in))) return rc;
-    }
-    if ((rc = run_chunks(c, seeded ? PASS_SEEDED : PASS_PROGRESSIVE))) return rc;
-    if (seeded) {
-        count_levels_kernel<<<unsigned(nq), 256, 0, st>>>(s->w_list, s->w_list_len, s->ws_keep_cap, s->w_fail, levels_dev,
-                                                          CLDRD_SEED_J, counts_out_dev);
-        CU_TRY(cudaGetLastError());
-        c.launches++;
-    } else {
-        CU_TRY(cudaMemsetAsync(counts_out_dev, 0, size_t(nq) * CLDRD_SEED_J * sizeof(int32_t), st));
-    }
-    if (eps_out_dev)
-        CU_TRY(cudaMemcpyAsync(eps_out_dev, s->w_band, size_t(nq) * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    s->pend.active = true;
-    s->pend.q = q_dev;
-    s->pend.nq = int(nq);
-    s->pend.k = k;
-    s->pend.seeded = seeded;
-    s->pend.launches = c.launches;
-    s->pend.chunks = c.chunks;
-    return CLDRD_OK;
-}
-
-int cldrd_scatter_finish(cldrd_shard* s, const int32_t* counts_dev, const float* levels_dev, int32_t world, int32_t rank,
-                         int64_t slice, int64_t q_base, float* const* peer_scores, int64_t* const* peer_rows,
-                         void* cuda_stream) {
-    if (!s || !peer_scores || !peer_rows) return fail(CLDRD_EINVAL, "scatter_finish: NULL argument");
-    if (!s->pend.active) return fail(CLDRD_ESTATE, "scatter_finish: no batch pending (call cldrd_scatter_begin)");
-    const int nq = s->pend.nq, k = s->pend.k;
-    s->pend.active = false;
-    if (world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || slice < 1 || q_base < 0 ||
-        q_base + nq > slice * world)
-        return fail(CLDRD_EINVAL, "scatter_finish: world=%d rank=%d slice=%lld do not cover queries [%lld, %lld)", world,
-                    rank, (long long)slice, (long long)q_base, (long long)(q_base + nq));
-    if (s->pend.seeded && (!counts_dev || !levels_dev)) return fail(CLDRD_EINVAL, "scatter_finish: NULL counts / levels");
-    for (int i = 0; i < world; ++i)
-        if (!peer_scores[i] || !peer_rows[i]) return fail(CLDRD_EINVAL, "scatter_finish: NULL buffer of rank %d", i);
-    DeviceGuard g(s->device);
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    BatchCtx c{};
-    c.s = s;
-    c.st = st;
-    c.q = s->pend.q;
-    c.nq = nq;
-    c.k = k;
-    const float* cut = nullptr;
-    if (s->pend.seeded) {
-        cut_from_counts_kernel<<<(nq + 255) / 256, 256, 0, st>>>(counts_dev, levels_dev, s->w_band, nq, CLDRD_SEED_J, k, s->w_cut);
-        CU_TRY(cudaGetLastError());
-        c.launches++;
-        cut = s->w_cut;
-    }
-    s->sc.world = world;
-    s->sc.rank = rank;
-    s->sc.slice = slice;
-    s->sc.q0 = q_base;
-    for (int i = 0; i < world; ++i) {
-        s->sc.scores[i] = peer_scores[i];
-        s->sc.rows[i] = peer_rows[i];
-    }
-    SearchTotals totals;
-    totals.launches = s->pend.launches;
-    totals.chunks = s->pend.chunks;
-    int rc = launch_rescore(c, nullptr, nullptr, false, nullptr, s->w_fail, st, 0, cut);
-    if (!rc) rc = read_stats(s, st);
-    totals.launches += c.launches;
-    if (!rc && s->h_stats[ST_RANGE_ERR])
-        rc = fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
-    unsigned long long first[ST_COUNT];
-    memcpy(first, s->h_stats, sizeof(first));
-    if (!rc && s->h_stats[ST_FAILED] != 0)
-        rc = run_fallbacks(s, s->pend.q, nq, k, false, nullptr, nullptr, st, s->pend.seeded, &totals);
-    s->sc.world = 0;
-    if (rc) return rc;
-    if (s->profile) {
-        for (size_t i = 0; i + 1 < s->ev_used; i += 2) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->scan_ms += ms;
-            s->ev_ms.push_back(ms);
-            s->scan_launches++;
-        }
-    }
-    s->stats[0] = totals.launches;
-    s->stats[1] = totals.chunks;
-    s->stats[2] = totals.fallback_queries;
-    s->stats[3] = int64_t(first[ST_RESCORED]);
-    s->stats[4] = int64_t(first[ST_SURVIVORS]);
-    s->stats[5] = int64_t(first[ST_MAX_LIST]);
-    s->stats[6] = int64_t(first[ST_TILES]);
-    s->stats[7] = int64_t(first[ST_EXACT_COMPACT]);
-    return CLDRD_OK;
-}
 
 int cldrd_peer_alloc(int device, int64_t nbytes, void** out_ptr, void* out_handle) {
     if (!out_ptr || !out_handle || nbytes < 1) return fail(CLDRD_EINVAL, "peer_alloc: bad argument");
@@ -1430,6 +1372,387 @@ int cldrd_peer_copy(int device, void* dst, const void* src, int64_t nbytes, void
     if (nbytes == 0) return CLDRD_OK;
     DeviceGuard g(device);
     CU_TRY(cudaMemcpyAsync(dst, src, size_t(nbytes), cudaMemcpyDefault, static_cast<cudaStream_t>(cuda_stream)));
+    return CLDRD_OK;
+}
+
+// ---- node-wide sharded search (include/cldrd.h "Sharded search on one node") ----------------------------------
+
+}  // extern "C"
+
+struct cldrd_node {
+    int device = 0, world = 1, rank = 0, cap_k = 0;
+    NodeLayout lay;
+    char* block = nullptr;                         // own exchange block
+    unsigned char handle[CLDRD_PEER_HANDLE_BYTES];
+    char* peer[CLDRD_MAX_PEERS];                   // every rank's block as this process sees it (own included)
+    bool opened[CLDRD_MAX_PEERS];                  // mapped by cldrd_peer_open: closed again by cldrd_node_detach
+    uint32_t epoch = 0;                            // barriers enqueued so far (the same sequence on every rank)
+    unsigned long long timeout_ns = 20000000000ull;
+    static constexpr int kRing = 4;                // batches in flight
+    BatchStatus* h_status = nullptr;               // page-locked [kRing], written by node_tail_kernel
+    BatchStatus* d_status = nullptr;               // the same memory as the device addresses it
+    cudaEvent_t done[kRing];
+    cudaEvent_t phase[kRing][6];
+    struct Slot {
+        int nq = 0, k = 0;
+        bool seeded = false;
+        int64_t launches = 0, chunks = 0, fallback_queries = 0;
+        size_t ev_lo = 0, ev_hi = 0;
+    } slot[kRing];
+    int64_t seq_begin = 0, seq_end = 0;
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int node_barrier(cldrd_shard* s, cldrd_node* n, cudaStream_t st) {
+    BarrierParams b{};
+    for (int p = 0; p < n->world; ++p) b.peer_flags[p] = reinterpret_cast<uint32_t*>(n->peer[p] + n->lay.flags);
+    b.my_flags = reinterpret_cast<const uint32_t*>(n->block + n->lay.flags);
+    b.world = n->world;
+    b.rank = n->rank;
+    b.epoch = ++n->epoch;
+    b.timeout_ns = n->timeout_ns;
+    b.err = s->w_stats + ST_KERNEL_ERR;
+    node_barrier_kernel<<<1, 32, 0, st>>>(b);
+    CU_TRY(cudaGetLastError());
+    return CLDRD_OK;
+}
+
+PeerPtrs node_ptrs(const cldrd_node* n, size_t off) {
+    PeerPtrs pp{};
+    for (int p = 0; p < n->world; ++p) pp.p[p] = n->peer[p] + off;
+    return pp;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k) {
+    if (world < 1 || world > CLDRD_MAX_PEERS || max_k < 1 || max_k > CLDRD_MAX_K) return 0;
+    return int64_t(node_layout(world, max_k).total);
+}
+
+int cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k) {
+    if (!out || world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || max_k < 1 || max_k > CLDRD_MAX_K)
+        return fail(CLDRD_EINVAL, "node_create: bad argument (world=%d rank=%d max_k=%d)", world, rank, max_k);
+    DeviceGuard g(device);
+    preload_kernels(device);
+    auto* n = new cldrd_node();
+    n->device = device;
+    n->world = world;
+    n->rank = rank;
+    n->cap_k = max_k;
+    n->lay = node_layout(world, max_k);
+    for (int p = 0; p < CLDRD_MAX_PEERS; ++p) {
+        n->peer[p] = nullptr;
+        n->opened[p] = false;
+    }
+    if (const char* e = getenv("CLDRD_BARRIER_TIMEOUT_MS")) n->timeout_ns = 1000000ull * (unsigned long long)std::max(1, atoi(e));
+    {   // the merge kernel's shared memory is sized once, for the largest k this node serves (no attribute changes
+        // between the launches of a batch)
+        int k_pad = 2;
+        while (k_pad < max_k) k_pad <<= 1;
+        const size_t smem = std::min<size_t>((size_t(world) * max_k + size_t(k_pad)) * 8, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            delete n;
+            return fail(CLDRD_ECUDA, "node_create: %s", cudaGetErrorString(e));
+        }
+    }
+    void* blk = nullptr;
+    int rc = cldrd_peer_alloc(device, int64_t(n->lay.total), &blk, n->handle);
+    if (rc) {
+        delete n;
+        return rc;
+    }
+    n->block = static_cast<char*>(blk);
+    n->peer[rank] = n->block;
+    // flags 0 = no barrier passed yet, keys 0 = padding
+    cudaError_t e = cudaMemset(n->block, 0, n->lay.total);
+    if (e == cudaSuccess) e = cudaHostAlloc(&n->h_status, sizeof(BatchStatus) * cldrd_node::kRing, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&n->d_status), n->h_status, 0);
+    for (int i = 0; i < cldrd_node::kRing && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&n->done[i], cudaEventDisableTiming);
+        for (int j = 0; j < 6 && e == cudaSuccess; ++j) e = cudaEventCreate(&n->phase[i][j]);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(n->block);
+        if (n->h_status) cudaFreeHost(n->h_status);
+        delete n;   // (events of a half-built ring are reclaimed with the context)
+        return fail(CLDRD_ECUDA, "node_create: %s", cudaGetErrorString(e));
+    }
+    *out = n;
+    return CLDRD_OK;
+}
+
+int cldrd_node_handle(const cldrd_node* n, void* out_handle) {
+    if (!n || !out_handle) return fail(CLDRD_EINVAL, "node_handle: NULL");
+    memcpy(out_handle, n->handle, CLDRD_PEER_HANDLE_BYTES);
+    return CLDRD_OK;
+}
+
+void* cldrd_node_block(const cldrd_node* n) { return n ? n->block : nullptr; }
+
+int cldrd_node_attach(cldrd_node* n, int32_t peer_rank, const void* handle, void* ptr, int32_t peer_device) {
+    if (!n || peer_rank < 0 || peer_rank >= n->world || peer_rank == n->rank || (!handle) == (!ptr))
+        return fail(CLDRD_EINVAL, "node_attach: bad argument (peer %d; exactly one of handle / pointer)", peer_rank);
+    if (n->peer[peer_rank]) return fail(CLDRD_ESTATE, "node_attach: rank %d is attached already", peer_rank);
+    DeviceGuard g(n->device);
+    if (handle) {
+        void* m = nullptr;
+        int rc = cldrd_peer_open(n->device, handle, &m);
+        if (rc) return rc;
+        n->peer[peer_rank] = static_cast<char*>(m);
+        n->opened[peer_rank] = true;
+        return CLDRD_OK;
+    }
+    if (peer_device >= 0 && peer_device != n->device) {   // same process, another GPU: direct peer access
+        int can = 0;
+        CU_TRY(cudaDeviceCanAccessPeer(&can, n->device, peer_device));
+        if (!can) return fail(CLDRD_ECUDA, "node_attach: device %d cannot access device %d", n->device, peer_device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+            return fail(CLDRD_ECUDA, "node_attach: cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+    }
+    n->peer[peer_rank] = static_cast<char*>(ptr);
+    return CLDRD_OK;
+}
+
+int cldrd_node_detach(cldrd_node* n) {
+    if (!n) return CLDRD_OK;
+    DeviceGuard g(n->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < n->world; ++p) {
+        if (n->opened[p]) cldrd_peer_close(n->device, n->peer[p]);
+        if (p != n->rank) n->peer[p] = nullptr;
+        n->opened[p] = false;
+    }
+    return CLDRD_OK;
+}
+
+void cldrd_node_destroy(cldrd_node* n) {
+    if (!n) return;
+    cldrd_node_detach(n);
+    DeviceGuard g(n->device);
+    for (int i = 0; i < cldrd_node::kRing; ++i) {
+        cudaEventDestroy(n->done[i]);
+        for (int j = 0; j < 6; ++j) cudaEventDestroy(n->phase[i][j]);
+    }
+    if (n->h_status) cudaFreeHost(n->h_status);
+    cudaFree(n->block);
+    delete n;
+}
+
+int cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** scores, void** ids) {
+    if (!n || owner_rank < 0 || owner_rank >= n->world || !n->peer[owner_rank] || !scores || !ids)
+        return fail(CLDRD_EINVAL, "node_result_ptrs: bad argument or rank %d not attached", owner_rank);
+    *scores = n->peer[owner_rank] + n->lay.res_d;
+    *ids = n->peer[owner_rank] + n->lay.res_i;
+    return CLDRD_OK;
+}
+
+int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
+                            float* out_scores, int64_t* out_ids, const int32_t* out_rows_dev, const int64_t* id_map_dev,
+                            void* cuda_stream) {
+    if (!s || !n || !q_dev || !out_scores || !out_ids || nq < 1 || nq > kQueryBatch)
+        return fail(CLDRD_EINVAL, "node_search_begin: bad argument (1 <= nq <= %d)", kQueryBatch);
+    if (k < 1 || k > n->cap_k) return fail(CLDRD_EINVAL, "node_search_begin: k=%d outside [1,%d] of this node", k, n->cap_k);
+    if (!s->finalized) return fail(CLDRD_ESTATE, "node_search_begin: shard not finalized");
+    if (s->device != n->device) return fail(CLDRD_EINVAL, "node_search_begin: shard and node live on different devices");
+    for (int p = 0; p < n->world; ++p)
+        if (!n->peer[p]) return fail(CLDRD_ESTATE, "node_search_begin: rank %d is not attached", p);
+    if (n->seq_begin - n->seq_end >= cldrd_node::kRing)
+        return fail(CLDRD_ESTATE, "node_search_begin: %d batches in flight (call cldrd_node_search_end)", cldrd_node::kRing);
+    if (reinterpret_cast<uintptr_t>(q_dev) % 16 && is_tc(s->scan_eff))
+        return fail(CLDRD_EINVAL, "search: query buffer must be 16-byte aligned");
+    int k_pad = 2;
+    while (k_pad < k) k_pad <<= 1;
+    const size_t merge_smem = (size_t(n->world) * k + size_t(k_pad)) * 8;
+    if (merge_smem > 200 * 1024) return fail(CLDRD_EINVAL, "node_search_begin: world*k=%d too large for the merge", n->world * k);
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int slot = int(n->seq_begin % cldrd_node::kRing);
+    cldrd_node::Slot& sl = n->slot[slot];
+    if (n->seq_begin == n->seq_end) {   // nothing in flight: the scan-timing events start over
+        s->ev_used = 0;
+        s->ev_rows.clear();
+    }
+    sl = cldrd_node::Slot();
+    sl.nq = int(nq);
+    sl.k = k;
+    sl.seeded = seeded != 0 && !s->no_seed;
+    sl.ev_lo = s->ev_used;
+    const bool sd = sl.seeded;
+    const int world = n->world, rank = n->rank;
+    const size_t plane = size_t(kQueryBatch) * CLDRD_SEED_J;   // elements per plane of the sample / count buffers
+    CU_TRY(cudaMemsetAsync(s->w_stats, 0, ST_COUNT * sizeof(unsigned long long), st));
+    CU_TRY(cudaEventRecord(n->phase[slot][0], st));
+    BatchCtx c{};
+    c.s = s;
+    c.st = st;
+    c.q = q_dev;
+    c.nq = int(nq);
+    c.k = k;
+    int rc = launch_prep(c);
+    if (rc) return rc;
+    // nobody raises a query of this batch before the first barrier below (seeded) / at all (unseeded)
+    CU_TRY(cudaMemsetAsync(n->block + n->lay.qfail, 0, size_t(nq) * sizeof(int), st));
+    int64_t extra = 0;
+    SearchTotals totals;
+    if (sd) {
+        // 1. sample scores -> plane [rank] of every rank's sample buffer; barrier; levels + seed from the union
+        const SamplePlan sp = sample_plan(s, k);
+        const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
+        c.seed_rank = double(CLDRD_SEED_J) / frac;
+        if ((rc = run_sample(c, node_ptrs(n, n->lay.topj), world, size_t(rank) * plane))) return rc;
+        if ((rc = node_barrier(s, n, st))) return rc;
+        levels_seed_kernel<<<unsigned(nq), 128, size_t(world) * CLDRD_SEED_J * sizeof(float), st>>>(
+            reinterpret_cast<const float*>(n->block + n->lay.topj), plane, world, CLDRD_SEED_J, s->tune_seed_bias, s->w_levels,
+            s->w_seed, s->w_thr, s->w_list_len);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(n->phase[slot][1], st));
+        // 2. fused scan + filter with that seed, select; candidates above every level -> plane [rank] everywhere
+        if ((rc = run_chunks(c, PASS_SEEDED))) return rc;
+        CU_TRY(cudaEventRecord(n->phase[slot][2], st));
+        count_levels_peers_kernel<<<unsigned(nq), 256, 0, st>>>(s->w_list, s->w_list_len, s->ws_keep_cap, s->w_fail, s->w_levels,
+                                                                CLDRD_SEED_J, node_ptrs(n, n->lay.counts), world,
+                                                                size_t(rank) * plane);
+        CU_TRY(cudaGetLastError());
+        if ((rc = node_barrier(s, n, st))) return rc;
+        extra += 4;
+    } else {
+        CU_TRY(cudaEventRecord(n->phase[slot][1], st));
+        if ((rc = run_chunks(c, PASS_PROGRESSIVE))) return rc;   // (host-synchronous: sizes its chunks from the first piece)
+        CU_TRY(cudaEventRecord(n->phase[slot][2], st));
+    }
+    // 3. exact re-score of what can still reach the global top-k; every list goes to the rank that merges the query
+    const int64_t slice = (nq + world - 1) / world;
+    s->sc.world = world;
+    s->sc.rank = rank;
+    s->sc.slice = slice;
+    s->sc.key_stride = n->cap_k;
+    s->sc.raise_fail = sd;
+    s->sc.keys = node_ptrs(n, n->lay.xkeys);
+    s->sc.qfail = node_ptrs(n, n->lay.qfail);
+    CountedCut cc;
+    cc.planes = reinterpret_cast<const int*>(n->block + n->lay.counts);
+    cc.stride = plane;
+    cc.parts = world;
+    cc.levels = s->w_levels;
+    rc = launch_rescore(c, nullptr, nullptr, false, nullptr, s->w_fail, st, 0, sd ? &cc : nullptr);
+    if (!rc && !sd) {
+        // unseeded batches are host-driven anyway: a query whose survivors overflowed is redone densely right here
+        rc = read_stats(s, st);
+        if (!rc && s->h_stats[ST_RANGE_ERR])
+            rc = fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
+        if (!rc && s->h_stats[ST_FAILED] != 0) {
+            const unsigned long long keep_rescored = s->h_stats[ST_RESCORED], keep_surv = s->h_stats[ST_SURVIVORS];
+            rc = run_fallbacks(s, q_dev, int(nq), k, false, nullptr, nullptr, st, false, &totals);
+            (void)keep_rescored;
+            (void)keep_surv;
+        }
+    }
+    s->sc.world = 0;
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(n->phase[slot][3], st));
+    if ((rc = node_barrier(s, n, st))) return rc;
+    // 4. merge + seed check + ids of this rank's slice, stored where the caller wants the result
+    const int64_t lo = int64_t(rank) * slice;
+    const int64_t n_mine = std::max<int64_t>(0, std::min<int64_t>(slice, nq - lo));
+    if (n_mine > 0) {
+        MergeKeysParams m{};
+        m.xkeys = reinterpret_cast<const uint64_t*>(n->block + n->lay.xkeys);
+        m.parts = world;
+        m.slice = slice;
+        m.key_stride = n->cap_k;
+        m.k = k;
+        m.k_pad = k_pad;
+        m.q_lo = lo;
+        m.seed = sd ? s->w_seed : nullptr;
+        m.band = s->w_band;
+        m.id_map = reinterpret_cast<const long long*>(id_map_dev);
+        m.out_scores = out_scores;
+        m.out_ids = reinterpret_cast<long long*>(out_ids);
+        m.out_rows = out_rows_dev;
+        m.qfail = node_ptrs(n, n->lay.qfail);
+        m.world = world;
+        merge_keys_kernel<<<unsigned(n_mine), 512, merge_smem, st>>>(m);
+        CU_TRY(cudaGetLastError());
+        extra += 1;
+    }
+    CU_TRY(cudaEventRecord(n->phase[slot][4], st));
+    if ((rc = node_barrier(s, n, st))) return rc;
+    // 5. every slice has landed and every raised query is known everywhere: status for the host
+    node_tail_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const int*>(n->block + n->lay.qfail), int(nq), s->w_stats,
+                                         n->d_status + slot);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(n->phase[slot][5], st));
+    CU_TRY(cudaEventRecord(n->done[slot], st));
+    extra += 3;
+    sl.launches = c.launches + totals.launches + extra;
+    sl.chunks = c.chunks + totals.chunks;
+    sl.fallback_queries = totals.fallback_queries;
+    sl.ev_hi = s->ev_used;
+    n->seq_begin++;
+    return CLDRD_OK;
+}
+
+int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int32_t* fail_idx_out, int32_t cap) {
+    if (!s || !n) return fail(CLDRD_EINVAL, "node_search_end: NULL");
+    if (n->seq_end == n->seq_begin) return fail(CLDRD_ESTATE, "node_search_end: no batch in flight");
+    DeviceGuard g(n->device);
+    const int slot = int(n->seq_end % cldrd_node::kRing);
+    const cldrd_node::Slot& sl = n->slot[slot];
+    n->seq_end++;
+    CU_TRY(cudaEventSynchronize(n->done[slot]));
+    const BatchStatus& hs = n->h_status[slot];
+    if (hs.stats[ST_KERNEL_ERR] >= kErrBarrierTimeout)
+        return fail(CLDRD_ECUDA, "node search: rank %llu did not reach a barrier within %llu ms (peer process gone, or the "
+                    "ranks issued different call sequences)", hs.stats[ST_KERNEL_ERR] - kErrBarrierTimeout, n->timeout_ns / 1000000ull);
+    if (hs.stats[ST_KERNEL_ERR]) return fail(CLDRD_ECUDA, "scan kernel watchdog fired (code %llu)", hs.stats[ST_KERNEL_ERR]);
+    if (hs.stats[ST_RANGE_ERR]) return fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, n->phase[slot][i], n->phase[slot][i + 1]) != cudaSuccess) cudaGetLastError();
+        n->phase_ms[i] = ms;
+    }
+    s->scan_ms = 0.0;
+    s->scan_launches = 0;
+    s->ev_ms.clear();
+    if (s->profile) {
+        for (size_t i = sl.ev_lo; i + 1 < sl.ev_hi; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->scan_ms += ms;
+            else cudaGetLastError();
+            s->ev_ms.push_back(ms);
+            s->scan_launches++;
+        }
+    }
+    const int nfail = hs.nfail;
+    s->stats[0] = sl.launches;
+    s->stats[1] = sl.chunks;
+    s->stats[2] = sl.fallback_queries + (sl.seeded ? nfail : 0);
+    s->stats[3] = int64_t(hs.stats[ST_RESCORED]);
+    s->stats[4] = int64_t(hs.stats[ST_SURVIVORS]);
+    s->stats[5] = int64_t(hs.stats[ST_MAX_LIST]);
+    s->stats[6] = int64_t(hs.stats[ST_TILES]);
+    s->stats[7] = int64_t(hs.stats[ST_EXACT_COMPACT]);
+    if (nfail_out) *nfail_out = nfail;
+    if (fail_idx_out)
+        for (int i = 0; i < nfail && i < cap; ++i) fail_idx_out[i] = hs.idx[i];
+    return CLDRD_OK;
+}
+
+int cldrd_node_phase_ms(const cldrd_node* n, double out[5]) {
+    if (!n || !out) return fail(CLDRD_EINVAL, "node_phase_ms: NULL");
+    for (int i = 0; i < 5; ++i) out[i] = n->phase_ms[i];
     return CLDRD_OK;
 }
 
@@ -1562,7 +1885,7 @@ int cldrd_host_alloc(void** out, int64_t nbytes) {
     if (!out || nbytes < 0) return fail(CLDRD_EINVAL, "host_alloc: bad argument");
     *out = nullptr;
     if (nbytes == 0) return CLDRD_OK;
-    cudaError_t e = cudaHostAlloc(out, size_t(nbytes), cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc(out, size_t(nbytes), cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? CLDRD_ENOMEM : CLDRD_ECUDA, "cudaHostAlloc(%lld) failed: %s",
@@ -1577,10 +1900,22 @@ void cldrd_host_free(void* p) {
 
 int cldrd_host_register(void* p, int64_t nbytes) {
     if (!p || nbytes < 1) return fail(CLDRD_EINVAL, "host_register: bad argument");
-    cudaError_t e = cudaHostRegister(p, size_t(nbytes), cudaHostRegisterPortable);
+    cudaError_t e = cudaHostRegister(p, size_t(nbytes), cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(CLDRD_ECUDA, "cudaHostRegister(%lld) failed: %s", (long long)nbytes, cudaGetErrorString(e));
+    }
+    return CLDRD_OK;
+}
+
+int cldrd_host_device_ptr(int device, void* host_ptr, void** out_dev_ptr) {
+    if (!host_ptr || !out_dev_ptr) return fail(CLDRD_EINVAL, "host_device_ptr: NULL");
+    DeviceGuard g(device);
+    *out_dev_ptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(out_dev_ptr, host_ptr, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CLDRD_ECUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
     }
     return CLDRD_OK;
 }

@@ -17,6 +17,10 @@
 
 namespace cldrd {
 
+struct PeerPtrs {
+    void* p[CLDRD_MAX_PEERS];   // the same buffer in every rank's exchange block, as mapped into this process
+};
+
 // ------------------------------------------------------------------------------------------
 // block-wide radix select of the k-th largest value among keys[0..n) (shared memory)
 // BITS = 32: on the score half only.  BITS = 64: on the full key (unique -> exactly k kept).
@@ -287,14 +291,27 @@ struct RescoreParams {
     // optional [nq]: list entries whose SCAN score is below cut[q] are dropped unscored (sharded search:
     // the shards agreed that such rows cannot be in the global top-k)
     const float* cut;
-    // scatter mode (sc_world > 0): output row r of this launch is query q_base + r of the search; it
-    // goes to plane [sc_rank], row Q % sc_slice of the buffers of rank Q / sc_slice (peer memory)
+    // ... or computed here (node-wide search): counts planes [cnt_parts][plane_stride] of int[j] per query that
+    // the shards stored into this rank's block; cut = T - 2*eps for the highest level T that at least k rows of the
+    // WHOLE index reach in scan score, -inf if no level does.  Why it is safe: k rows with scan score >= T have
+    // exact score >= T - eps, so the exact k-th best is >= T - eps, and a row of the top-k scans >= T - 2*eps.
+    const int* cnt_planes;
+    size_t cnt_plane_stride;
+    int cnt_parts;
+    const float* levels;  // [nq][lv_j], descending
+    int lv_j;
+    const float* band;    // [nq] 2*eps
+    // scatter mode (sc_world > 0): output row r of this launch is query q_base + r of the batch; its list goes
+    // to plane [sc_rank], row Q % sc_slice of the key buffer of rank Q / sc_slice (peer memory over NVLink):
+    // u64 keys (exact score, GLOBAL row), best first, 0 = padding
     int sc_world;
     int sc_rank;
     long long sc_slice;
     long long q_base;
-    float* sc_scores[CLDRD_MAX_PEERS];
-    int64_t* sc_rows[CLDRD_MAX_PEERS];
+    int sc_key_stride;
+    int sc_raise_fail;    // a query this shard could not finish is raised in every rank's qfail (seeded batches)
+    PeerPtrs sc_keys;
+    PeerPtrs sc_qfail;
 };
 
 // One CTA per query: exact fp32 score of every listed row, sort, emit the k best.
@@ -305,12 +322,22 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     float* q_s = reinterpret_cast<float*>(sm_raw + size_t(p.n_pad) * 8);
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    if (p.fail && p.fail[q]) return;
     int L = p.list_len[q];
-    if (L > p.n_pad) {   // only possible when launched with less shared memory than keep_cap needs
-        if (tid == 0 && p.fail_set) {
+    const bool failed = p.fail && p.fail[q];
+    if (failed || L > p.n_pad) {
+        // L > n_pad: only possible when launched with less shared memory than keep_cap needs
+        if (!failed && tid == 0 && p.fail_set) {
             p.fail_set[q] = 1;
             atomicAdd(&p.stats[ST_FAILED], 1ull);
+        }
+        if (p.sc_world > 0 && p.sc_raise_fail) {
+            // the merging rank gets an empty list, and every rank learns that the query has to be searched again
+            const long long Q = p.q_base + (long long)(p.out_index ? p.out_index[q] : q);
+            const int dest = int(Q / p.sc_slice);
+            uint64_t* ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
+                           (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
+            for (int i = tid; i < p.k; i += blockDim.x) ok[i] = 0;
+            if (tid < p.sc_world) static_cast<int*>(p.sc_qfail.p[tid])[Q] = 1;
         }
         return;
     }
@@ -319,11 +346,29 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     while (n_pad < L) n_pad <<= 1;
     for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
     __shared__ int s_kept;
-    if (tid == 0) s_kept = 0;
+    __shared__ uint32_t s_cut;
+    if (tid == 0) {
+        s_kept = 0;
+        s_cut = p.cut ? f2ord(p.cut[q]) : 0u;
+    }
+    if (p.cnt_planes && tid < 32) {   // lv_j <= 64 levels: lane b looks at levels b and b + 32
+        int c0 = 0, c1 = 0;
+        for (int part = 0; part < p.cnt_parts; ++part) {
+            const int* c = p.cnt_planes + size_t(part) * p.cnt_plane_stride + size_t(q) * p.lv_j;
+            if (tid < p.lv_j) c0 += c[tid];
+            if (tid + 32 < p.lv_j) c1 += c[tid + 32];
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, tid < p.lv_j && c0 >= p.k);
+        const unsigned m1 = __ballot_sync(0xffffffffu, tid + 32 < p.lv_j && c1 >= p.k);
+        if (tid == 0) {
+            const int b = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
+            s_cut = b >= 0 ? f2ord(p.levels[size_t(q) * p.lv_j + b] - p.band[q]) : 0u;
+        }
+    }
     __syncthreads();
     const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const uint32_t cut_ord = p.cut ? f2ord(p.cut[q]) : 0u;
+    const uint32_t cut_ord = s_cut;
     int kept = 0;
     for (int i = warp; i < L; i += nwarps) {
         const uint64_t cand = my_list[i];
@@ -342,18 +387,23 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     if (tid == 0) atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)L);
     block_bitonic_desc(keys, n_pad);
     const size_t orow = p.out_index ? size_t(p.out_index[q]) : size_t(q);
-    float* os;
-    int64_t* oi;
     if (p.sc_world > 0) {
         const long long Q = p.q_base + (long long)orow;
         const int dest = int(Q / p.sc_slice);
-        const size_t at = (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * p.k;
-        os = p.sc_scores[dest] + at;
-        oi = p.sc_rows[dest] + at;
-    } else {
-        os = p.out_scores + orow * p.k;
-        oi = p.out_ids + orow * p.k;
+        uint64_t* ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
+                       (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
+        for (int i = tid; i < p.k; i += blockDim.x) {
+            uint64_t key = 0;
+            if (i < L) {
+                key = keys[i];
+                key = (key & 0xFFFFFFFF00000000ull) | uint64_t(~(uint32_t(p.row0) + key_row(key)));
+            }
+            ok[i] = key;
+        }
+        return;
     }
+    float* os = p.out_scores + orow * p.k;
+    int64_t* oi = p.out_ids + orow * p.k;
     for (int i = tid; i < p.k; i += blockDim.x) {
         if (i < L) {
             uint64_t key = keys[i];
@@ -535,8 +585,10 @@ __global__ void index_prep_kernel(const float* xb, int64_t nrows, int d, int lp_
 // makes the seed more conservative).  One CTA per query: radix-select the j-th largest, then sort
 // the few values at or above it.  Output best first, -inf padded.   j <= 64.
 // dyn smem: keys[cols] u64 (orderable float in the high half)
+// The [nq][j] result is stored at element offset out_off of every buffer in outs (node-wide search: plane `rank` of
+// every rank's sample buffer, peer stores over NVLink; nouts = 1 for a local result).
 __global__ void __launch_bounds__(256) sample_topj_kernel(const float* vals, int ld, int cols, int j,
-                                                          float* out /*[nq][j]*/) {
+                                                          PeerPtrs outs, int nouts, size_t out_off) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     __shared__ uint32_t hist[256];
@@ -582,7 +634,10 @@ __global__ void __launch_bounds__(256) sample_topj_kernel(const float* vals, int
         }
     }
     __syncthreads();
-    for (int i = tid; i < j; i += blockDim.x) out[size_t(q) * j + i] = ord2f(uint32_t(top[i] >> 32));
+    for (int i = tid; i < j; i += blockDim.x) {
+        const float v = ord2f(uint32_t(top[i] >> 32));
+        for (int o = 0; o < nouts; ++o) (static_cast<float*>(outs.p[o]) + out_off)[size_t(q) * j + i] = v;
+    }
 }
 
 // seed[q] = j-th best of the parts*j sample scores gathered from all shards ([parts][nq][j]).
@@ -610,81 +665,6 @@ __global__ void seed_from_samples_kernel(const float* topj, int parts, int nq, i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) seed[q] = best;
-}
-
-// levels[q][0..j) = the j best of the parts*j sample scores gathered from all shards, best first
-// (levels[q][j-1] is the seed of seed_from_samples_kernel).  One CTA per query; dyn smem parts*j floats.
-__global__ void levels_from_samples_kernel(const float* topj, int parts, int nq, int j, float* levels) {
-    extern __shared__ float lv_s[];
-    const int q = blockIdx.x;
-    const int n = parts * j;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        const int part = c / j, i = c - part * j;
-        lv_s[c] = topj[(size_t(part) * nq + q) * j + i];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        const float v = lv_s[c];
-        int r = 0;
-        for (int t = 0; t < n; ++t) {
-            const float x = lv_s[t];
-            r += (x > v) || (x == v && t < c);
-        }
-        if (r < j) levels[size_t(q) * j + r] = v;
-    }
-}
-
-// counts[q][b] = how many entries of this shard's candidate list have a scan score >= levels[q][b]
-// (levels descending, j <= 64).  Failed queries (redone by the fallback) count nothing, which is safe:
-// the counts only have to be lower bounds.
-__global__ void count_levels_kernel(const uint64_t* list, const int* list_len, int keep_cap, const int* fail,
-                                    const float* levels, int j, int* counts) {
-    __shared__ int hist[64];
-    __shared__ float lv[64];
-    const int q = blockIdx.x;
-    if (threadIdx.x < j) {
-        hist[threadIdx.x] = 0;
-        lv[threadIdx.x] = levels[size_t(q) * j + threadIdx.x];
-    }
-    __syncthreads();
-    const int L = (fail && fail[q]) ? 0 : list_len[q];
-    const uint64_t* my = list + size_t(q) * keep_cap;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const float sc = ord2f(key_ord(my[i]));
-        int lo = 0, hi = j;            // smallest b with lv[b] <= sc
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (lv[mid] <= sc) hi = mid;
-            else lo = mid + 1;
-        }
-        if (lo < j) atomicAdd(&hist[lo], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < j; ++b) {
-            acc += hist[b];
-            counts[size_t(q) * j + b] = acc;
-        }
-    }
-}
-
-// cut[q] = T - 2*eps for the highest level T that at least k rows of the WHOLE index reach in scan score
-// (counts summed over the shards), -inf if no level does.  Why it is safe: k rows with scan score >= T
-// have exact score >= T - eps, so the exact k-th best is >= T - eps, and a row of the top-k has scan
-// score >= T - 2*eps.
-__global__ void cut_from_counts_kernel(const int* counts, const float* levels, const float* band, int nq, int j,
-                                       int k, float* cut) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    float c = -INFINITY;
-    for (int b = 0; b < j; ++b) {
-        if (counts[size_t(q) * j + b] >= k) {
-            c = levels[size_t(q) * j + b] - band[q];
-            break;
-        }
-    }
-    cut[q] = c;
 }
 
 // After the exact re-score: fail[q] = 1 unless the k-th returned score clears seed + eps.

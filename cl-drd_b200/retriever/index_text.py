@@ -54,7 +54,9 @@ def main(args):
     tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name_or_path)
     path = args.queries_path if args.is_query else args.passages_path
     dataset = SequenceDataset.create_from_seqs_file(path, tokenizer, args.max_length, is_query=args.is_query)
-    loader = DataLoader(dataset, batch_size=args.batch_size, shuffle=False, num_workers=0, collate_fn=dataset.collate_fn)
+    # the reference tokenises with 4 worker processes (retriever/index_text.py:84)
+    workers = int(os.environ.get("CLDRD_LOADER_WORKERS", "4"))
+    loader = DataLoader(dataset, batch_size=args.batch_size, shuffle=False, num_workers=workers, collate_fn=dataset.collate_fn)
     stem = (Path(args.resume).stem.split(".")[0] if args.resume else args.index_name) + ".index"
     index_path = os.path.join(args.index_dir, stem)
     n = len(dataset)
@@ -63,19 +65,50 @@ def main(args):
     check(lib().cldrd_index_writer_begin(C.byref(w), index_path.encode(), n, hidden, 1, 0))
     text_ids = []
     n_nan = 0
-    for batch in loader:
-        with torch.no_grad():
-            with torch.autocast(device_type=dev.type, dtype=torch.float16, enabled=dev.type == "cuda"):
-                seq = {k: v.to(dev) for k, v in batch["seq"].items()}
-                reps = model.query_embs(seq) if args.is_query else model.passage_embs(seq)
-        rows = np.ascontiguousarray(reps.float().cpu().numpy())
+    # Two page-locked slots: batch i's rows travel device -> host and are appended to the file while the encoder
+    # already works on batch i+1 (the reference blocks on `.cpu().numpy()` after every batch, retrieval_utils.py:47).
+    on_gpu = dev.type == "cuda"
+    slots = [torch.empty((args.batch_size, hidden), dtype=torch.float32, pin_memory=on_gpu) for _ in range(2)]
+    ready = [torch.cuda.Event() if on_gpu else None for _ in range(2)]
+    pending = []      # (slot, rows) copied but not yet written
+
+    def flush_one():
+        nonlocal n_nan
+        slot, m = pending.pop(0)
+        if on_gpu:
+            ready[slot].synchronize()
+        rows = slots[slot][:m].numpy()
         n_nan += int(np.isnan(rows).sum())
-        check(lib().cldrd_index_writer_append(w, ptr(rows), rows.shape[0]))
-        text_ids.extend(batch["id"])
-    print(f"# nan in embeddings: {n_nan}")
-    print("embs dtype: ", np.dtype(np.float32))
-    text_ids_arr = np.array(text_ids, dtype=np.int64)
-    check(lib().cldrd_index_writer_finish(w, ptr(text_ids_arr)))
+        check(lib().cldrd_index_writer_append(w, ptr(rows), m))
+
+    finished = False
+    try:
+        for i, batch in enumerate(loader):
+            with torch.no_grad():
+                with torch.autocast(device_type=dev.type, dtype=torch.float16, enabled=on_gpu):
+                    seq = {k: v.to(dev, non_blocking=True) for k, v in batch["seq"].items()}
+                    reps = model.query_embs(seq) if args.is_query else model.passage_embs(seq)
+            slot = i % 2
+            while len(pending) >= 2 or any(p[0] == slot for p in pending):
+                flush_one()
+            m = reps.shape[0]
+            slots[slot][:m].copy_(reps.float(), non_blocking=True)
+            if on_gpu:
+                ready[slot].record()
+            pending.append((slot, m))
+            text_ids.extend(batch["id"])
+            if len(pending) == 2:
+                flush_one()
+        while pending:
+            flush_one()
+        print(f"# nan in embeddings: {n_nan}")
+        print("embs dtype: ", np.dtype(np.float32))
+        text_ids_arr = np.array(text_ids, dtype=np.int64)
+        check(lib().cldrd_index_writer_finish(w, ptr(text_ids_arr)))
+        finished = True
+    finally:
+        if not finished:      # encoder or I/O error mid-way: release the writer (handle, fd); the file stays incomplete
+            lib().cldrd_index_writer_finish(w, None)
     meta = {"text_ids": text_ids_arr, "text_id_to_idx": {tid: idx for idx, tid in enumerate(text_ids)}}
     with open(os.path.join(args.index_dir, "meta.pkl"), "wb") as f:
         pickle.dump(meta, f)

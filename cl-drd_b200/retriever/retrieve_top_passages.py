@@ -2,9 +2,13 @@
 retriever/retrieve_top_passages.py (:28-109).  The search runs on the B200 kernels; the regroup and
 writer loops are one native call.
 
+The embeddings stay on the device between the encoder and the search (no per-batch `.cpu().numpy()`
+as in retriever/retrieval_utils.py:47).
+
 Launched under torchrun (`torchrun --nproc-per-node G retrieve_top_passages.py ...`) it is the one-process-per-GPU
-form: every rank loads only its row shard of the index file, encodes the queries, and takes part in the sharded
-search (cldrd.dist.ShardedSearcher.search_host); rank 0 writes the run file."""
+form: every rank loads only its row shard of the index file; rank 0 encodes the queries and broadcasts the
+embeddings (the sharded protocol needs bit-identical replicas); all ranks take part in the sharded search
+(cldrd.dist.ShardedSearcher.search); rank 0 writes the run file."""
 import argparse
 import os
 import sys
@@ -45,18 +49,14 @@ def check_paths(queries_path, output_path):
             assert tag in output_path
 
 
-def main(args, is_query_side=True, header="# unique query"):
+def _loader(dataset):
+    # the reference tokenises with 4 worker processes (retriever/retrieve_top_passages.py:81)
+    workers = int(os.environ.get("CLDRD_LOADER_WORKERS", "4"))
+    return DataLoader(dataset, batch_size=512, shuffle=False, num_workers=workers, collate_fn=dataset.collate_fn)
+
+
+def _encode(args, is_query_side):
     from transformers import AutoTokenizer
-    check_paths(args.queries_path, args.output_path)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-        torch.cuda.set_device(local_rank)
-        own_group = not dist.is_initialized()
-        if own_group:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     model = DualEncoder(args.model_name_or_path, share_weights=args.share_weights)
     print("************************* share weights = {} *************************".format(args.share_weights))
     if args.resume:
@@ -65,25 +65,45 @@ def main(args, is_query_side=True, header="# unique query"):
     model.cuda()
     tokenizer = AutoTokenizer.from_pretrained(args.tokenizer_name_or_path)
     dataset = SequenceDataset.create_from_seqs_file(args.queries_path, tokenizer, args.max_length, is_query=is_query_side)
-    loader = DataLoader(dataset, batch_size=512, shuffle=False, num_workers=0, collate_fn=dataset.collate_fn)
-    query_embs, query_ids = get_embeddings_from_scratch(model, loader, use_fp16=True, is_query=is_query_side,
-                                                        show_progress_bar=True)
+    return get_embeddings_from_scratch(model, _loader(dataset), use_fp16=True, is_query=is_query_side,
+                                       show_progress_bar=True, to_device=True)
+
+
+def main(args, is_query_side=True, header="# unique query"):
+    check_paths(args.queries_path, args.output_path)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     os.environ.setdefault("CLDRD_SCAN", args.precision)
     if world > 1:
-        import numpy as np
         import torch.distributed as dist
         from cldrd.dist import ShardedSearcher
-        searcher = ShardedSearcher.from_file(args.index_path, device=torch.cuda.current_device(), scan=args.precision)
-        nn_scores, nn_doc_ids = searcher.search_host(np.ascontiguousarray(query_embs, dtype=np.float32), args.top_k)
-        if rank == 0:
-            print(f"{header} = {len(set(query_ids))}")
-            avg = cldrd.write_run_file(args.output_path, query_ids, nn_doc_ids, nn_scores)
-            print(f"average ranks per query = {avg}")
-        dist.barrier()
-        searcher.shard.close()
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        own_group = not dist.is_initialized()
         if own_group:
-            dist.destroy_process_group()
+            dist.init_process_group("nccl", device_id=dev)
+        searcher = ShardedSearcher.from_file(args.index_path, device=local_rank, scan=args.precision)
+        try:
+            # one encoder run; every shard must see the same bits
+            query_embs, query_ids = _encode(args, is_query_side) if rank == 0 else (None, None)
+            shape = torch.tensor(list(query_embs.shape) if rank == 0 else [0, 0], dtype=torch.int64, device=dev)
+            dist.broadcast(shape, src=0)
+            if rank != 0:
+                query_embs = torch.empty(tuple(shape.tolist()), dtype=torch.float32, device=dev)
+            dist.broadcast(query_embs, src=0)
+            D, I = searcher.search(query_embs, args.top_k)
+            if rank == 0:
+                print(f"{header} = {len(set(query_ids))}")
+                avg = cldrd.write_run_file(args.output_path, query_ids, I.cpu().numpy(), D.cpu().numpy())
+                print(f"average ranks per query = {avg}")
+            dist.barrier()
+        finally:
+            searcher.close()
+            if own_group:
+                dist.destroy_process_group()
         return
+    query_embs, query_ids = _encode(args, is_query_side)
     index = cldrd.read_index(args.index_path)                      # headers only; rows stream file -> HBM
     devs = [int(x) for x in str(args.gpus).split(",")]
     index = convert_index_to_gpu(index, devs if len(devs) > 1 else devs[0], False)

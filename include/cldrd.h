@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLDRD_ABI_VERSION 1
+#define CLDRD_ABI_VERSION 2
 
 /* error codes */
 #define CLDRD_OK        0
@@ -155,45 +155,68 @@ int cldrd_search_dev_seeded(cldrd_shard* s, const float* q_dev, int64_t nq, int3
 int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k,
                       const float* seed_dev, const float* eps2_dev, int32_t* fail_dev,
                       void* cuda_stream);
-/* Step 3 fused with the exchange (one process per GPU on ONE node, NVLink / NVSwitch peer memory):
- * the same seeded search, but the re-score kernel stores each query's list straight into the
- * exchange buffer of the rank that will merge that query, instead of a local array that an NCCL
- * all-to-all would then move.  Query Q (0 <= Q < nq) belongs to rank Q / slice; in that rank's buffers
- * (peer_scores[dest], float32, and peer_rows[dest], int64 GLOBAL rows, both laid out
- * [world][slice][k]) this shard fills plane [rank], row Q % slice, all k columns (-FLT_MAX / -1
- * padded).  peer_scores / peer_rows are HOST arrays of `world` device pointers valid in this
- * process (cldrd_peer_open of the owners' handles; the own entry is the own allocation).  After a
- * barrier over the ranks, each rank merges its planes with cldrd_merge_planes(parts=world, w=k).
- * world <= CLDRD_MAX_PEERS.  seed_dev NULL = unseeded (retry of seed misses). */
+/* ---------------------------------------------------------------------------------------------
+ * Sharded search on one node: one shard per GPU, exchanges over NVLink / NVSwitch peer memory
+ * (what `index_cpu_to_gpu_multiple(..., shard=True)` + IndexShards' host-thread merge stand for in
+ * retriever/retrieval_utils.py:174-182).  One process per GPU (blocks mapped with CUDA IPC) or one
+ * process driving several GPUs (blocks addressed directly).
+ *
+ * Every rank owns an exchange block of cldrd_node_block_bytes(world, max_k) bytes with the same
+ * layout; the peers' kernels store into it.  A batch of at most CLDRD_QUERY_BATCH replicated queries
+ * is ONE asynchronous call per rank, cldrd_node_search_begin, which enqueues on the caller's stream:
+ *   1. sample scan; the CLDRD_SEED_J best sample scores per query go to plane [rank] of every rank's
+ *      sample buffer (peer stores by the kernel); barrier; every rank derives the same J levels per query
+ *      from the union, best first; the last level seeds the filter threshold (a scan score near rank 3.5 k
+ *      of the WHOLE index);
+ *   2. fused scan + filter + select over the shard; how many of its candidates scan at or above each
+ *      level goes to plane [rank] of every rank's count buffer; barrier;
+ *   3. re-score: T = the highest level that >= k rows of the whole index reach (summed counts);
+ *      candidates scanning below T - 2*eps are dropped unscored (k rows scanning >= T put the exact
+ *      k-th score above T - eps, so a top-k row scans above T - 2*eps); the rest are scored in fp32,
+ *      sorted and stored as u64 keys (score, GLOBAL row) straight into the key planes of the rank that
+ *      merges the query (query i of the batch belongs to rank i / ceil(nq / world)); barrier;
+ *   4. every rank merges its slice (same key order as the single-shard search: bit-identical result),
+ *      checks the seed (k-th merged score >= seed + eps), applies id_map and stores the rows through
+ *      out_scores / out_ids: any memory this GPU can address -- its own, the collecting rank's result
+ *      buffer (cldrd_node_result_ptrs) or page-locked host memory; barrier;
+ *   5. a status record (queries that have to be searched again: seed missed, survivor overflow) goes to
+ *      page-locked memory; cldrd_node_search_end waits for the batch and returns it.
+ * The barriers are flag kernels over the same peer memory; a rank that never arrives ends in CLDRD_ECUDA
+ * after CLDRD_BARRIER_TIMEOUT_MS (default 20 000), never in a hung GPU.  No host synchronisation and no
+ * NCCL call inside a seeded batch; up to 4 batches may be in flight per node (begin ... begin, end ... end),
+ * every rank issuing the same sequence of calls.  seeded = 0 (small shards, retry of raised queries) runs
+ * the progressive scheme instead of steps 1-2 and re-scores every candidate.
+ * out_rows_dev (optional, int32 [nq]): output row of batch query i (default i).  q_dev, out_* and
+ * out_rows_dev must stay valid until the batch has ended. */
 #define CLDRD_MAX_PEERS 16
-int cldrd_search_dev_scatter(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
-                             const float* seed_dev, int32_t world, int32_t rank, int64_t slice,
-                             float* const* peer_scores, int64_t* const* peer_rows,
-                             float* eps2_out_dev, void* cuda_stream);
-/* The same in two calls per batch of at most CLDRD_QUERY_BATCH queries, with one more exchange in
- * between, so that a shard re-scores only what can still reach the GLOBAL top-k (about k / world rows
- * per query instead of everything above the seed):
- *   cldrd_levels_from_samples: levels[q][0..J) = the J best sample scores of the all-gathered samples,
- *       best first (J = CLDRD_SEED_J; levels[q][J-1] is the seed of cldrd_seed_from_samples).
- *   cldrd_scatter_begin: scan + select with that seed; counts_out[q][b] = how many candidates of this
- *       shard have a scan score >= levels[q][b].  levels_dev NULL = unseeded (counts are zeroed).
- *   (caller: all-reduce SUM of the counts over the shards)
- *   cldrd_scatter_finish: T = the highest level that >= k rows of the whole index reach; candidates with
- *       scan score < T - 2*eps are dropped (k rows with scan score >= T put the exact k-th score above
- *       T - eps, so a top-k row scans above T - 2*eps); the rest are re-scored and stored as in
- *       cldrd_search_dev_scatter, batch query i being query q_base + i of the search.
- * One batch in flight per shard; q_dev must stay valid until cldrd_scatter_finish returns. */
 #define CLDRD_QUERY_BATCH 8192
-int cldrd_levels_from_samples(int device, const float* topj_dev, int32_t parts, int64_t nq,
-                              float* levels_out_dev, void* cuda_stream);
-int cldrd_scatter_begin(cldrd_shard* s, const float* q_dev, int64_t nq, int32_t k,
-                        const float* levels_dev, int32_t* counts_out_dev, float* eps2_out_dev,
-                        void* cuda_stream);
-int cldrd_scatter_finish(cldrd_shard* s, const int32_t* counts_dev, const float* levels_dev,
-                         int32_t world, int32_t rank, int64_t slice, int64_t q_base,
-                         float* const* peer_scores, int64_t* const* peer_rows, void* cuda_stream);
+typedef struct cldrd_node cldrd_node;
+int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k);
+int  cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k);
+/* CLDRD_PEER_HANDLE_BYTES bytes to hand to the other processes (any byte transport) */
+int  cldrd_node_handle(const cldrd_node* n, void* out_handle);
+void* cldrd_node_block(const cldrd_node* n);
+/* make rank peer_rank's block addressable: `handle` from its process (CUDA IPC), or, inside one process, its
+ * cldrd_node_block pointer and device (peer access is enabled when the devices differ) */
+int  cldrd_node_attach(cldrd_node* n, int32_t peer_rank, const void* handle, void* ptr, int32_t peer_device);
+/* unmap the peers' blocks (every rank detaches before anybody destroys) */
+int  cldrd_node_detach(cldrd_node* n);
+void cldrd_node_destroy(cldrd_node* n);
+/* result buffers [CLDRD_QUERY_BATCH][max_k] float32 / int64 inside rank owner_rank's block, as this process
+ * addresses them: what the ranks pass as out_scores / out_ids to collect a batch on one GPU */
+int  cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** scores, void** ids);
+int  cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k,
+                             int32_t seeded, float* out_scores, int64_t* out_ids,
+                             const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream);
+/* Oldest batch in flight: waits for it, fills cldrd_shard_last_stats / last_scan_time, returns how many of
+ * its queries have to be searched again (the same on every rank) and their batch indices, ascending. */
+int  cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int32_t* fail_idx_out,
+                           int32_t cap);
+/* device milliseconds of the last ended batch: [0] prep + sample + barrier + levels, [1] scan + select,
+ * [2] counts + barrier + re-score/scatter, [3] barrier + merge/store, [4] barrier + status */
+int  cldrd_node_phase_ms(const cldrd_node* n, double out[5]);
 
-/* Exchange buffers for the calls above: device memory that other processes of the node can map.
+/* Device memory that other processes of the node can map (the node blocks above are made of it).
  * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
  * cldrd.dist sends them through its process group); cldrd_peer_open maps a peer's handle into this process
  * (`device` = the opening process' GPU; needs peer access between the two GPUs);
@@ -225,6 +248,10 @@ void cldrd_host_free(void* p);
  * node write their slice of the results into, each over its own PCIe link). */
 int  cldrd_host_register(void* p, int64_t nbytes);
 int  cldrd_host_unregister(void* p);
+/* The address under which kernels on `device` store into page-locked host memory obtained from
+ * cldrd_host_alloc / cldrd_host_register (the merge kernels of a sharded search write their slice of the
+ * result straight into the caller's host arrays over their own PCIe link). */
+int  cldrd_host_device_ptr(int device, void* host_ptr, void** out_dev_ptr);
 
 /* Merge per-shard candidate lists (replaces faiss IndexShards' CPU merge_knn_results behind
  * retriever/retrieval_utils.py:176-182).  Inputs are [parts][nq][k] device arrays of scores and

@@ -14,6 +14,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "cl-drd_b200")]
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
+    ap.add_argument("--backend", default="nccl")
+    ap.add_argument("--same-device", action="store_true", help="every rank on cuda:0 (one-GPU box; needs gloo)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -21,9 +23,14 @@ def main():
     from cldrd.index import shard_ranges
     from oracle import flat_ip as O
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl", device_id=dev)
+    local = 0 if args.same_device else int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(args.backend)
+    transports = ("p2p", "nccl") if args.backend == "nccl" else ("p2p",)
     res = {}
     # (name, rows, d, queries, k, seed bias): "manyq" crosses the 8192-query batch of the engine and is not a
     # multiple of the world size; "miss" pushes every seed above every score so that all queries take the retry
@@ -42,13 +49,13 @@ def main():
         s = CD.ShardedSearcher.from_rows(rows, rr.start, n, scan="f16", id_map=id_map)
         os.environ["CLDRD_SEED_BIAS"] = "0"
         out = {}
-        for transport in ("p2p", "nccl"):      # peer-memory scatter (default) and the NCCL all-to-all path
+        for transport in transports:           # peer-memory exchange (default) and the NCCL all-to-all path
             os.environ["CLDRD_DIST_P2P"] = "1" if transport == "p2p" else "0"
             out[transport] = s.search(q, k)
             torch.cuda.synchronize()
             print(f"[rank {rank}] {name}/{transport} done", file=sys.stderr, flush=True)
             if transport == "p2p":
-                res[f"p2p_used_{name}"] = getattr(s, "_px", None) is not None
+                res[f"p2p_used_{name}"] = getattr(s, "_nx", None) is not None
                 res[f"seed_misses_{name}"] = getattr(s, "last_seed_misses", None)
         os.environ["CLDRD_DIST_P2P"] = "1"
         Dh, Ih = s.search_host(xq, k)          # host in, host out: slices land in one shared page-locked block
@@ -68,6 +75,7 @@ def main():
                 r = O.compare_topk(D.cpu().numpy(), I.cpu().numpy(), D_ref, I_ref, *O.search(xb, ids, xq, k + 16, dtype=np.float64))
                 res["oracle_ok"] = bool(r["ok"])
             one.shard.close()
+        s.close()
         dist.barrier()
     if rank == 0:
         with open(args.out, "w") as f:

@@ -22,7 +22,7 @@ def test_header_symbols_exported(cldrd_lib):
     for n in names:
         assert hasattr(cldrd_lib, n), f"{n} declared in cldrd.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert cldrd_lib.cldrd_abi_version() == 1
+    assert cldrd_lib.cldrd_abi_version() == 2
 
 
 def test_no_torch_types_in_header():
@@ -79,10 +79,15 @@ def test_sharded_entry_points_validate_arguments(cldrd_lib):
     assert cldrd_lib.cldrd_peer_copy(0, None, None, 16, None) == _lib.E_INVAL
     assert cldrd_lib.cldrd_host_register(None, 0) == _lib.E_INVAL
     assert cldrd_lib.cldrd_host_unregister(None) == 0
-    assert cldrd_lib.cldrd_scatter_begin(None, None, 1, 10, None, None, None, None) == _lib.E_INVAL
-    assert cldrd_lib.cldrd_scatter_finish(None, None, None, 2, 0, 4, 0, None, None, None) == _lib.E_INVAL
-    assert cldrd_lib.cldrd_search_dev_scatter(None, None, 1, 10, None, 2, 0, 4, None, None, None, None) == _lib.E_INVAL
-    assert cldrd_lib.cldrd_levels_from_samples(0, None, 2, 4, None, None) == _lib.E_INVAL
+    n = C.c_void_p()
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 0, 0, 100) == _lib.E_INVAL              # world < 1
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 2, 100) == _lib.E_INVAL              # rank outside the world
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 0, _lib.MAX_K + 1) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_block_bytes(17, 100) == 0 and cldrd_lib.cldrd_node_block_bytes(8, 1000) > 8 * 1024 * 1000 * 8
+    assert cldrd_lib.cldrd_node_search_begin(None, None, None, 1, 10, 1, None, None, None, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_search_end(None, None, None, None, 0) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_attach(None, 0, None, None, -1) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_detach(None) == 0
     assert cldrd_lib.cldrd_merge_planes(0, None, None, 2, 4, 5, 10, 10, None, None, None, None) == _lib.E_INVAL   # nq > plane_rows
     assert _lib.MAX_PEERS == 16 and _lib.QUERY_BATCH == 8192 and _lib.PEER_HANDLE_BYTES == 72
 

@@ -625,77 +625,122 @@ def test_embedding_like_distribution_stays_exact_and_seeded(cldrd_lib, scan):
     gpu.close()
 
 
+def _in_process_shards(rows, N, world, scan="f16", ids=None):
+    """GpuIndexShards over `world` row ranges of a device tensor, all on GPU 0 (zero-copy shards)."""
+    import cldrd
+    from cldrd import dist as CD
+    from cldrd.index import GpuIndexShards, shard_ranges
+    parts = [CD.ShardedSearcher.from_rows(rows[rr.start:rr.stop], rr.start, N, scan=scan) for rr in shard_ranges(N, world)]
+    return GpuIndexShards([p.shard for p in parts], ids, N, rows.shape[1])
+
+
 @pytest.mark.parametrize("k", [100, 1000])
-def test_two_phase_scatter_protocol_on_one_gpu(cldrd_lib, k):
-    """The sharded search of cldrd.dist without processes: 3 shards on one GPU, plain device buffers standing
-    in for the peers' exchange buffers.  levels -> scatter_begin -> sum of counts -> scatter_finish (re-score
-    only above the agreed cut, results stored plane-wise into the owner's buffers) -> merge_planes.  Must equal
-    the single-shard search bit for bit, and the cut must really cut."""
+def test_node_protocol_three_shards_on_one_gpu(cldrd_lib, k):
+    """The node-wide sharded search (cldrd_node_*) without processes: 3 shards on one GPU, each with its own
+    exchange block and stream, blocks addressed directly.  sample -> levels -> scan -> counts -> counted cut ->
+    re-score + scatter -> merge + seed check, all asynchronous, flag barriers between the shards' streams.
+    Must equal the single-shard search bit for bit, and the counted cut must really cut."""
     import torch
     from cldrd import dist as CD
-    from cldrd._lib import check, lib, SEED_J
-    from cldrd.index import shard_ranges
     xb, xq = _big(nq=70, seed=203)
     N, nq, world = xb.shape[0], xq.shape[0], 3
+    ids = O.synth_ids(N, 204)
     rows = torch.from_numpy(xb).cuda()
-    q = torch.from_numpy(xq).cuda()
-    one = CD.ShardedSearcher.from_rows(rows, 0, N, scan="f16")
-    D1, I1 = one.local.search_device(q, k, translate_ids=False)
-    shards = [CD.ShardedSearcher.from_rows(rows[rr.start:rr.stop], rr.start, N, scan="f16") for rr in shard_ranges(N, world)]
-    bound = max(_norm_bound(s) for s in shards + [one])
-    for s in shards:
-        check(lib().cldrd_shard_set_norm_bound(s.shard.handle, C.c_float(bound)))
-    topj = torch.stack([s.local.sample_device(q, k) for s in shards])
-    levels = torch.empty((nq, SEED_J), dtype=torch.float32, device="cuda")
-    check(lib().cldrd_levels_from_samples(0, C.c_void_p(topj.data_ptr()), world, nq, C.c_void_p(levels.data_ptr()), None))
-    seed = torch.empty((nq,), dtype=torch.float32, device="cuda")
-    check(lib().cldrd_seed_from_samples(0, C.c_void_p(topj.data_ptr()), world, nq, C.c_void_p(seed.data_ptr()), None))
-    torch.cuda.synchronize()
-    lv = levels.cpu().numpy()
-    assert (np.diff(lv, axis=1) <= 0).all() and np.array_equal(lv[:, -1], seed.cpu().numpy())
-    sl = (nq + world - 1) // world
-    xD = [torch.full((world, sl, k), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
-    xI = [torch.full((world, sl, k), -1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    c_xD = (C.c_void_p * world)(*[t.data_ptr() for t in xD])
-    c_xI = (C.c_void_p * world)(*[t.data_ptr() for t in xI])
-    counts = [torch.empty((nq, SEED_J), dtype=torch.int32, device="cuda") for _ in range(world)]
-    eps2 = torch.empty((nq,), dtype=torch.float32, device="cuda")
-    for r, s in enumerate(shards):
-        check(lib().cldrd_scatter_begin(s.shard.handle, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(levels.data_ptr()),
-                                        C.c_void_p(counts[r].data_ptr()), C.c_void_p(eps2.data_ptr()), None))
-    # a second begin without finish is a state error, not a silent overwrite
-    rc = lib().cldrd_scatter_begin(shards[0].shard.handle, C.c_void_p(q.data_ptr()), nq, k, None,
-                                   C.c_void_p(counts[0].data_ptr()), None, None)
-    assert rc != 0
-    total = torch.stack(counts).sum(dim=0).to(torch.int32).contiguous()
-    tc = total.cpu().numpy()
-    assert (np.diff(tc, axis=1) >= 0).all() and (tc[:, -1] >= k).all()      # counts grow level by level; the seed level clears k
-    rescored = 0
-    for r, s in enumerate(shards):
-        check(lib().cldrd_scatter_finish(s.shard.handle, C.c_void_p(total.data_ptr()), C.c_void_p(levels.data_ptr()), world, r, sl,
-                                         0, c_xD, c_xI, None))
-        st = s.shard.stats()
-        assert st["fallback_queries"] == 0, st
-        rescored += st["rescored"]
-    D = torch.empty((world * sl, k), dtype=torch.float32, device="cuda")
-    I = torch.empty((world * sl, k), dtype=torch.int64, device="cuda")
-    for r in range(world):
-        n_mine = max(0, min(sl, nq - r * sl))
-        check(lib().cldrd_merge_planes(0, C.c_void_p(xD[r].data_ptr()), C.c_void_p(xI[r].data_ptr()), world, sl, n_mine, k, k, None,
-                                       C.c_void_p(D[r * sl:].data_ptr()), C.c_void_p(I[r * sl:].data_ptr()), None))
-    fail = torch.ones((nq,), dtype=torch.int32, device="cuda")
-    check(lib().cldrd_verify_seed(0, C.c_void_p(D.data_ptr()), nq, k, C.c_void_p(seed.data_ptr()), C.c_void_p(eps2.data_ptr()),
-                                  C.c_void_p(fail.data_ptr()), None))
-    torch.cuda.synchronize()
-    ok = (fail == 0)
-    assert int(ok.sum()) >= nq - 2
-    assert torch.equal(D[:nq][ok], D1[ok]) and torch.equal(I[:nq][ok], I1[ok])
+    one = _gpu_index(xb, ids, "f16")
+    D1, I1 = one.search(xq, k)
+    one.close()
+    multi = _in_process_shards(rows, N, world, ids=ids)
+    D, I = multi.search(xq, k)
+    assert multi.last_seed_misses <= 2
+    assert np.array_equal(D, D1) and np.array_equal(I, I1)
+    stats = multi.last_stats()
+    assert all(st["tc_tiles"] > 0 for st in stats), stats
+    rescored = sum(st["rescored"] for st in stats)
     # without the cut every shard re-scores all it collected above the seed (~3.5k rows per query over the
     # shards); with it, about k plus one level step plus the error band
     assert rescored / nq < 1.6 * k + 400, (rescored / nq, k)
-    # finish without begin
-    rc = lib().cldrd_scatter_finish(shards[0].shard.handle, C.c_void_p(total.data_ptr()), C.c_void_p(levels.data_ptr()), world, 0, sl,
-                                    0, c_xD, c_xI, None)
-    assert rc != 0
-    for s in shards + [one]:
-        s.shard.close()
+    # results are caller-owned: a second search does not touch the first one's arrays
+    D2, I2 = multi.search(xq[::-1].copy(), k)
+    assert np.array_equal(D, D1) and np.array_equal(D2[::-1], D1) and np.array_equal(I2[::-1], I1)
+    multi.close()
+
+
+def test_node_protocol_retry_many_batches_and_small_shards(cldrd_lib, monkeypatch):
+    """The rare paths of the node-wide search on one GPU: every seed missed (all queries raised by the merge's
+    seed check and searched again unseeded), more queries than one 8192-query batch with several batches in
+    flight and a query count that the shards do not divide, shards below the seeding size."""
+    import torch
+    xb, xq = _big(nq=33, seed=205)
+    N = xb.shape[0]
+    rows = torch.from_numpy(xb).cuda()
+    one = _gpu_index(xb, None, "f16")
+    D1, I1 = one.search(xq, 50)
+    monkeypatch.setenv("CLDRD_SEED_BIAS", "1e6")
+    multi = _in_process_shards(rows, N, 2)
+    monkeypatch.setenv("CLDRD_SEED_BIAS", "0")
+    D, I = multi.search(xq, 50)
+    assert multi.last_seed_misses == 33
+    assert np.array_equal(D, D1) and np.array_equal(I, I1)
+    multi.close()
+    # 3 full batches + a ragged one, k small; the ring of batches in flight wraps
+    xq2 = O.synth(3 * 8192 + 77, 64, 206)
+    multi = _in_process_shards(rows, N, 3)
+    Dm, Im = multi.search(xq2, 10)
+    Ds, Is = one.search(xq2, 10)
+    assert np.array_equal(Dm, Ds) and np.array_equal(Im, Is)
+    multi.close()
+    one.close()
+    # small index: unseeded batches (progressive scheme per shard), fewer rows than k on a shard
+    xs, xqs = O.synth(2500, 64, 207), O.synth(40, 64, 208)
+    rs = torch.from_numpy(xs).cuda()
+    multi = _in_process_shards(rs, 2500, 3)
+    one = _gpu_index(xs, None, "f16")
+    for kk in (7, 1000, 2048):
+        Dm, Im = multi.search(xqs, kk)
+        Ds, Is = one.search(xqs, kk)
+        assert np.array_equal(Dm, Ds) and np.array_equal(Im, Is), kk
+    multi.close()
+    one.close()
+
+
+def test_shards_settle_on_one_scan_precision(cldrd_lib):
+    """scan="auto" picks f16 or tf32 per shard from that shard's own value range; the error band of the sharded
+    protocol must be the same on every shard, so one shard outside the fp16 range moves all of them to tf32."""
+    import cldrd
+    xb, xq = O.synth(40_000, 64, 210), O.synth(30, 64, 211)
+    xb[35_000, 3] = 1.0e5                       # only the second shard exceeds the fp16 range
+    host = cldrd.IndexFlatIP(64)
+    host.add(xb)
+    co = cldrd.GpuMultipleClonerOptions()
+    co.shard = True
+    co.scan = "auto"
+    multi = cldrd.index_cpu_to_gpu_multiple(None, [0, 0], host, co)
+    assert [sh.scan for sh in multi._shards] == ["tf32", "tf32"]
+    D, I = multi.search(xq, 100)
+    D_ref, I_ref = O.search(xb, None, xq, 100)
+    r = O.compare_topk(D, I, D_ref, I_ref, *O.search(xb, None, xq, 116, dtype=np.float64))
+    assert r["ok"], r
+    multi.close()
+
+
+def test_one_gpu_two_ranks_gloo_ipc(cldrd_lib, tmp_path):
+    """cldrd.dist with one process per shard on a ONE-GPU box: two ranks on cuda:0, gloo for the setup
+    collectives (NCCL refuses two ranks on one device), CUDA-IPC blocks on the same device.  The sharded result
+    must equal the single-shard result bit for bit, through search and search_host."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "dist_result.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "dist_worker.py"), "--out", str(out), "--backend", "gloo",
+           "--same-device"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-8000:]
+    res = json.loads(out.read_text())
+    for name in ("small", "big", "manyq", "miss"):
+        assert res[f"bit_equal_{name}_p2p"], res
+        assert res[f"p2p_used_{name}"], res          # the peer-memory exchange is the path that ran
+        assert res[f"bit_equal_{name}_host"] and res[f"host_shared_{name}"], res
+    assert res["oracle_ok"], res
+    assert res["seed_misses_miss"] == 33 and res["seed_misses_big"] == 0, res
