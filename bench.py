@@ -372,9 +372,9 @@ def main():
             return searcher.local.search_device(q, k, translate_ids=True)
         return searcher.search(q, k)
 
+    shard.set_profiling(True)
     for _ in range(warmup):
         step_dev()
-    shard.set_profiling(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()      # before the barrier: spawning nvidia-smi must not delay rank 0 inside the timed region
@@ -384,6 +384,7 @@ def main():
     D_dev = I_dev = None
     e0.record()
     for _ in range(args.steps):
+        D_dev = I_dev = None               # a caller's loop drops the previous result before it asks for the next one
         D_dev, I_dev = step_dev()
         ms, nl = shard.scan_time()
         scan_ms_total += ms
@@ -397,6 +398,10 @@ def main():
     stats = shard.stats()
     qps = nq * args.steps / (dev_ms / 1e3)
     phase_ms = getattr(searcher, "last_phase_ms", None)
+    phase_by_rank = None
+    if world > 1:
+        phase_by_rank = [None] * world
+        dist.all_gather_object(phase_by_rank, phase_ms)
 
     # ---- end-to-end loop with host buffers: `e2e` ---------------------------------------------------
     q_np = q_host.numpy()
@@ -526,6 +531,8 @@ def main():
         }
         if phase_ms:
             line["phase_ms_last_batch"] = phase_ms
+        if phase_by_rank:
+            line["phase_ms_last_batch_by_rank"] = [{k: round(v, 3) for k, v in p.items()} if p else None for p in phase_by_rank]
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:

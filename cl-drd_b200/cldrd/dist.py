@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Optional, Tuple
 
 import torch
@@ -118,10 +119,10 @@ class _NodeExchange:
         return d.value, i.value
 
     def phase_ms(self) -> dict:
-        arr = (C.c_double * 5)()
+        arr = (C.c_double * 6)()
         check(lib().cldrd_node_phase_ms(self.handle, arr))
         return dict(zip(["sample+barrier+levels", "scan+select", "counts+barrier+rescore", "barrier+merge+store",
-                         "barrier+status"], list(arr)))
+                         "barrier+status", "idle_before_batch"], list(arr)))
 
     def close(self):
         """Collective: every rank unmaps its peers before anybody frees."""
@@ -378,6 +379,7 @@ class ShardedSearcher:
         st = torch.cuda.current_stream(q.device).cuda_stream
         idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
         inflight, again = [], []
+        t_host0 = time.perf_counter()
         with self.local._lock:
             for b0 in range(0, n, _lib.QUERY_BATCH):
                 nb = min(_lib.QUERY_BATCH, n - b0)
@@ -391,9 +393,12 @@ class ShardedSearcher:
                 inflight.append(b0)
                 if after_batch is not None:
                     after_batch(b0, nb)
+            t_host1 = time.perf_counter()
             while inflight:
                 again += self._end_batch(nx, inflight.pop(0))
         self.last_phase_ms = nx.phase_ms()
+        self.last_phase_ms["host_enqueue"] = (t_host1 - t_host0) * 1e3
+        self.last_phase_ms["host_wait"] = (time.perf_counter() - t_host1) * 1e3
         return again
 
     def _check_q(self, q: torch.Tensor, k: int) -> torch.Tensor:

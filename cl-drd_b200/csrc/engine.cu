@@ -1400,7 +1400,7 @@ struct cldrd_node {
         size_t ev_lo = 0, ev_hi = 0;
     } slot[kRing];
     int64_t seq_begin = 0, seq_end = 0;
-    double phase_ms[5] = {0, 0, 0, 0, 0};
+    double phase_ms[6] = {0, 0, 0, 0, 0, 0};   // [5]: device idle between the previous batch and this one
 };
 
 namespace {
@@ -1723,6 +1723,13 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
         if (cudaEventElapsedTime(&ms, n->phase[slot][i], n->phase[slot][i + 1]) != cudaSuccess) cudaGetLastError();
         n->phase_ms[i] = ms;
     }
+    n->phase_ms[5] = 0.0;
+    if (n->seq_end >= 2) {   // (seq_end was advanced above) the batch before this one: end of its status kernel -> our start
+        const int prev = int((n->seq_end - 2) % cldrd_node::kRing);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, n->phase[prev][5], n->phase[slot][0]) == cudaSuccess) n->phase_ms[5] = ms;
+        else cudaGetLastError();
+    }
     s->scan_ms = 0.0;
     s->scan_launches = 0;
     s->ev_ms.clear();
@@ -1750,9 +1757,9 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
     return CLDRD_OK;
 }
 
-int cldrd_node_phase_ms(const cldrd_node* n, double out[5]) {
+int cldrd_node_phase_ms(const cldrd_node* n, double out[6]) {
     if (!n || !out) return fail(CLDRD_EINVAL, "node_phase_ms: NULL");
-    for (int i = 0; i < 5; ++i) out[i] = n->phase_ms[i];
+    for (int i = 0; i < 6; ++i) out[i] = n->phase_ms[i];
     return CLDRD_OK;
 }
 

@@ -213,8 +213,9 @@ int  cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, 
 int  cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int32_t* fail_idx_out,
                            int32_t cap);
 /* device milliseconds of the last ended batch: [0] prep + sample + barrier + levels, [1] scan + select,
- * [2] counts + barrier + re-score/scatter, [3] barrier + merge/store, [4] barrier + status */
-int  cldrd_node_phase_ms(const cldrd_node* n, double out[5]);
+ * [2] counts + barrier + re-score/scatter, [3] barrier + merge/store, [4] barrier + status,
+ * [5] device idle on this stream between the end of the previous batch and the start of this one */
+int  cldrd_node_phase_ms(const cldrd_node* n, double out[6]);
 
 /* Device memory that other processes of the node can map (the node blocks above are made of it).
  * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
