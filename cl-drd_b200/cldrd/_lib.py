@@ -15,6 +15,7 @@ SEED_J = 32
 MAX_PEERS = 16            # CLDRD_MAX_PEERS
 QUERY_BATCH = 8192        # CLDRD_QUERY_BATCH
 PEER_HANDLE_BYTES = 72    # CLDRD_PEER_HANDLE_BYTES
+MAX_OUT_SETS = 8          # CLDRD_MAX_OUT_SETS
 
 E_INVAL, E_IO, E_FORMAT, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
 
@@ -68,6 +69,9 @@ SIGNATURES = {
     "cldrd_node_result_ptrs": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cldrd_node_search_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cldrd_node_set_outputs": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cldrd_node_search_begin_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_node_search_end": (C.c_int, [C.c_void_p, C.c_void_p, _c_i32p, _c_i32p, C.c_int32]),
     "cldrd_node_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cldrd_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -139,20 +139,44 @@ class _NodeExchange:
         self.ok = False
 
 
+class _Lease:
+    """Lives as long as a caller references the arrays of one result set; the set is handed out again afterwards."""
+
+    def __init__(self, host: "_SharedHostResult", j: int):
+        self.host, self.j = host, j
+        host.busy[j] = True
+
+    def __del__(self):
+        try:
+            self.host.busy[self.j] = False
+        except Exception:
+            pass
+
+
 class _SharedHostResult:
-    """[rows, k] float32 scores + int64 ids in ONE shared-memory mapping that every rank of the node has
-    page-locked (cldrd_host_register): each rank copies its merged slice device -> host over its own PCIe
-    link, rank 0 reads the whole result as numpy arrays without any further copy."""
+    """Result sets of [rows, k] float32 scores + int64 ids in ONE shared-memory mapping that every rank of the node
+    has page-locked (cldrd_host_register): every rank's merge kernel stores its slice of a result straight into the
+    set over its own PCIe link, rank 0 hands the set to the caller as numpy arrays without any further copy.
+
+    `index.search` returns arrays the caller owns, so a set goes back into rotation only when the caller
+    has dropped every reference to its arrays (`_Lease`); rank 0 picks a free set per search and the choice reaches the
+    other ranks' kernels through the exchange block (cldrd_node_search_begin_set).  The last set is scratch: when all
+    others are still referenced the result is stored there and copied into fresh arrays."""
 
     _serial = 0
+    ROTATION_MAX_BYTES = 256 << 20     # larger results (config 5: 1.2 GB) get one set + scratch
 
     def __init__(self, rank: int, rows: int, k: int, group, register: bool = True, device: int = 0):
         import mmap
         self.rank, self.group = rank, group
         self.cap_elems = rows * k
-        self.nbytes = self.cap_elems * 12 + 64
+        self.stride = (self.cap_elems * 12 + 64 + 4095) // 4096 * 4096
+        self.nsets = (3 if self.stride <= self.ROTATION_MAX_BYTES else 1) + 1
+        self.busy = [False] * self.nsets
+        self.nbytes = self.stride * self.nsets
         self.mm, self.base, self.ok = None, 0, False
-        self.dev_base = 0        # the block as this rank's kernels address it
+        self.addr = 0            # host address of the mapping
+        self.dev_base = 0        # the mapping as this rank's kernels address it
         # every step below ends in a collective that all ranks reach whatever failed locally
         name, fd = [None], -1
         if rank == 0:
@@ -182,6 +206,7 @@ class _SharedHostResult:
                 if rank != 0:
                     fd = os.open(name[0], os.O_RDWR)
                 self.mm = mmap.mmap(fd, self.nbytes)
+                self.addr = C.addressof(C.c_char.from_buffer(self.mm))
             except (OSError, ValueError):
                 good = False
         if fd >= 0:
@@ -193,7 +218,7 @@ class _SharedHostResult:
             except OSError:
                 pass
         if good and register:
-            self.base = C.addressof(C.c_char.from_buffer(self.mm))
+            self.base = self.addr
             reg = lib().cldrd_host_register(C.c_void_p(self.base), self.nbytes) == 0
             if not reg:
                 self.base = 0
@@ -212,11 +237,27 @@ class _SharedHostResult:
     def fits(self, rows: int, k: int) -> bool:
         return rows * k <= self.cap_elems
 
-    def views(self, n: int, k: int, rows_alloc: int):
-        """numpy views: D [n,k] at byte 0, I [n,k] behind the score block of rows_alloc rows."""
+    def pick(self) -> int:
+        """rank 0: a set no caller references any more, else the scratch set (the last one)."""
+        for j in range(self.nsets - 1):
+            if not self.busy[j]:
+                return j
+        return self.nsets - 1
+
+    def set_ptrs(self, rows_alloc: int, k: int):
+        """(scores, ids) device addresses of every set for a result of rows_alloc rows."""
+        ioff = self.ids_offset(rows_alloc, k)
+        return ([self.dev_base + j * self.stride for j in range(self.nsets)],
+                [self.dev_base + j * self.stride + ioff for j in range(self.nsets)])
+
+    def views(self, j: int, n: int, k: int, rows_alloc: int, lease: bool = True):
+        """numpy arrays over set j: D [n,k] at byte 0, I [n,k] behind the score block of rows_alloc rows.  With
+        lease=True the set stays out of rotation until both arrays (and every view of them) are gone."""
         import numpy as np
-        D = np.frombuffer(self.mm, dtype=np.float32, count=n * k, offset=0).reshape(n, k)
-        I = np.frombuffer(self.mm, dtype=np.int64, count=n * k, offset=self.ids_offset(rows_alloc, k)).reshape(n, k)
+        buf = (C.c_char * self.stride).from_address(self.addr + j * self.stride)
+        buf._keep = (self.mm, _Lease(self, j) if lease else None)
+        D = np.frombuffer(buf, dtype=np.float32, count=n * k, offset=0).reshape(n, k)
+        I = np.frombuffer(buf, dtype=np.int64, count=n * k, offset=self.ids_offset(rows_alloc, k)).reshape(n, k)
         return D, I
 
     @staticmethod
@@ -258,6 +299,7 @@ class ShardedSearcher:
         self._nx_disabled = False
         self._host: Optional[_SharedHostResult] = None
         self._host_disabled = False
+        self._host_sets_for = None
         self._setup_done = False
         self._id_map_synced = False
         self.last_seed_misses = 0
@@ -371,31 +413,47 @@ class ShardedSearcher:
         return [b0 + idx[i] for i in range(nfail.value)]
 
     def _run_node(self, nx: _NodeExchange, q: torch.Tensor, k: int, seeded: bool, out_of_batch, out_rows=None,
-                  after_batch=None):
+                  after_batch=None, out_set=None, on_end=None):
         """Queue the batches of one search (at most RING in flight), return the queries (indices into q) that
         have to be searched again -- the same list on every rank.  out_of_batch(b0, nb) -> (scores ptr, ids ptr)
-        of the batch's output rows; out_rows: optional int32 device tensor, output row of every query."""
+        of the batch's output rows; out_rows: optional int32 device tensor, output row of every query.
+        out_set (instead of out_of_batch): results go to a registered output set, rows from the batch's first
+        query on; the value is the set rank 0 picked (>= 0 there, -1 on the ranks that follow).
+        on_end(b0, nb, raised): called when a batch has ended (its rows have landed everywhere), in order."""
         n = q.shape[0]
         st = torch.cuda.current_stream(q.device).cuda_stream
         idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
         inflight, again = [], []
+
+        def end_oldest():
+            b0 = inflight.pop(0)
+            raised = self._end_batch(nx, b0)
+            again.extend(raised)
+            if on_end is not None:
+                on_end(b0, min(_lib.QUERY_BATCH, n - b0), raised)
+
         t_host0 = time.perf_counter()
         with self.local._lock:
             for b0 in range(0, n, _lib.QUERY_BATCH):
                 nb = min(_lib.QUERY_BATCH, n - b0)
                 if len(inflight) >= self.RING:
-                    again += self._end_batch(nx, inflight.pop(0))
-                oD, oI = out_of_batch(b0, nb)
+                    end_oldest()
                 rows = C.c_void_p(out_rows[b0:b0 + nb].data_ptr()) if out_rows is not None else None
-                check(lib().cldrd_node_search_begin(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()), nb,
-                                                    int(k), 1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
-                                                    C.c_void_p(st)))
+                if out_set is not None:
+                    check(lib().cldrd_node_search_begin_set(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()),
+                                                            nb, int(k), 1 if seeded else 0, int(out_set),
+                                                            0 if out_rows is not None else b0, rows, idm, C.c_void_p(st)))
+                else:
+                    oD, oI = out_of_batch(b0, nb)
+                    check(lib().cldrd_node_search_begin(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()), nb,
+                                                        int(k), 1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
+                                                        C.c_void_p(st)))
                 inflight.append(b0)
                 if after_batch is not None:
                     after_batch(b0, nb)
             t_host1 = time.perf_counter()
             while inflight:
-                again += self._end_batch(nx, inflight.pop(0))
+                end_oldest()
         self.last_phase_ms = nx.phase_ms()
         self.last_phase_ms["host_enqueue"] = (t_host1 - t_host0) * 1e3
         self.last_phase_ms["host_wait"] = (time.perf_counter() - t_host1) * 1e3
@@ -456,20 +514,17 @@ class ShardedSearcher:
                 outI[idx] = tmpI
         return (outD, outI) if self.rank == 0 else (None, None)
 
-    def search_host(self, q_host, k: int, copy: bool = False):
+    def search_host(self, q_host, k: int, on_batch=None):
         """Host buffers in, host buffers out (the shape of the reference's `index.search(x, k)`,
         retriever/retrieval_utils.py:135).
 
         q_host: the replicated float32 [nq, d] queries in host memory (numpy array or CPU tensor; page-locked
-        memory makes the upload asynchronous).  Returns numpy (D, I) on rank 0, (None, None) elsewhere.  On one
-        node every rank's merge kernel stores its slice of the result straight into one shared page-locked block
-        over its own PCIe link; rank 0 returns views of that block (valid until the next search_host call) or,
-        with copy=True, fresh arrays."""
+        memory makes the upload asynchronous).  Returns numpy (D, I) on rank 0, (None, None) elsewhere; the arrays
+        belong to the caller (they stay valid, untouched by later searches, for as long as they are referenced).
+        On one node every rank's merge kernel stores its slice of the result straight into a shared page-locked
+        result set over its own PCIe link; rank 0 hands out a set the caller no longer references."""
         qh = torch.as_tensor(q_host)
         assert qh.dtype == torch.float32 and qh.dim() == 2 and qh.shape[1] == self.d
-        if not 1 <= int(k) <= _lib.MAX_K:
-            raise RuntimeError(f"search: k={k} outside [1, {_lib.MAX_K}]")
-        k = int(k)
         n = qh.shape[0]
         dev = torch.device("cuda", self.shard.device)
         stage = getattr(self, "_q_stage", None)
@@ -477,10 +532,27 @@ class ShardedSearcher:
             stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
         q = stage[:n]
         q.copy_(qh, non_blocking=True)
+        return self.search_to_host(q, k, on_batch)
+
+    def search_to_host(self, q: torch.Tensor, k: int, on_batch=None):
+        """Device-resident queries in (e.g. straight from the encoder: SURVEY §8 f-3), host arrays out; otherwise
+        `search_host`.  on_batch(b0, nb, D_rows, I_rows), rank 0 only: called in order as soon as the rows of an
+        8192-query batch have landed in host memory, while later batches are still being searched -- the run-file
+        writer of config 5 (502 939 queries) works on batch i while batch i+1 is scanned."""
+        q = self._check_q(q, k)
+        k = int(k)
+        n = q.shape[0]
+        dev = q.device
 
         def via_device():
             D, I = self.search(q, k)
-            return (D.cpu().numpy(), I.cpu().numpy()) if self.rank == 0 else (None, None)
+            if self.rank != 0:
+                return None, None
+            D, I = D.cpu().numpy(), I.cpu().numpy()
+            if on_batch is not None:
+                for b0 in range(0, n, _lib.QUERY_BATCH):
+                    on_batch(b0, min(_lib.QUERY_BATCH, n - b0), D[b0:b0 + _lib.QUERY_BATCH], I[b0:b0 + _lib.QUERY_BATCH])
+            return D, I
 
         if self.world == 1 or n == 0:
             return via_device()
@@ -494,25 +566,45 @@ class ShardedSearcher:
             if host is not None:
                 host.close()
             host = self._host = _SharedHostResult(self.rank, n, k, self.group, device=dev.index)
+            self._host_sets_for = None
             if not host.ok:           # agreed by all ranks
                 host = self._host = None
                 self._host_disabled = True
         if host is None:
             return via_device()
-        baseD = host.dev_base
-        baseI = host.dev_base + host.ids_offset(n, k)
-        again = self._run_node(nx, q, k, self.ntotal >= self.SEED_MIN_ROWS,
-                               lambda b0, nb: (baseD + b0 * k * 4, baseI + b0 * k * 8))
+        if self._host_sets_for != (id(nx), n, k):      # the set addresses depend on the result shape
+            sD, sI = host.set_ptrs(n, k)
+            check(lib().cldrd_node_set_outputs(nx.handle, host.nsets, (C.c_void_p * host.nsets)(*sD),
+                                               (C.c_void_p * host.nsets)(*sI)))
+            self._host_sets_for = (id(nx), n, k)
+        j = host.pick() if self.rank == 0 else -1
+        Dv = Iv = None
+        if self.rank == 0:
+            Dv, Iv = host.views(j, n, k, n, lease=j != host.nsets - 1)
+        held = []          # batches whose callback waits for the retry of a raised query (rare)
+
+        def on_end(b0, nb, raised):
+            if on_batch is None or self.rank != 0:
+                return
+            if raised or held:
+                held.append((b0, nb))
+            else:
+                on_batch(b0, nb, Dv[b0:b0 + nb], Iv[b0:b0 + nb])
+
+        again = self._run_node(nx, q, k, self.ntotal >= self.SEED_MIN_ROWS, None, out_set=j, on_end=on_end)
         self.last_seed_misses = len(again)
         if again:
             rows = torch.tensor(again, dtype=torch.int32, device=dev)
             q2 = q[rows.long()].contiguous()
-            left = self._run_node(nx, q2, k, False, lambda b0, nb: (baseD, baseI), rows)
+            left = self._run_node(nx, q2, k, False, None, out_rows=rows, out_set=j)
             assert not left, "an unseeded batch cannot raise queries"
         if self.rank != 0:
             return None, None
-        D, I = host.views(n, k, n)
-        return (D.copy(), I.copy()) if copy else (D, I)
+        for b0, nb in held:
+            on_batch(b0, nb, Dv[b0:b0 + nb], Iv[b0:b0 + nb])
+        if j == host.nsets - 1:       # every rotating set is still referenced by the caller: scratch + one copy
+            return Dv.copy(), Iv.copy()
+        return Dv, Iv
 
     def close(self):
         """Collective: releases the exchange block, the shared host block and the shard."""

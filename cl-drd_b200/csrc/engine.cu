@@ -320,6 +320,7 @@ void preload_kernels(int device) {
     preload_one(count_levels_peers_kernel);
     preload_one(merge_keys_kernel);
     preload_one(node_tail_kernel);
+    preload_one(node_publish_kernel);
 }
 
 // error-bound coefficients: eps = coef * |q| * max|b| + abs_coef * (|q| + max|b|)   
@@ -1400,6 +1401,9 @@ struct cldrd_node {
         size_t ev_lo = 0, ev_hi = 0;
     } slot[kRing];
     int64_t seq_begin = 0, seq_end = 0;
+    int out_sets = 0;                              // cldrd_node_set_outputs
+    float* set_scores[CLDRD_MAX_OUT_SETS];
+    long long* set_ids[CLDRD_MAX_OUT_SETS];
     double phase_ms[6] = {0, 0, 0, 0, 0, 0};   // [5]: device idle between the previous batch and this one
 };
 
@@ -1558,11 +1562,16 @@ int cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** score
     return CLDRD_OK;
 }
 
-int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
-                            float* out_scores, int64_t* out_ids, const int32_t* out_rows_dev, const int64_t* id_map_dev,
-                            void* cuda_stream) {
-    if (!s || !n || !q_dev || !out_scores || !out_ids || nq < 1 || nq > kQueryBatch)
+}  // extern "C"
+
+static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
+                                  float* out_scores, int64_t* out_ids, bool use_sets, int32_t out_select, int64_t out_row0,
+                                  const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream) {
+    if (!s || !n || !q_dev || (!use_sets && (!out_scores || !out_ids)) || nq < 1 || nq > kQueryBatch)
         return fail(CLDRD_EINVAL, "node_search_begin: bad argument (1 <= nq <= %d)", kQueryBatch);
+    if (use_sets && (n->out_sets < 1 || out_select >= n->out_sets || out_row0 < 0))
+        return fail(CLDRD_EINVAL, "node_search_begin_set: set %d of %d registered sets, first row %lld", out_select, n->out_sets,
+                    (long long)out_row0);
     if (k < 1 || k > n->cap_k) return fail(CLDRD_EINVAL, "node_search_begin: k=%d outside [1,%d] of this node", k, n->cap_k);
     if (!s->finalized) return fail(CLDRD_ESTATE, "node_search_begin: shard not finalized");
     if (s->device != n->device) return fail(CLDRD_EINVAL, "node_search_begin: shard and node live on different devices");
@@ -1604,6 +1613,10 @@ int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, i
     if (rc) return rc;
     // nobody raises a query of this batch before the first barrier below (seeded) / at all (unseeded)
     CU_TRY(cudaMemsetAsync(n->block + n->lay.qfail, 0, size_t(nq) * sizeof(int), st));
+    if (use_sets && out_select >= 0) {   // this rank picks the output set; every rank reads it behind the next barrier
+        node_publish_kernel<<<1, 32, 0, st>>>(node_ptrs(n, n->lay.ctrl), n->world, out_select);
+        CU_TRY(cudaGetLastError());
+    }
     int64_t extra = 0;
     SearchTotals totals;
     if (sd) {
@@ -1680,6 +1693,15 @@ int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, i
         m.id_map = reinterpret_cast<const long long*>(id_map_dev);
         m.out_scores = out_scores;
         m.out_ids = reinterpret_cast<long long*>(out_ids);
+        if (use_sets) {
+            m.out_sets = n->out_sets;
+            m.ctrl = reinterpret_cast<const int*>(n->block + n->lay.ctrl);
+            m.out_row0 = out_row0;
+            for (int i = 0; i < n->out_sets; ++i) {
+                m.set_scores[i] = n->set_scores[i];
+                m.set_ids[i] = n->set_ids[i];
+            }
+        }
         m.out_rows = out_rows_dev;
         m.qfail = node_ptrs(n, n->lay.qfail);
         m.world = world;
@@ -1701,6 +1723,35 @@ int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, i
     sl.fallback_queries = totals.fallback_queries;
     sl.ev_hi = s->ev_used;
     n->seq_begin++;
+    return CLDRD_OK;
+}
+
+extern "C" {
+
+int cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
+                            float* out_scores, int64_t* out_ids, const int32_t* out_rows_dev, const int64_t* id_map_dev,
+                            void* cuda_stream) {
+    return node_search_begin_impl(s, n, q_dev, nq, k, seeded, out_scores, out_ids, false, -1, 0, out_rows_dev, id_map_dev,
+                                  cuda_stream);
+}
+
+int cldrd_node_search_begin_set(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
+                                int32_t out_select, int64_t out_row0, const int32_t* out_rows_dev, const int64_t* id_map_dev,
+                                void* cuda_stream) {
+    return node_search_begin_impl(s, n, q_dev, nq, k, seeded, nullptr, nullptr, true, out_select, out_row0, out_rows_dev,
+                                  id_map_dev, cuda_stream);
+}
+
+int cldrd_node_set_outputs(cldrd_node* n, int32_t count, void* const* scores, void* const* ids) {
+    if (!n || count < 0 || count > CLDRD_MAX_OUT_SETS || (count && (!scores || !ids)))
+        return fail(CLDRD_EINVAL, "node_set_outputs: bad argument (count <= %d)", CLDRD_MAX_OUT_SETS);
+    if (n->seq_begin != n->seq_end) return fail(CLDRD_ESTATE, "node_set_outputs: batches in flight");
+    for (int i = 0; i < count; ++i) {
+        if (!scores[i] || !ids[i]) return fail(CLDRD_EINVAL, "node_set_outputs: NULL buffer in set %d", i);
+        n->set_scores[i] = static_cast<float*>(scores[i]);
+        n->set_ids[i] = static_cast<long long*>(ids[i]);
+    }
+    n->out_sets = count;
     return CLDRD_OK;
 }
 

@@ -13,6 +13,7 @@ namespace cldrd {
 // process, use the pointer directly).  Byte offsets from the block base.
 struct NodeLayout {
     size_t flags = 0;    // u32 [CLDRD_MAX_PEERS]        barrier epochs, slot p written by rank p
+    size_t ctrl = 0;     // i32 [16]                     [0]: output set chosen by the publishing rank for this batch
     size_t qfail = 0;    // i32 [QB]                     query must be searched again (any rank may raise it)
     size_t topj = 0;     // f32 [world][QB][J]           sample scores, plane p written by rank p
     size_t counts = 0;   // i32 [world][QB][J]           candidates above each level, plane p written by rank p
@@ -30,6 +31,7 @@ __host__ inline NodeLayout node_layout(int world, int cap_k) {
     l.slice = int64_t((QB + size_t(world) - 1) / size_t(world));
     size_t o = 0;
     l.flags = o;  o = up(o + CLDRD_MAX_PEERS * 4);
+    l.ctrl = o;   o = up(o + 16 * 4);
     l.qfail = o;  o = up(o + QB * 4);
     l.topj = o;   o = up(o + size_t(world) * QB * J * 4);
     l.counts = o; o = up(o + size_t(world) * QB * J * 4);
@@ -178,6 +180,13 @@ struct MergeKeysParams {
     const long long* id_map;   // optional global row -> external id
     float* out_scores;         // [*][k]
     long long* out_ids;        // [*][k]
+    // ... or, when out_sets > 0, one of several registered output sets, chosen per batch by ONE rank and published in
+    // every rank's ctrl word before the barrier that precedes this kernel (rows start at out_row0 of the set)
+    int out_sets;
+    const int* ctrl;
+    long long out_row0;
+    float* set_scores[CLDRD_MAX_OUT_SETS];
+    long long* set_ids[CLDRD_MAX_OUT_SETS];
     const int* out_rows;       // optional: output row of batch query Q (default Q)
     PeerPtrs qfail;            // i32 [QB] in every rank's block
     int world;
@@ -232,9 +241,17 @@ __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
                 for (int w = 0; w < p.world; ++w) static_cast<int*>(p.qfail.p[w])[Q] = 1;
         }
     }
-    const size_t orow = p.out_rows ? size_t(p.out_rows[Q]) : size_t(Q);
-    float* os = p.out_scores + orow * p.k;
-    long long* oi = p.out_ids + orow * p.k;
+    size_t orow = p.out_rows ? size_t(p.out_rows[Q]) : size_t(Q);
+    float* os = p.out_scores;
+    long long* oi = p.out_ids;
+    if (p.out_sets > 0) {
+        const int sel = min(max(*p.ctrl, 0), p.out_sets - 1);
+        os = p.set_scores[sel];
+        oi = p.set_ids[sel];
+        orow += size_t(p.out_row0);
+    }
+    os += orow * p.k;
+    oi += orow * p.k;
     for (int i = tid; i < p.k; i += blockDim.x) {
         const uint64_t key = i < m ? top[i] : 0ull;
         if (key != 0) {
@@ -246,6 +263,11 @@ __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
             oi[i] = -1;
         }
     }
+}
+
+// One rank tells all ranks which registered output set this batch goes to.
+__global__ void node_publish_kernel(PeerPtrs ctrl, int world, int value) {
+    if (threadIdx.x < world) static_cast<int*>(ctrl.p[threadIdx.x])[0] = value;
 }
 
 // End of a batch: the queries raised in qfail, in ascending order, the device counters and the completion mark go to

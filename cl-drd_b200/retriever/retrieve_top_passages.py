@@ -13,6 +13,7 @@ import argparse
 import os
 import sys
 
+import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
@@ -20,6 +21,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cldrd  # noqa: E402
 from cldrd.encoder import DualEncoder, SequenceDataset, load_checkpoint  # noqa: E402
 from cldrd.retrieval_utils import convert_index_to_gpu, get_embeddings_from_scratch, index_retrieve_arrays  # noqa: E402
+
+
+SEARCH_CHUNK = 8 * 8192     # queries per search call when the run file is streamed
 
 
 def get_args(argv=None):
@@ -92,10 +96,14 @@ def main(args, is_query_side=True, header="# unique query"):
             if rank != 0:
                 query_embs = torch.empty(tuple(shape.tolist()), dtype=torch.float32, device=dev)
             dist.broadcast(query_embs, src=0)
-            D, I = searcher.search(query_embs, args.top_k)
+            # the run file grows batch by batch while later batches are still being searched
+            stream = cldrd.RunFileStream(args.output_path) if rank == 0 else None
+            qids = np.asarray(query_ids, dtype=np.int64) if rank == 0 else None
+            searcher.search_to_host(query_embs, args.top_k,
+                                    on_batch=(lambda b0, nb, D, I: stream.put(qids[b0:b0 + nb], I, D)) if rank == 0 else None)
             if rank == 0:
                 print(f"{header} = {len(set(query_ids))}")
-                avg = cldrd.write_run_file(args.output_path, query_ids, I.cpu().numpy(), D.cpu().numpy())
+                avg = stream.close()
                 print(f"average ranks per query = {avg}")
             dist.barrier()
         finally:
@@ -107,9 +115,20 @@ def main(args, is_query_side=True, header="# unique query"):
     index = cldrd.read_index(args.index_path)                      # headers only; rows stream file -> HBM
     devs = [int(x) for x in str(args.gpus).split(",")]
     index = convert_index_to_gpu(index, devs if len(devs) > 1 else devs[0], False)
-    nn_scores, nn_doc_ids = index_retrieve_arrays(index, query_embs, args.top_k)
-    print(f"{header} = {len(set(query_ids))}")
-    avg = cldrd.write_run_file(args.output_path, query_ids, nn_doc_ids, nn_scores)
+    if len(query_ids) <= SEARCH_CHUNK:
+        nn_scores, nn_doc_ids = index_retrieve_arrays(index, query_embs, args.top_k)
+        print(f"{header} = {len(set(query_ids))}")
+        avg = cldrd.write_run_file(args.output_path, query_ids, nn_doc_ids, nn_scores)
+    else:
+        # large query sets (the 502 939 training queries of the curriculum step, :48-50): search chunk i+1 while the
+        # writer thread formats chunk i
+        stream = cldrd.RunFileStream(args.output_path)
+        qids = np.asarray(query_ids, dtype=np.int64)
+        for c0 in range(0, len(query_ids), SEARCH_CHUNK):
+            nn_scores, nn_doc_ids = index_retrieve_arrays(index, query_embs[c0:c0 + SEARCH_CHUNK], args.top_k)
+            stream.put(qids[c0:c0 + SEARCH_CHUNK], nn_doc_ids, nn_scores)
+        print(f"{header} = {len(set(query_ids))}")
+        avg = stream.close()
     print(f"average ranks per query = {avg}")
 
 

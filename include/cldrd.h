@@ -208,6 +208,18 @@ int  cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** scor
 int  cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k,
                              int32_t seeded, float* out_scores, int64_t* out_ids,
                              const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream);
+/* Output sets: several result buffers registered once per rank (count <= CLDRD_MAX_OUT_SETS; scores[j] / ids[j] are set
+ * j's float32 / int64 [rows][k] arrays as THIS rank's GPU addresses them, e.g. sub-blocks of one shared page-locked
+ * host mapping), so that the rank that hands results to the caller can pick, batch by batch, a buffer the caller no
+ * longer references -- `index.search` returns arrays the caller owns -- without a host round trip to the
+ * other ranks: cldrd_node_search_begin_set is cldrd_node_search_begin with the output given as (set, first row);
+ * exactly one rank passes out_select >= 0, which a kernel publishes in every rank's block ahead of the merge; the
+ * others pass -1 and follow. */
+#define CLDRD_MAX_OUT_SETS 8
+int  cldrd_node_set_outputs(cldrd_node* n, int32_t count, void* const* scores, void* const* ids);
+int  cldrd_node_search_begin_set(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k,
+                                 int32_t seeded, int32_t out_select, int64_t out_row0,
+                                 const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream);
 /* Oldest batch in flight: waits for it, fills cldrd_shard_last_stats / last_scan_time, returns how many of
  * its queries have to be searched again (the same on every rank) and their batch indices, ascending. */
 int  cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int32_t* fail_idx_out,

@@ -60,8 +60,21 @@ def main():
         os.environ["CLDRD_DIST_P2P"] = "1"
         Dh, Ih = s.search_host(xq, k)          # host in, host out: slices land in one shared page-locked block
         res[f"host_shared_{name}"] = getattr(s, "_host", None) is not None
+        # the arrays belong to the caller: four more searches (reversed queries) while the first result is still
+        # referenced -- the rotation of result sets runs out and the scratch-and-copy path is taken -- must not touch it
+        keep = [s.search_host(np.ascontiguousarray(xq[::-1]), k) for _ in range(4)] if name in ("small", "big") else []
+        if name == "manyq":     # batches reported to the caller as they land, in order, with the final rows
+            seen = []
+            Dq, Iq = s.search_to_host(q, k, on_batch=lambda b0, nb, Db, Ib: seen.append((b0, nb, Db.copy(), Ib.copy())))
+            if rank == 0:
+                res["on_batch_ok"] = [(b0, nb) for b0, nb, _, _ in seen] == [(0, 8192), (8192, nq - 8192)] and all(
+                    np.array_equal(Db, Dh[b0:b0 + nb]) and np.array_equal(Ib, Ih[b0:b0 + nb]) for b0, nb, Db, Ib in seen) and \
+                    np.array_equal(Dq, Dh) and np.array_equal(Iq, Ih)
         if rank == 0:
-            Dh, Ih = Dh.copy(), Ih.copy()
+            for Dr, Ir in keep:
+                res[f"host_owned_{name}"] = res.get(f"host_owned_{name}", True) and bool(
+                    np.array_equal(Dr[::-1], Dh) and np.array_equal(Ir[::-1], Ih))
+            del keep
             full = torch.from_numpy(xb).to(dev)
             one = CD.ShardedSearcher.from_rows(full, 0, n, scan="f16", id_map=id_map)
             one.world, one.rank = 1, 0

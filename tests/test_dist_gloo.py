@@ -61,7 +61,9 @@ def _shared_block_worker(rank, world, port, out):
     n, k, sl = 7, 5, 4                                            # 7 queries, slices of 4 rows, 2 ranks
     blk = CD._SharedHostResult(rank, world * sl, k, None, register=False)
     res["mapped"] = blk.ok
-    D, I = blk.views(world * sl, k, world * sl)
+    assert blk.nsets == 4 and blk.pick() == 0
+    D, I = blk.views(0, world * sl, k, world * sl)
+    assert blk.pick() == 1                      # set 0 is referenced by D and I: the next result goes to set 1
     lo = rank * sl
     D[lo:lo + sl] = float(rank + 1)
     I[lo:lo + sl] = 100 * (rank + 1) + np.arange(k)
@@ -69,6 +71,11 @@ def _shared_block_worker(rank, world, port, out):
     if rank == 0:
         res["shared"] = bool((D[:sl] == 1).all() and (D[sl:] == 2).all() and (I[sl:, 0] == 200).all())
         res["ids_aligned"] = CD._SharedHostResult.ids_offset(world * sl, k) % 8 == 0 and I.ctypes.data % 8 == 0
+    view = D[1:3]
+    del D, I
+    res["view_keeps_the_set"] = blk.pick() == 1     # a slice of a handed-out array still owns the set
+    del view
+    res["set_returns_when_dropped"] = blk.pick() == 0
     dist.barrier()
     # (2) without CUDA the page-lock is refused: all ranks must agree on ok == False, nobody hangs
     blk2 = CD._SharedHostResult(rank, world * sl, k, None, register=True)

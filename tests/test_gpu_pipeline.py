@@ -79,6 +79,15 @@ def test_index_text_then_retrieve_top_passages(cldrd_lib, tmp_path):
     I_run = np.array([int(ln[1]) for ln in lines], dtype=np.int64).reshape(25, 20)
     r = O.compare_topk(D_run, I_run, D_ref, I_ref, *O.search(xb, ids, xq, 36, dtype=np.float64))
     assert r["ok"], r
+    # streamed form (query sets above SEARCH_CHUNK: the run file grows chunk by chunk behind the search): same bytes
+    run_s = tmp_path / "runs" / "dev.streamed.run"
+    b.output_path = str(run_s)
+    old_chunk, retrieve_top_passages.SEARCH_CHUNK = retrieve_top_passages.SEARCH_CHUNK, 7
+    try:
+        retrieve_top_passages.main(b)
+    finally:
+        retrieve_top_passages.SEARCH_CHUNK = old_chunk
+    assert run_s.read_bytes() == run.read_bytes()
     # the transposed script: passages against the same index, top-5
     run2 = tmp_path / "runs" / "passages.run"
     c = retrieve_top_queries.get_args(["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir,

@@ -475,8 +475,30 @@ def test_torchrun_two_ranks_nccl(cldrd_lib, tmp_path):
         assert res[f"bit_equal_{name}_p2p"] and res[f"bit_equal_{name}_nccl"], res
         assert res[f"p2p_used_{name}"], res          # the peer-memory exchange is the path that ran
         assert res[f"bit_equal_{name}_host"] and res[f"host_shared_{name}"], res
-    assert res["oracle_ok"], res
+    assert res["oracle_ok"] and res["host_owned_small"] and res["host_owned_big"] and res["on_batch_ok"], res
     assert res["seed_misses_miss"] == 33 and res["seed_misses_big"] == 0, res
+
+
+def test_device_resident_queries_equal_numpy_path(cldrd_lib):
+    """embeddings handed over on the device (no `.cpu().numpy()` round trip,
+    retriever/retrieval_utils.py:47) give the same bits as the numpy call, on one GPU and on in-process shards."""
+    import torch
+    import cldrd
+    from cldrd.retrieval_utils import index_retrieve_arrays
+    xb, xq, ids = O.synth(40_000, 64, 420), O.synth(90, 64, 421), O.synth_ids(40_000, 422)
+    gpu = _gpu_index(xb, ids, "f16")
+    D, I = gpu.search(xq, 100)
+    Dd, Id = index_retrieve_arrays(gpu, torch.from_numpy(xq).cuda(), 100)
+    assert isinstance(Dd, np.ndarray) and np.array_equal(Dd, D) and np.array_equal(Id, I)
+    with pytest.raises(TypeError):
+        gpu.search(torch.from_numpy(xq).cuda().double(), 10)
+    gpu.close()
+    host = cldrd.IndexIDMap(cldrd.IndexFlatIP(64))
+    host.add_with_ids(xb, ids)
+    multi = cldrd.index_cpu_to_gpu_multiple(None, [0, 0], host, None)
+    Dm, Im = multi.search(torch.from_numpy(xq).cuda(), 100)
+    assert np.array_equal(Dm, D) and np.array_equal(Im, I)
+    multi.close()
 
 
 def test_more_queries_than_one_batch(cldrd_lib):
@@ -795,5 +817,5 @@ def test_one_gpu_two_ranks_gloo_ipc(cldrd_lib, tmp_path):
         assert res[f"bit_equal_{name}_p2p"], res
         assert res[f"p2p_used_{name}"], res          # the peer-memory exchange is the path that ran
         assert res[f"bit_equal_{name}_host"] and res[f"host_shared_{name}"], res
-    assert res["oracle_ok"], res
+    assert res["oracle_ok"] and res["host_owned_small"] and res["host_owned_big"] and res["on_batch_ok"], res
     assert res["seed_misses_miss"] == 33 and res["seed_misses_big"] == 0, res

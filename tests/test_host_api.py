@@ -148,6 +148,27 @@ def test_run_writer_threads_do_not_change_the_bytes(cldrd_lib, tmp_path):
     assert f2.read_bytes() == files[0]
 
 
+def test_run_file_stream_equals_one_call(cldrd_lib, tmp_path):
+    """RunFileStream (blocks appended by a writer thread while the caller goes on searching) == one write_run_file
+    call over the concatenated blocks == the reference's loop (retrieve_top_passages.py:90-109)."""
+    import cldrd
+    rng = np.random.default_rng(9)
+    n, k = 5000, 37
+    D = (rng.standard_normal((n, k)) * 20 + 60).astype(np.float32)
+    I = rng.integers(0, 8_841_823, (n, k), dtype=np.int64)
+    qids = rng.permutation(10 ** 7)[:n].astype(np.int64)
+    a, b = tmp_path / "sub" / "stream.tsv", tmp_path / "one.tsv"
+    st = cldrd.RunFileStream(str(a))             # creates the parent directory like the reference (:99-100)
+    for c0 in range(0, n, 777):
+        st.put(qids[c0:c0 + 777], I[c0:c0 + 777], D[c0:c0 + 777])
+    assert st.close() == k
+    assert cldrd.write_run_file(str(b), qids, I, D) == k
+    assert a.read_bytes() == b.read_bytes()
+    ref = tmp_path / "ref.tsv"
+    O.write_run(str(ref), qids[:200].tolist(), I[:200], D[:200])
+    assert a.read_bytes().startswith(ref.read_bytes())
+
+
 def test_score_text_matches_python_repr(cldrd_lib):
     import cldrd
     rng = np.random.default_rng(1)
