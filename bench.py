@@ -271,6 +271,37 @@ def index_load_rate(torch, np, rank, world, dev, barrier, max_over_ranks, n_rows
             os.unlink(path)
 
 
+def inprocess_e2e(torch, np, cldrd, CD, world, n_rows, d, scan, ids_np, q_np, k, steps, D_ref, I_ref):
+    """`GpuIndexShards.search(numpy)` over all GPUs from this one process: queries/s end to end, and whether the result
+    equals the one-process-per-GPU result bit for bit."""
+    from cldrd.index import GpuIndexShards, shard_ranges
+    parts = []
+    for r, rr in enumerate(shard_ranges(n_rows, world)):
+        dv = torch.device("cuda", r)
+        with torch.cuda.device(dv):
+            g = torch.Generator(device=dv).manual_seed(1000 + r)
+            rows = torch.empty((len(rr), d), dtype=torch.float32, device=dv)
+            for r0 in range(0, len(rr), 1 << 20):
+                rows[r0:r0 + (1 << 20)].normal_(generator=g)
+            parts.append(CD.ShardedSearcher.from_rows(rows, rr.start, n_rows, scan=scan))
+    multi = GpuIndexShards([p.shard for p in parts], ids_np, n_rows, d)
+    try:
+        for _ in range(2):
+            multi.search(q_np, k)
+        D = I = None
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            D = I = None
+            D, I = multi.search(q_np, k)
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": q_np.shape[0] / dt, "unit": "queries/s", "ms_per_step": dt * 1e3,
+                "equals_per_process_result_bitwise": bool(np.array_equal(D, D_ref) and np.array_equal(I, I_ref)),
+                "api": "index_cpu_to_gpu_multiple(shard=True) -> GpuIndexShards.search(numpy): one process, one host thread, "
+                       "all GPUs; merge kernels store straight into the caller's page-locked arrays"}
+    finally:
+        multi.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -382,10 +413,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms_total, scan_launches, launches = 0.0, 0, 0
     D_dev = I_dev = None
+    phase_hist = []
     e0.record()
     for _ in range(args.steps):
         D_dev = I_dev = None               # a caller's loop drops the previous result before it asks for the next one
         D_dev, I_dev = step_dev()
+        if world > 1 and searcher.last_phase_ms:
+            phase_hist.append(dict(searcher.last_phase_ms))
         ms, nl = shard.scan_time()
         scan_ms_total += ms
         scan_launches += nl
@@ -400,8 +434,10 @@ def main():
     phase_ms = getattr(searcher, "last_phase_ms", None)
     phase_by_rank = None
     if world > 1:
+        # mean over the timed steps (last batch of each step), one record per rank: shows which GPU the others wait for
+        mean = {k_: sum(p[k_] for p in phase_hist) / len(phase_hist) for k_ in phase_hist[0]} if phase_hist else phase_ms
         phase_by_rank = [None] * world
-        dist.all_gather_object(phase_by_rank, phase_ms)
+        dist.all_gather_object(phase_by_rank, mean)
 
     # ---- end-to-end loop with host buffers: `e2e` ---------------------------------------------------
     q_np = q_host.numpy()
@@ -452,6 +488,44 @@ def main():
         if rank == 0:
             extras["writer"] = writer_rate(np, D_host, I_host, nq, k)
         extras["index_load"] = index_load_rate(torch, np, rank, world, dev, barrier, max_over_ranks)
+        if world > 1:
+            # The faiss-shaped multi-GPU call of the reference, retrieval_utils.py:165-182: ONE process drives all N GPUs
+            # (index_cpu_to_gpu_multiple(..., shard=True) -> index.search(numpy)).  Rank 0 builds it next to the ranks'
+            # own shards (same rows, same seeds) while the other ranks wait on a host-side barrier.
+            cpu_group = dist.new_group(backend="gloo")
+            if rank == 0:
+                try:
+                    extras["e2e_inprocess"] = inprocess_e2e(torch, np, cldrd, CD, world, n_rows, d, scan, ids_np, q_np, k, args.steps,
+                                                            D_host, I_host)
+                except Exception as e:      # a side measurement must not take the line down
+                    extras["e2e_inprocess"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            dist.barrier(group=cpu_group)
+
+    if not args.no_extras and args.workload == "curriculum":
+        # the curriculum step end to end: host queries in, run file out, the file growing batch by batch behind the
+        # search (retriever/retrieve_top_passages.py:88-109 on the 502 939 training queries)
+        where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        path = os.path.join(where, f"cldrd_bench_c5_{os.getpid()}.tsv")
+        qids = np.arange(nq, dtype=np.int64) * 3 + 7
+        D_host = I_host = None
+        barrier()
+        t0 = time.perf_counter()
+        stream = cldrd.RunFileStream(path) if rank == 0 else None
+        if world == 1:
+            chunk = 8 * 8192
+            for c0 in range(0, nq, chunk):
+                Dc, Ic = searcher.local.search(q_np[c0:c0 + chunk], k)
+                stream.put(qids[c0:c0 + chunk], Ic, Dc)
+        else:
+            searcher.search_host(q_host, k, on_batch=(lambda b0, nb, Db, Ib: stream.put(qids[b0:b0 + nb], Ib, Db)) if rank == 0 else None)
+        if rank == 0:
+            stream.close()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if rank == 0:
+            extras["e2e_with_run_file"] = {"value": nq / dt, "unit": "queries/s", "seconds": dt, "lines": nq * k,
+                                           "bytes": os.path.getsize(path), "where": where,
+                                           "note": "search_host + RunFileStream: batch i is formatted and written while batch i+1 is searched"}
+            os.unlink(path)
 
     # ---- roofline of the scan kernel ----------------------------------------------------------------
     peaks = load_peaks()
@@ -532,7 +606,7 @@ def main():
         if phase_ms:
             line["phase_ms_last_batch"] = phase_ms
         if phase_by_rank:
-            line["phase_ms_last_batch_by_rank"] = [{k: round(v, 3) for k, v in p.items()} if p else None for p in phase_by_rank]
+            line["phase_ms_mean_by_rank"] = [{k: round(v, 3) for k, v in p.items()} if p else None for p in phase_by_rank]
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -18,7 +18,7 @@ l = json.loads(sys.stdin.read())
 print(l['n_gpus'], 'value', round(l['value']), 'ms', round(l['ms_per_step'], 2), 'e2e', round(l['e2e']['value']), 'e2e ms', round(l['e2e']['ms_per_step'], 2))
 print(' roofline', {k: round(v, 3) for k, v in l['roofline'].items() if k in ('frac', 'step_frac', 'e2e_frac', 'scan_ms_per_step', 'scan_share_of_step')})
 print(' phases', l.get('phase_ms_last_batch'))
-for r, p in enumerate(l.get('phase_ms_last_batch_by_rank') or []): print('   rank', r, p)
+for r, p in enumerate(l.get('phase_ms_mean_by_rank') or []): print('   rank', r, p)
 print(' parity', l['parity'])
-print(' extras', {k: l.get(k) for k in ('writer', 'index_load')})" || tail -n 30 gpurun_out/bench_n$n.log
+print(' extras', {k: l.get(k) for k in ('writer', 'index_load', 'e2e_inprocess', 'e2e_with_run_file')})" || tail -n 30 gpurun_out/bench_n$n.log
 done
