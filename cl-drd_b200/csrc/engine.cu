@@ -16,6 +16,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common_host.h"
 #include "scan_simt.cuh"
 #include "scan_tc.cuh"
@@ -49,6 +51,12 @@ constexpr int kMaxRunLenByGroup = 64;  // ... stretched up to this if that makes
                                     // every unit owns a fresh survivor segment and the survivors
                                     // spread exactly evenly (with a few groups per CTA the
                                     // (query, CTA) cells would be loaded very unevenly)
+
+// NVTX range for the timeline tools (Nsight Systems / ncu --nvtx); a no-op when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -428,6 +436,7 @@ cudaEvent_t next_event(cldrd_shard* s) {
 }
 
 int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_stride = 1) {
+    NvtxRange nvtx(mode == TC_FILTER ? "cldrd::scan(filter)" : mode == TC_MAXES ? "cldrd::scan(sample)" : "cldrd::scan(dense)");
     const bool dense = mode != TC_FILTER;
     cldrd_shard* s = c.s;
     if (s->profile) {
@@ -839,6 +848,7 @@ int run_fallbacks(cldrd_shard* s, const float* q_dev, int nq, int k, bool transl
 int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool translate, int seed_mode,
                  const float* seed_ext, float* out_scores, int64_t* out_ids, float* eps_out, cudaStream_t st,
                  SearchTotals* tot) {
+    NvtxRange nvtx("cldrd::search_batch");
     BatchCtx c{};
     c.s = s;
     c.st = st;
@@ -1026,6 +1036,7 @@ int cldrd_shard_load_file(cldrd_shard* s, const char* path) {
                     (long long)s->nrows, (long long)info.ntotal);
     if (s->xb && !s->xb_owned) return fail(CLDRD_ESTATE, "shard_load_file: rows were adopted");
     DeviceGuard g(s->device);
+    NvtxRange nvtx("cldrd::shard_load_file");
     if ((rc = ensure_rows(s))) return rc;
     // pread -> page-locked ring -> cudaMemcpyAsync: the payload starts at an odd byte offset (82), so it is staged
     // rather than mapped.  One reader is bound by a single core's page-cache copy (a few GB/s) while the PCIe link
@@ -1126,6 +1137,7 @@ int cldrd_shard_finalize(cldrd_shard* s, void* cuda_stream) {
     if (!s) return fail(CLDRD_EINVAL, "shard_finalize: NULL");
     if (s->nrows > 0 && !s->xb) return fail(CLDRD_ESTATE, "shard_finalize: no rows uploaded / loaded / adopted");
     DeviceGuard g(s->device);
+    NvtxRange nvtx("cldrd::shard_finalize");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     // can TMA describe this shape?  (row pitch multiple of 16 bytes, 16-byte aligned base)
     s->scan_eff = s->scan;
@@ -1586,6 +1598,7 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
     const size_t merge_smem = (size_t(n->world) * k + size_t(k_pad)) * 8;
     if (merge_smem > 200 * 1024) return fail(CLDRD_EINVAL, "node_search_begin: world*k=%d too large for the merge", n->world * k);
     DeviceGuard g(s->device);
+    NvtxRange nvtx("cldrd::node_search_begin");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int slot = int(n->seq_begin % cldrd_node::kRing);
     cldrd_node::Slot& sl = n->slot[slot];
@@ -1759,6 +1772,7 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
     if (!s || !n) return fail(CLDRD_EINVAL, "node_search_end: NULL");
     if (n->seq_end == n->seq_begin) return fail(CLDRD_ESTATE, "node_search_end: no batch in flight");
     DeviceGuard g(n->device);
+    NvtxRange nvtx("cldrd::node_search_end");
     const int slot = int(n->seq_end % cldrd_node::kRing);
     const cldrd_node::Slot& sl = n->slot[slot];
     n->seq_end++;
