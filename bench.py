@@ -443,6 +443,10 @@ def main():
     q_np = q_host.numpy()
 
     def step_e2e():
+        if encode is not None and world == 1:
+            # configs[2]: token ids from pinned host memory -> encoder -> search on the device-resident embeddings
+            # (GpuIndexFlat.search takes the CUDA tensor: SURVEY f-3) -> numpy results
+            return searcher.local.search(encode(), k)
         if world == 1:
             return searcher.local.search(q_np, k)          # numpy in -> numpy out (cldrd_search_host)
         # every rank uploads its replica of the queries from pinned memory; every rank's merge kernel stores its slice
@@ -594,7 +598,7 @@ def main():
                        "chunks_per_pass": stats["chunks"], "rescored_per_query": stats["rescored"] / stats_q,
                        "survivors_per_query": stats["survivors"] / stats_q, "fallback_queries": stats["fallback_queries"]},
             "clocks": clocks,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4 if encode is None else nq * 30 * 8 * 2,
                     "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3 / args.steps,
                     "api": "GpuIndexFlat.search(numpy) -> cldrd_search_host" if world == 1 else
                            "pinned host -> ShardedSearcher.search_host -> merge kernels store into a shared page-locked host block"},

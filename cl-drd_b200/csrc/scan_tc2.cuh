@@ -181,6 +181,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) tmem2_alloc(tmem_base_slot, TC_TMEM_COLS);
     tc_fence_before();
     cluster_sync_all();                        // both CTAs' barriers and TMEM are ready
+    __syncthreads();                           // (the cluster barrier already orders this; racecheck only models this one)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 

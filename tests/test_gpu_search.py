@@ -611,7 +611,9 @@ def test_accumulator_worst_case_same_sign_equal_magnitude(cldrd_lib, scan, d):
     from cldrd._lib import check
     rng = np.random.Generator(np.random.PCG64(710 + d))
     nb, nq = 1024, 128
-    mags = np.array([1.0 + 2.0 ** -7, 1.0 + 3 * 2.0 ** -7, 1.5 + 2.0 ** -7, 1.0 + 2.0 ** -6], dtype=np.float32)
+    # 8 significant bits each (bf16-exact); products near 4 with 14 fraction bits: already at d = 768 the partial sums
+    # (up to ~3000) need 26 bits, at d = 4096 28 bits
+    mags = np.array([2.0 - 2.0 ** -6, 2.0 - 2.0 ** -7, 1.5 + 2.0 ** -7, 2.0 - 2.0 ** -5], dtype=np.float32)
     xb = rng.choice(mags, size=(nb, d)).astype(np.float32)
     xq = rng.choice(mags, size=(nq, d)).astype(np.float32)
     xb[:256] = mags[0]                       # equal magnitudes everywhere: the purest same-direction case
