@@ -59,8 +59,10 @@ SIGNATURES = {
     "cldrd_seed_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "cldrd_search_dev_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_verify_seed": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cldrd_node_block_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
-    "cldrd_node_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32]),
+    "cldrd_node_block_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "cldrd_node_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "cldrd_node_query_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cldrd_node_spread_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "cldrd_node_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cldrd_node_block": (C.c_void_p, [C.c_void_p]),
     "cldrd_node_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
@@ -136,7 +138,7 @@ class _PinnedPool:
     result is needed for every call.  A buffer returns to the pool when the ndarray that wraps it
     (and every view of it) has been garbage-collected."""
 
-    def __init__(self, max_bytes: int = 1 << 30):
+    def __init__(self, max_bytes: int = 4 << 30):
         self.free = {}          # nbytes -> [ptr]
         self.held = 0
         self.max_bytes = max_bytes

@@ -82,14 +82,15 @@ class _NodeExchange:
     process (CUDA IPC handles travel through the process group once, at construction).  Everything a search
     exchanges afterwards is stored by kernels into these blocks (include/cldrd.h, "Sharded search on one node")."""
 
-    def __init__(self, device: int, rank: int, world: int, max_k: int, group):
+    def __init__(self, device: int, rank: int, world: int, max_k: int, group, d: int = 0):
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.max_k = max_k
+        self.d = d if d % 4 == 0 else 0        # query buffer for host-side queries (cldrd_node_spread_queries)
         self.handle = C.c_void_p()
         ok = True
         mine = torch.zeros((_lib.PEER_HANDLE_BYTES,), dtype=torch.uint8)
         try:
-            check(lib().cldrd_node_create(C.byref(self.handle), device, world, rank, max_k))
+            check(lib().cldrd_node_create(C.byref(self.handle), device, world, rank, max_k, self.d))
             buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
             check(lib().cldrd_node_handle(self.handle, buf))
             mine = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
@@ -112,6 +113,11 @@ class _NodeExchange:
         self.ok = ok
         if not ok:
             self.close()
+
+    def query_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().cldrd_node_query_ptr(self.handle, C.byref(p)))
+        return p.value
 
     def result_ptrs(self, owner: int):
         d, i = C.c_void_p(), C.c_void_p()
@@ -398,7 +404,7 @@ class ShardedSearcher:
             return nx
         if nx is not None:
             nx.close()
-        self._nx = _NodeExchange(self.shard.device, self.rank, self.world, int(k), self.group)
+        self._nx = _NodeExchange(self.shard.device, self.rank, self.world, int(k), self.group, self.d)
         if not self._nx.ok:
             self._nx = None
             self._nx_disabled = True
@@ -413,15 +419,24 @@ class ShardedSearcher:
         return [b0 + idx[i] for i in range(nfail.value)]
 
     def _run_node(self, nx: _NodeExchange, q: torch.Tensor, k: int, seeded: bool, out_of_batch, out_rows=None,
-                  after_batch=None, out_set=None, on_end=None):
+                  after_batch=None, out_set=None, on_end=None, n_queries=None):
         """Queue the batches of one search (at most RING in flight), return the queries (indices into q) that
         have to be searched again -- the same list on every rank.  out_of_batch(b0, nb) -> (scores ptr, ids ptr)
         of the batch's output rows; out_rows: optional int32 device tensor, output row of every query.
         out_set (instead of out_of_batch): results go to a registered output set, rows from the batch's first
         query on; the value is the set rank 0 picked (>= 0 there, -1 on the ranks that follow).
-        on_end(b0, nb, raised): called when a batch has ended (its rows have landed everywhere), in order."""
-        n = q.shape[0]
-        st = torch.cuda.current_stream(q.device).cuda_stream
+        on_end(b0, nb, raised): called when a batch has ended (its rows have landed everywhere), in order.
+        q: the replicated queries as a CUDA tensor, or a callable (b0, nb) -> device address of the batch's queries
+        (with n_queries) that may enqueue whatever brings them there."""
+        if callable(q):
+            q_of_batch, n = q, int(n_queries)
+        else:
+            n = q.shape[0]
+
+            def q_of_batch(b0, nb):
+                return q[b0:b0 + nb].data_ptr()
+
+        st = torch.cuda.current_stream(torch.device("cuda", self.shard.device)).cuda_stream
         idm = C.c_void_p(self.id_map.data_ptr()) if self.id_map is not None else None
         inflight, again = [], []
 
@@ -439,13 +454,14 @@ class ShardedSearcher:
                 if len(inflight) >= self.RING:
                     end_oldest()
                 rows = C.c_void_p(out_rows[b0:b0 + nb].data_ptr()) if out_rows is not None else None
+                qp = q_of_batch(b0, nb)
                 if out_set is not None:
-                    check(lib().cldrd_node_search_begin_set(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()),
+                    check(lib().cldrd_node_search_begin_set(self.shard.handle, nx.handle, C.c_void_p(qp),
                                                             nb, int(k), 1 if seeded else 0, int(out_set),
                                                             0 if out_rows is not None else b0, rows, idm, C.c_void_p(st)))
                 else:
                     oD, oI = out_of_batch(b0, nb)
-                    check(lib().cldrd_node_search_begin(self.shard.handle, nx.handle, C.c_void_p(q[b0:b0 + nb].data_ptr()), nb,
+                    check(lib().cldrd_node_search_begin(self.shard.handle, nx.handle, C.c_void_p(qp), nb,
                                                         int(k), 1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
                                                         C.c_void_p(st)))
                 inflight.append(b0)
@@ -525,27 +541,34 @@ class ShardedSearcher:
         result set over its own PCIe link; rank 0 hands out a set the caller no longer references."""
         qh = torch.as_tensor(q_host)
         assert qh.dtype == torch.float32 and qh.dim() == 2 and qh.shape[1] == self.d
-        n = qh.shape[0]
-        dev = torch.device("cuda", self.shard.device)
-        stage = getattr(self, "_q_stage", None)
-        if stage is None or stage.shape[0] < n:
-            stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
-        q = stage[:n]
-        q.copy_(qh, non_blocking=True)
-        return self.search_to_host(q, k, on_batch)
+        if not 1 <= int(k) <= _lib.MAX_K:
+            raise RuntimeError(f"search: k={k} outside [1, {_lib.MAX_K}]")
+        return self._to_host(None, qh.contiguous(), int(k), on_batch)
 
     def search_to_host(self, q: torch.Tensor, k: int, on_batch=None):
         """Device-resident queries in (e.g. straight from the encoder: SURVEY §8 f-3), host arrays out; otherwise
         `search_host`.  on_batch(b0, nb, D_rows, I_rows), rank 0 only: called in order as soon as the rows of an
         8192-query batch have landed in host memory, while later batches are still being searched -- the run-file
         writer of config 5 (502 939 queries) works on batch i while batch i+1 is scanned."""
-        q = self._check_q(q, k)
-        k = int(k)
-        n = q.shape[0]
-        dev = q.device
+        return self._to_host(self._check_q(q, k), None, int(k), on_batch)
+
+    def _upload(self, qh: torch.Tensor) -> torch.Tensor:
+        dev = torch.device("cuda", self.shard.device)
+        n = qh.shape[0]
+        stage = getattr(self, "_q_stage", None)
+        if stage is None or stage.shape[0] < n:
+            stage = self._q_stage = torch.empty((max(n, 1), self.d), dtype=torch.float32, device=dev)
+        q = stage[:n]
+        q.copy_(qh, non_blocking=True)
+        return q
+
+    def _to_host(self, q: Optional[torch.Tensor], qh: Optional[torch.Tensor], k: int, on_batch):
+        """q: the queries on the device, or None with qh: the queries in host memory."""
+        n = q.shape[0] if q is not None else qh.shape[0]
+        dev = torch.device("cuda", self.shard.device)
 
         def via_device():
-            D, I = self.search(q, k)
+            D, I = self.search(q if q is not None else self._upload(qh), k)
             if self.rank != 0:
                 return None, None
             D, I = D.cpu().numpy(), I.cpu().numpy()
@@ -591,11 +614,31 @@ class ShardedSearcher:
             else:
                 on_batch(b0, nb, Dv[b0:b0 + nb], Iv[b0:b0 + nb])
 
-        again = self._run_node(nx, q, k, self.ntotal >= self.SEED_MIN_ROWS, None, out_set=j, on_end=on_end)
+        if q is None and nx.d == self.d:
+            # Host queries: G uploads of the same 21 MB over G PCIe links pulling from one buffer cost more than the
+            # whole exchange of the search.  Every rank uploads 1/G of the batch into its block and the part is stored
+            # into every other rank's block over NVLink (cldrd_node_spread_queries).
+            st = torch.cuda.current_stream(dev).cuda_stream
+            qx, row_bytes, src = nx.query_ptr(), self.d * 4, qh.data_ptr()
+
+            def q_src(b0, nb):
+                sl = (nb + self.world - 1) // self.world
+                lo = min(nb, self.rank * sl)
+                hi = min(nb, lo + sl)
+                if hi > lo:
+                    check(lib().cldrd_peer_copy(dev.index, C.c_void_p(qx + lo * row_bytes), C.c_void_p(src + (b0 + lo) * row_bytes),
+                                                (hi - lo) * row_bytes, C.c_void_p(st)))
+                check(lib().cldrd_node_spread_queries(self.shard.handle, nx.handle, lo, hi - lo, C.c_void_p(st)))
+                return qx
+        else:
+            if q is None:
+                q = self._upload(qh)
+            q_src = q
+        again = self._run_node(nx, q_src, k, self.ntotal >= self.SEED_MIN_ROWS, None, out_set=j, on_end=on_end, n_queries=n)
         self.last_seed_misses = len(again)
         if again:
             rows = torch.tensor(again, dtype=torch.int32, device=dev)
-            q2 = q[rows.long()].contiguous()
+            q2 = q[rows.long()].contiguous() if q is not None else qh[torch.tensor(again, dtype=torch.int64)].to(dev)
             left = self._run_node(nx, q2, k, False, None, out_rows=rows, out_set=j)
             assert not left, "an unseeded batch cannot raise queries"
         if self.rank != 0:

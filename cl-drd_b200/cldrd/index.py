@@ -583,7 +583,7 @@ class GpuIndexShards:
         try:
             for r, sh in enumerate(self._shards):
                 h = C.c_void_p()
-                check(lib().cldrd_node_create(C.byref(h), sh.device, G, r, int(k)))
+                check(lib().cldrd_node_create(C.byref(h), sh.device, G, r, int(k), 0))
                 self._nodes.append(h)
             for r, sh in enumerate(self._shards):
                 for p, other in enumerate(self._shards):

@@ -329,6 +329,7 @@ void preload_kernels(int device) {
     preload_one(merge_keys_kernel);
     preload_one(node_tail_kernel);
     preload_one(node_publish_kernel);
+    preload_one(node_spread_kernel);
 }
 
 // error-bound coefficients: eps = coef * |q| * max|b| + abs_coef * (|q| + max|b|)   
@@ -1393,7 +1394,7 @@ int cldrd_peer_copy(int device, void* dst, const void* src, int64_t nbytes, void
 }  // extern "C"
 
 struct cldrd_node {
-    int device = 0, world = 1, rank = 0, cap_k = 0;
+    int device = 0, world = 1, rank = 0, cap_k = 0, d = 0;
     NodeLayout lay;
     char* block = nullptr;                         // own exchange block
     unsigned char handle[CLDRD_PEER_HANDLE_BYTES];
@@ -1445,14 +1446,16 @@ PeerPtrs node_ptrs(const cldrd_node* n, size_t off) {
 
 extern "C" {
 
-int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k) {
-    if (world < 1 || world > CLDRD_MAX_PEERS || max_k < 1 || max_k > CLDRD_MAX_K) return 0;
-    return int64_t(node_layout(world, max_k).total);
+int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k, int32_t d) {
+    if (world < 1 || world > CLDRD_MAX_PEERS || max_k < 1 || max_k > CLDRD_MAX_K || d < 0) return 0;
+    return int64_t(node_layout(world, max_k, d).total);
 }
 
-int cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k) {
-    if (!out || world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || max_k < 1 || max_k > CLDRD_MAX_K)
-        return fail(CLDRD_EINVAL, "node_create: bad argument (world=%d rank=%d max_k=%d)", world, rank, max_k);
+int cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k, int32_t d) {
+    if (!out || world < 1 || world > CLDRD_MAX_PEERS || rank < 0 || rank >= world || max_k < 1 || max_k > CLDRD_MAX_K || d < 0 ||
+        d % 4 != 0)
+        return fail(CLDRD_EINVAL, "node_create: bad argument (world=%d rank=%d max_k=%d d=%d; d a multiple of 4 or 0)", world,
+                    rank, max_k, d);
     DeviceGuard g(device);
     preload_kernels(device);
     auto* n = new cldrd_node();
@@ -1460,7 +1463,8 @@ int cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank,
     n->world = world;
     n->rank = rank;
     n->cap_k = max_k;
-    n->lay = node_layout(world, max_k);
+    n->d = d;
+    n->lay = node_layout(world, max_k, d);
     for (int p = 0; p < CLDRD_MAX_PEERS; ++p) {
         n->peer[p] = nullptr;
         n->opened[p] = false;
@@ -1564,6 +1568,33 @@ void cldrd_node_destroy(cldrd_node* n) {
     if (n->h_status) cudaFreeHost(n->h_status);
     cudaFree(n->block);
     delete n;
+}
+
+int cldrd_node_query_ptr(const cldrd_node* n, void** q_dev) {
+    if (!n || !q_dev) return fail(CLDRD_EINVAL, "node_query_ptr: NULL");
+    if (n->d == 0) return fail(CLDRD_ESTATE, "node_query_ptr: the node was created without a query buffer (d = 0)");
+    *q_dev = n->block + n->lay.qx;
+    return CLDRD_OK;
+}
+
+int cldrd_node_spread_queries(cldrd_shard* s, cldrd_node* n, int64_t row0, int64_t nrows, void* cuda_stream) {
+    if (!s || !n || row0 < 0 || nrows < 0 || row0 + nrows > kQueryBatch)
+        return fail(CLDRD_EINVAL, "node_spread_queries: rows [%lld, +%lld) outside the batch", (long long)row0, (long long)nrows);
+    if (n->d == 0) return fail(CLDRD_ESTATE, "node_spread_queries: the node was created without a query buffer (d = 0)");
+    if (!s->finalized) return fail(CLDRD_ESTATE, "node_spread_queries: shard not finalized");
+    for (int p = 0; p < n->world; ++p)
+        if (!n->peer[p]) return fail(CLDRD_ESTATE, "node_spread_queries: rank %d is not attached", p);
+    DeviceGuard g(n->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (nrows > 0 && n->world > 1) {
+        const size_t off16 = size_t(row0) * n->d / 4, n16 = size_t(nrows) * n->d / 4;
+        const int blocks = int(std::min<size_t>((n16 + 255) / 256, size_t(s->num_sms) * 4));
+        node_spread_kernel<<<blocks, 256, 0, st>>>(node_ptrs(n, n->lay.qx), n->world, n->rank, off16, n16);
+        CU_TRY(cudaGetLastError());
+    }
+    // every rank's part has landed everywhere before anybody reads the batch.  (The counters the barrier reports into
+    // are reset by the search that follows, so a rank that never arrives shows up there as its first barrier.)
+    return node_barrier(s, n, st);
 }
 
 int cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** scores, void** ids) {

@@ -20,11 +20,12 @@ struct NodeLayout {
     size_t xkeys = 0;    // u64 [world][slice][cap_k]    re-scored lists of the queries this rank merges
     size_t res_d = 0;    // f32 [QB][cap_k]              merged scores (used on the rank that collects the result)
     size_t res_i = 0;    // i64 [QB][cap_k]              merged ids
+    size_t qx = 0;       // f32 [QB][d]                  the batch's queries: every rank uploads 1/G and stores it everywhere
     size_t total = 0;
     int64_t slice = 0;   // rows per plane of xkeys = ceil(QB / world)
 };
 
-__host__ inline NodeLayout node_layout(int world, int cap_k) {
+__host__ inline NodeLayout node_layout(int world, int cap_k, int d = 0) {
     NodeLayout l;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t QB = CLDRD_QUERY_BATCH, J = CLDRD_SEED_J;
@@ -38,6 +39,7 @@ __host__ inline NodeLayout node_layout(int world, int cap_k) {
     l.xkeys = o;  o = up(o + size_t(world) * size_t(l.slice) * size_t(cap_k) * 8);
     l.res_d = o;  o = up(o + QB * size_t(cap_k) * 4);
     l.res_i = o;  o = up(o + QB * size_t(cap_k) * 8);
+    l.qx = o;     o = up(o + QB * size_t(d) * 4);
     l.total = o;
     return l;
 }
@@ -262,6 +264,17 @@ __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
             os[i] = -FLT_MAX;
             oi[i] = -1;
         }
+    }
+}
+
+// Replicated queries without G uploads of the same bytes: this rank's part of the batch (uploaded host -> own block) is
+// stored into the same place of every other rank's block over NVLink.  16-byte vectors; n16 = number of float4.
+__global__ void node_spread_kernel(PeerPtrs qx, int world, int rank, size_t off16, size_t n16) {
+    const float4* src = static_cast<const float4*>(qx.p[rank]) + off16;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x) {
+        const float4 v = src[i];
+        for (int p = 0; p < world; ++p)
+            if (p != rank) (static_cast<float4*>(qx.p[p]) + off16)[i] = v;
     }
 }
 

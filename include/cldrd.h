@@ -191,8 +191,9 @@ int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k
 #define CLDRD_MAX_PEERS 16
 #define CLDRD_QUERY_BATCH 8192
 typedef struct cldrd_node cldrd_node;
-int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k);
-int  cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k);
+/* d > 0 adds a query buffer [CLDRD_QUERY_BATCH][d] float32 to the block (cldrd_node_spread_queries); 0 = none */
+int64_t cldrd_node_block_bytes(int32_t world, int32_t max_k, int32_t d);
+int  cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank, int32_t max_k, int32_t d);
 /* CLDRD_PEER_HANDLE_BYTES bytes to hand to the other processes (any byte transport) */
 int  cldrd_node_handle(const cldrd_node* n, void* out_handle);
 void* cldrd_node_block(const cldrd_node* n);
@@ -208,6 +209,13 @@ int  cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** scor
 int  cldrd_node_search_begin(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k,
                              int32_t seeded, float* out_scores, int64_t* out_ids,
                              const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream);
+/* Replicated queries from HOST memory without `world` uploads of the same bytes (index.search(x, k) hands over host
+ * arrays: retriever/retrieval_utils.py:135): every rank copies only rows [row0, row0 + nrows) of the batch -- its 1/world
+ * -- host -> cldrd_node_query_ptr() + row0*d floats, then calls cldrd_node_spread_queries, which stores that part into
+ * every other rank's query buffer over NVLink and ends in a barrier; afterwards cldrd_node_query_ptr() holds the whole
+ * batch on every rank and is what the rank passes as q_dev.  All ranks call it, before the batch's search_begin. */
+int  cldrd_node_query_ptr(const cldrd_node* n, void** q_dev);
+int  cldrd_node_spread_queries(cldrd_shard* s, cldrd_node* n, int64_t row0, int64_t nrows, void* cuda_stream);
 /* Output sets: several result buffers registered once per rank (count <= CLDRD_MAX_OUT_SETS; scores[j] / ids[j] are set
  * j's float32 / int64 [rows][k] arrays as THIS rank's GPU addresses them, e.g. sub-blocks of one shared page-locked
  * host mapping), so that the rank that hands results to the caller can pick, batch by batch, a buffer the caller no

@@ -80,10 +80,14 @@ def test_sharded_entry_points_validate_arguments(cldrd_lib):
     assert cldrd_lib.cldrd_host_register(None, 0) == _lib.E_INVAL
     assert cldrd_lib.cldrd_host_unregister(None) == 0
     n = C.c_void_p()
-    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 0, 0, 100) == _lib.E_INVAL              # world < 1
-    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 2, 100) == _lib.E_INVAL              # rank outside the world
-    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 0, _lib.MAX_K + 1) == _lib.E_INVAL
-    assert cldrd_lib.cldrd_node_block_bytes(17, 100) == 0 and cldrd_lib.cldrd_node_block_bytes(8, 1000) > 8 * 1024 * 1000 * 8
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 0, 0, 100, 0) == _lib.E_INVAL              # world < 1
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 2, 100, 0) == _lib.E_INVAL              # rank outside the world
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 0, _lib.MAX_K + 1, 0) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_create(C.byref(n), 0, 2, 0, 100, 770) == _lib.E_INVAL            # d not a multiple of 4
+    assert cldrd_lib.cldrd_node_block_bytes(17, 100, 0) == 0 and cldrd_lib.cldrd_node_block_bytes(8, 1000, 0) > 8 * 1024 * 1000 * 8
+    assert cldrd_lib.cldrd_node_block_bytes(8, 1000, 768) - cldrd_lib.cldrd_node_block_bytes(8, 1000, 0) == 8192 * 768 * 4
+    assert cldrd_lib.cldrd_node_spread_queries(None, None, 0, 1, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_query_ptr(None, None) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_search_begin(None, None, None, 1, 10, 1, None, None, None, None, None) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_search_end(None, None, None, None, 0) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_attach(None, 0, None, None, -1) == _lib.E_INVAL
