@@ -50,6 +50,31 @@ def read_run(path) -> Tuple[np.ndarray, List[np.ndarray]]:
     return qids, [np.asarray(l, dtype=np.int64) for l in lists]
 
 
+def rerank_with_teacher(qids: Sequence[int], ranked_pids: Sequence[np.ndarray], teacher_qids: Sequence[int],
+                        teacher_ranked: Sequence[np.ndarray], keep_unscored: bool = True) -> List[np.ndarray]:
+    """Teacher re-rank of the student's candidates before they are cut into groups (the "relT" lists of
+    dataset/nway_dataset.py:239-261 are ranked by the TEACHER).  The teacher's order comes as a run file, which is
+    what the reference's re-ranker writes: evaluation/reranking_evaluator.py:70-86 scores (query, passage) pairs and
+    evaluation/utils.py:145-159 (`write_rankdata`) sorts them by score and writes "qid\tpid\trank\tscore".
+    Per query: the student's candidates in teacher order; candidates the teacher did not score keep their student
+    order behind the scored ones (keep_unscored) or are dropped; passages only the teacher lists are ignored
+    (they were not retrieved).  A query the teacher file lacks keeps its student order."""
+    t_of = {int(q): np.asarray(l, dtype=np.int64) for q, l in zip(teacher_qids, teacher_ranked)}
+    out = []
+    for qid, ranked in zip(qids, ranked_pids):
+        ranked = np.asarray(ranked, dtype=np.int64)
+        t = t_of.get(int(qid))
+        if t is None:
+            out.append(ranked)
+            continue
+        cand = set(ranked[ranked >= 0].tolist())
+        scored = [p for p in t.tolist() if p in cand]
+        seen = set(scored)
+        rest = [p for p in ranked.tolist() if p >= 0 and p not in seen] if keep_unscored else []
+        out.append(np.asarray(scored + rest, dtype=np.int64))
+    return out
+
+
 def _window(ranked: np.ndarray, lo: int, hi: int) -> np.ndarray:
     return ranked[min(lo, ranked.shape[0]):min(hi, ranked.shape[0])]
 

@@ -2,7 +2,10 @@
 `NwayDataset.create_from_relT_most_semi_hard_file` (dataset/nway_dataset.py:213-261).
 
     python make_curriculum_groups.py --run_path top200.run --output_path groups.train.json --label_mode 9 \
-        [--qrels_path qrels.train.tsv] [--most_window 10,50] [--semi_window 50,200] [--seed 0]
+        [--teacher_run_path reranked.run] [--qrels_path qrels.train.tsv] [--most_window 10,50] [--semi_window 50,200] [--seed 0]
+
+--teacher_run_path: the file the reference's re-ranker writes for the same candidates (evaluation/reranking_evaluator.py
+-> evaluation/utils.py:write_rankdata): the student's top-200 are put into the teacher's order before they are cut.
 """
 import argparse
 import os
@@ -22,6 +25,7 @@ def get_args(argv=None):
     p.add_argument("--run_path", required=True, help="qid\\tpid\\trank\\tscore, ranked (retrieve_top_passages.py --top_k 200)")
     p.add_argument("--output_path", required=True)
     p.add_argument("--label_mode", default="9", choices=sorted(CU.LABEL_MODE_SHAPES, key=int))
+    p.add_argument("--teacher_run_path", default=None, help="qid\\tpid\\trank\\tscore sorted by the teacher's score (write_rankdata)")
     p.add_argument("--qrels_path", default=None, help="qid\\t0\\tpid\\trel (evaluation/retrieval_evaluator.py reads the same file)")
     p.add_argument("--most_window", default=None, type=_pair)
     p.add_argument("--semi_window", default=None, type=_pair)
@@ -42,6 +46,9 @@ def read_qrels(path):
 
 def main(args):
     qids, lists = CU.read_run(args.run_path)
+    if args.teacher_run_path:
+        t_qids, t_lists = CU.read_run(args.teacher_run_path)
+        lists = CU.rerank_with_teacher(qids, lists, t_qids, t_lists)
     qrels = read_qrels(args.qrels_path) if args.qrels_path else None
     ex = CU.groups_for_label_mode(qids, lists, args.label_mode, most_window=args.most_window,
                                   semi_window=args.semi_window, qrels=qrels, seed=args.seed,

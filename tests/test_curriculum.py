@@ -173,3 +173,52 @@ def test_in_memory_hand_off_matches_run_file_metrics(tmp_path):
     in_mem = in_mem[0] if isinstance(in_mem, tuple) else in_mem
     for key, v in from_file.items():
         assert in_mem[key] == v, key
+
+
+def _teacher_file(path, qids, lists, seed=11, drop_every=7):
+    """A teacher's scores for the student's candidates, written the way evaluation/utils.py:145-159 (write_rankdata)
+    writes them: per query sorted by score, "qid\\tpid\\trank\\tscore".  Every `drop_every`-th candidate is left unscored."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rank = {}
+    with open(path, "w") as f:
+        for q, l in zip(qids, lists):
+            scored = [(int(p), float(s)) for i, (p, s) in enumerate(zip(l, rng.standard_normal(len(l)))) if i % drop_every]
+            scored.sort(key=lambda x: x[1], reverse=True)
+            rank[int(q)] = [p for p, _ in scored]
+            for i, (p, s) in enumerate(scored):
+                f.write(f"{int(q)}\t{p}\t{i + 1}\t{s}\n")
+    return rank
+
+
+def test_teacher_rerank_orders_the_candidates_before_the_cut(tmp_path):
+    """f-4: groups are cut from the TEACHER's order of the student's top-200 (the reference's re-ranker output),
+    not from the student's own ranks."""
+    qids, lists = _ranked(nq=6)
+    teacher = _teacher_file(tmp_path / "teacher.run", qids[:5], lists[:5])       # the last query has no teacher scores
+    t_qids, t_lists = CU.read_run(tmp_path / "teacher.run")
+    rer = CU.rerank_with_teacher(qids, lists, t_qids, t_lists)
+    for q, l, r in zip(qids[:5], lists[:5], rer[:5]):
+        t = teacher[int(q)]
+        assert r[:len(t)].tolist() == t                                          # teacher order first
+        unscored = [int(p) for i, p in enumerate(l) if i % 7 == 0]
+        assert r[len(t):].tolist() == unscored                                   # then the rest in student order
+        assert sorted(r.tolist()) == sorted(l.tolist())
+    assert rer[5].tolist() == lists[5].tolist()
+    dropped = CU.rerank_with_teacher(qids, lists, t_qids, t_lists, keep_unscored=False)
+    assert dropped[0].tolist() == teacher[int(qids[0])]
+    ex = CU.build_groups(qids, rer, seed=0)
+    assert ex[0]["relT_pids"] == teacher[int(qids[0])][:10]
+    # through the CLI
+    run = tmp_path / "student.run"
+    with open(run, "w") as f:
+        for q, l in zip(qids, lists):
+            for i, p in enumerate(l):
+                f.write(f"{int(q)}\t{int(p)}\t{i + 1}\t{200.0 - i}\n")
+    spec = importlib.util.spec_from_file_location("mk2", os.path.join(ROOT, "cl-drd_b200", "retriever", "make_curriculum_groups.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    out = tmp_path / "groups.json"
+    mk.main(mk.get_args(["--run_path", str(run), "--teacher_run_path", str(tmp_path / "teacher.run"), "--output_path", str(out),
+                         "--label_mode", "9"]))
+    got = [json.loads(ln) for ln in out.read_text().splitlines()]
+    assert got == ex
