@@ -75,6 +75,7 @@ SIGNATURES = {
     "cldrd_node_search_begin_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "cldrd_node_search_end": (C.c_int, [C.c_void_p, C.c_void_p, _c_i32p, _c_i32p, C.c_int32]),
+    "cldrd_node_set_wait_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "cldrd_node_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "cldrd_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "cldrd_peer_free": (C.c_int, [C.c_int, C.c_void_p]),

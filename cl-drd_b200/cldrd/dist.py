@@ -447,6 +447,9 @@ class ShardedSearcher:
             if on_end is not None:
                 on_end(b0, min(_lib.QUERY_BATCH, n - b0), raised)
 
+        # several batches: the host runs ahead of the GPU anyway (RING batches queued), so the ranks sleep-poll instead of
+        # spinning and leave their cores to whatever consumes the batches (the run-file writer's formatting threads)
+        check(lib().cldrd_node_set_wait_mode(nx.handle, 1 if n > _lib.QUERY_BATCH else 0))
         t_host0 = time.perf_counter()
         with self.local._lock:
             for b0 in range(0, n, _lib.QUERY_BATCH):

@@ -1414,6 +1414,7 @@ struct cldrd_node {
         size_t ev_lo = 0, ev_hi = 0;
     } slot[kRing];
     int64_t seq_begin = 0, seq_end = 0;
+    int wait_mode = 0;                             // cldrd_node_set_wait_mode: 0 spin, 1 sleep-poll
     int out_sets = 0;                              // cldrd_node_set_outputs
     float* set_scores[CLDRD_MAX_OUT_SETS];
     long long* set_ids[CLDRD_MAX_OUT_SETS];
@@ -1807,6 +1808,16 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
     const int slot = int(n->seq_end % cldrd_node::kRing);
     const cldrd_node::Slot& sl = n->slot[slot];
     n->seq_end++;
+    if (n->wait_mode == 1) {
+        // long searches with host work going on beside them (the run-file writer formats batch i on all cores while
+        // batch i+1 is scanned): do not burn a core per rank spinning on the event
+        for (;;) {
+            cudaError_t q = cudaEventQuery(n->done[slot]);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return fail(CLDRD_ECUDA, "node_search_end: %s", cudaGetErrorString(q));
+            usleep(100);
+        }
+    }
     CU_TRY(cudaEventSynchronize(n->done[slot]));
     const BatchStatus& hs = n->h_status[slot];
     if (hs.stats[ST_KERNEL_ERR] >= kErrBarrierTimeout)
@@ -1850,6 +1861,12 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
     if (nfail_out) *nfail_out = nfail;
     if (fail_idx_out)
         for (int i = 0; i < nfail && i < cap; ++i) fail_idx_out[i] = hs.idx[i];
+    return CLDRD_OK;
+}
+
+int cldrd_node_set_wait_mode(cldrd_node* n, int32_t mode) {
+    if (!n || mode < 0 || mode > 1) return fail(CLDRD_EINVAL, "node_set_wait_mode: mode 0 (spin) or 1 (sleep-poll)");
+    n->wait_mode = mode;
     return CLDRD_OK;
 }
 

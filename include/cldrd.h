@@ -232,6 +232,9 @@ int  cldrd_node_search_begin_set(cldrd_shard* s, cldrd_node* n, const float* q_d
  * its queries have to be searched again (the same on every rank) and their batch indices, ascending. */
 int  cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int32_t* fail_idx_out,
                            int32_t cap);
+/* How cldrd_node_search_end waits: 0 (default) spins on the batch's event (lowest latency: one batch, nothing else to
+ * do); 1 polls it every 100 us, leaving the core to host work that runs beside a long search (run-file writer). */
+int  cldrd_node_set_wait_mode(cldrd_node* n, int32_t mode);
 /* device milliseconds of the last ended batch: [0] prep + sample + barrier + levels, [1] scan + select,
  * [2] counts + barrier + re-score/scatter, [3] barrier + merge/store, [4] barrier + status,
  * [5] device idle on this stream between the end of the previous batch and the start of this one */
