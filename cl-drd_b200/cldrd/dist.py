@@ -125,10 +125,10 @@ class _NodeExchange:
         return d.value, i.value
 
     def phase_ms(self) -> dict:
-        arr = (C.c_double * 6)()
+        arr = (C.c_double * 7)()
         check(lib().cldrd_node_phase_ms(self.handle, arr))
         return dict(zip(["sample+barrier+levels", "scan+select", "counts+barrier+rescore", "barrier+merge+store",
-                         "barrier+status", "idle_before_batch"], list(arr)))
+                         "barrier+status", "idle_before_batch", "of_which_counts+barrier"], list(arr)))
 
     def close(self):
         """Collective: every rank unmaps its peers before anybody frees."""

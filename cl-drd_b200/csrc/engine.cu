@@ -1406,7 +1406,7 @@ struct cldrd_node {
     BatchStatus* h_status = nullptr;               // page-locked [kRing], written by node_tail_kernel
     BatchStatus* d_status = nullptr;               // the same memory as the device addresses it
     cudaEvent_t done[kRing];
-    cudaEvent_t phase[kRing][6];
+    cudaEvent_t phase[kRing][7];                   // [6]: after the counts barrier (splits phase 2)
     struct Slot {
         int nq = 0, k = 0;
         bool seeded = false;
@@ -1418,7 +1418,7 @@ struct cldrd_node {
     int out_sets = 0;                              // cldrd_node_set_outputs
     float* set_scores[CLDRD_MAX_OUT_SETS];
     long long* set_ids[CLDRD_MAX_OUT_SETS];
-    double phase_ms[6] = {0, 0, 0, 0, 0, 0};   // [5]: device idle between the previous batch and this one
+    double phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};   // [5]: device idle before this batch, [6]: counts + barrier part of [2]
 };
 
 namespace {
@@ -1497,7 +1497,7 @@ int cldrd_node_create(cldrd_node** out, int device, int32_t world, int32_t rank,
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&n->d_status), n->h_status, 0);
     for (int i = 0; i < cldrd_node::kRing && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&n->done[i], cudaEventDisableTiming);
-        for (int j = 0; j < 6 && e == cudaSuccess; ++j) e = cudaEventCreate(&n->phase[i][j]);
+        for (int j = 0; j < 7 && e == cudaSuccess; ++j) e = cudaEventCreate(&n->phase[i][j]);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1564,7 +1564,7 @@ void cldrd_node_destroy(cldrd_node* n) {
     DeviceGuard g(n->device);
     for (int i = 0; i < cldrd_node::kRing; ++i) {
         cudaEventDestroy(n->done[i]);
-        for (int j = 0; j < 6; ++j) cudaEventDestroy(n->phase[i][j]);
+        for (int j = 0; j < 7; ++j) cudaEventDestroy(n->phase[i][j]);
     }
     if (n->h_status) cudaFreeHost(n->h_status);
     cudaFree(n->block);
@@ -1684,11 +1684,13 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
                                                                 size_t(rank) * plane);
         CU_TRY(cudaGetLastError());
         if ((rc = node_barrier(s, n, st))) return rc;
+        CU_TRY(cudaEventRecord(n->phase[slot][6], st));
         extra += 4;
     } else {
         CU_TRY(cudaEventRecord(n->phase[slot][1], st));
         if ((rc = run_chunks(c, PASS_PROGRESSIVE))) return rc;   // (host-synchronous: sizes its chunks from the first piece)
         CU_TRY(cudaEventRecord(n->phase[slot][2], st));
+        CU_TRY(cudaEventRecord(n->phase[slot][6], st));
     }
     // 3. exact re-score of what can still reach the global top-k; every list goes to the rank that merges the query
     const int64_t slice = (nq + world - 1) / world;
@@ -1830,6 +1832,11 @@ int cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, int
         if (cudaEventElapsedTime(&ms, n->phase[slot][i], n->phase[slot][i + 1]) != cudaSuccess) cudaGetLastError();
         n->phase_ms[i] = ms;
     }
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, n->phase[slot][2], n->phase[slot][6]) != cudaSuccess) cudaGetLastError();
+        n->phase_ms[6] = ms;
+    }
     n->phase_ms[5] = 0.0;
     if (n->seq_end >= 2) {   // (seq_end was advanced above) the batch before this one: end of its status kernel -> our start
         const int prev = int((n->seq_end - 2) % cldrd_node::kRing);
@@ -1870,9 +1877,9 @@ int cldrd_node_set_wait_mode(cldrd_node* n, int32_t mode) {
     return CLDRD_OK;
 }
 
-int cldrd_node_phase_ms(const cldrd_node* n, double out[6]) {
+int cldrd_node_phase_ms(const cldrd_node* n, double out[7]) {
     if (!n || !out) return fail(CLDRD_EINVAL, "node_phase_ms: NULL");
-    for (int i = 0; i < 6; ++i) out[i] = n->phase_ms[i];
+    for (int i = 0; i < 7; ++i) out[i] = n->phase_ms[i];
     return CLDRD_OK;
 }
 

@@ -237,8 +237,9 @@ int  cldrd_node_search_end(cldrd_shard* s, cldrd_node* n, int32_t* nfail_out, in
 int  cldrd_node_set_wait_mode(cldrd_node* n, int32_t mode);
 /* device milliseconds of the last ended batch: [0] prep + sample + barrier + levels, [1] scan + select,
  * [2] counts + barrier + re-score/scatter, [3] barrier + merge/store, [4] barrier + status,
- * [5] device idle on this stream between the end of the previous batch and the start of this one */
-int  cldrd_node_phase_ms(const cldrd_node* n, double out[6]);
+ * [5] device idle on this stream between the end of the previous batch and the start of this one,
+ * [6] the part of [2] before the re-score starts (count kernel + waiting for the slowest rank's scan) */
+int  cldrd_node_phase_ms(const cldrd_node* n, double out[7]);
 
 /* Device memory that other processes of the node can map (the node blocks above are made of it).
  * cldrd_peer_alloc: cudaMalloc + an opaque CLDRD_PEER_HANDLE_BYTES handle to hand to the peers (any byte transport;
