@@ -342,9 +342,16 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
         return;
     }
     for (int i = tid; i < p.d; i += blockDim.x) q_s[i] = p.q[size_t(q) * p.d + i];
+    // the candidate list comes into shared memory in one coalesced sweep (a warp that fetched its entries one by one
+    // from global memory paid a dependent-load latency per entry: with the short lists of a many-shard search that
+    // was as long as the row gather itself)
+    const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
+    for (int i = tid; i < L; i += blockDim.x) keys[i] = my_list[i];
+    constexpr int kRankSortMax = 512;       // up to here one counting pass beats log^2(n) barrier-separated bitonic passes
     int n_pad = 2;
     while (n_pad < L) n_pad <<= 1;
-    for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
+    if (L > kRankSortMax)
+        for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
     __shared__ int s_kept;
     __shared__ uint32_t s_cut;
     if (tid == 0) {
@@ -366,50 +373,71 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
         }
     }
     __syncthreads();
-    const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const uint32_t cut_ord = s_cut;
     int kept = 0;
-    for (int i = warp; i < L; i += nwarps) {
-        const uint64_t cand = my_list[i];
+    for (int i = warp; i < L; i += nwarps) {     // entry i is read and rewritten by the same warp
+        const uint64_t cand = keys[i];
         if (key_ord(cand) < cut_ord) {   // warp-uniform
+            __syncwarp();
             if (lane == 0) keys[i] = 0;
             continue;
         }
         const uint32_t row = key_row(cand);
         float s = exact_dot_warp(q_s, p.xb + size_t(row) * p.d, p.d, p.vec4 != 0, lane);
+        __syncwarp();
         if (lane == 0) keys[i] = make_key(s, row);
         ++kept;
     }
     if (lane == 0 && kept) atomicAdd(&s_kept, kept);
     __syncthreads();
-    L = s_kept;                      // dropped entries are zero keys: they sort behind the kept ones
+    const int n_all = L;             // entries in shared memory: exact keys, zero where an entry was dropped
+    L = s_kept;                      // zero keys order behind every kept one
     if (tid == 0) atomicAdd(&p.stats[ST_RESCORED], (unsigned long long)L);
-    block_bitonic_desc(keys, n_pad);
     const size_t orow = p.out_index ? size_t(p.out_index[q]) : size_t(q);
+    uint64_t* ok = nullptr;
+    float* os = nullptr;
+    int64_t* oi = nullptr;
     if (p.sc_world > 0) {
         const long long Q = p.q_base + (long long)orow;
         const int dest = int(Q / p.sc_slice);
-        uint64_t* ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
-                       (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
-        for (int i = tid; i < p.k; i += blockDim.x) {
-            uint64_t key = 0;
-            if (i < L) {
-                key = keys[i];
-                key = (key & 0xFFFFFFFF00000000ull) | uint64_t(~(uint32_t(p.row0) + key_row(key)));
-            }
-            ok[i] = key;
-        }
-        return;
+        ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
+             (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
+    } else {
+        os = p.out_scores + orow * p.k;
+        oi = p.out_ids + orow * p.k;
     }
-    float* os = p.out_scores + orow * p.k;
-    int64_t* oi = p.out_ids + orow * p.k;
-    for (int i = tid; i < p.k; i += blockDim.x) {
-        if (i < L) {
-            uint64_t key = keys[i];
-            uint32_t row = key_row(key);
-            os[i] = ord2f(key_ord(key));
-            oi[i] = p.ids ? p.ids[row] : (p.row0 + int64_t(row));
+    // entry `key` goes to position r of the sorted output (r < k)
+    auto emit = [&](int r, uint64_t key) {
+        const uint32_t row = key_row(key);
+        if (ok) {
+            ok[r] = (key & 0xFFFFFFFF00000000ull) | uint64_t(~(uint32_t(p.row0) + row));
+        } else {
+            os[r] = ord2f(key_ord(key));
+            oi[r] = p.ids ? p.ids[row] : (p.row0 + int64_t(row));
+        }
+    };
+    if (n_all <= kRankSortMax) {
+        // short list: every thread ranks its entry against all others (keys are distinct: one row, one key) and stores
+        // it at its rank -- one pass over shared memory instead of ~40 barrier-separated compare-exchange passes
+        for (int i = tid; i < n_all; i += blockDim.x) {
+            const uint64_t key = keys[i];
+            if (key == 0) continue;
+            int r = 0;
+#pragma unroll 8
+            for (int j = 0; j < n_all; ++j) {
+                const uint64_t x = keys[j];
+                r += (x > key) || (x == key && j < i);
+            }
+            if (r < p.k) emit(r, key);
+        }
+    } else {
+        block_bitonic_desc(keys, n_pad);
+        for (int i = tid; i < min(L, p.k); i += blockDim.x) emit(i, keys[i]);
+    }
+    for (int i = L + tid; i < p.k; i += blockDim.x) {   // padding behind the list
+        if (ok) {
+            ok[i] = 0;
         } else {
             os[i] = -FLT_MAX;
             oi[i] = -1;
