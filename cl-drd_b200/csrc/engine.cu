@@ -186,6 +186,7 @@ struct cldrd_shard {
         int key_stride = 0;
         bool raise_fail = false;
         PeerPtrs keys;
+        PeerPtrs len;
         PeerPtrs qfail;
     } sc;
 
@@ -647,6 +648,7 @@ int launch_rescore(BatchCtx& c, float* out_scores, int64_t* out_ids, bool transl
         p.sc_key_stride = s->sc.key_stride;
         p.sc_raise_fail = s->sc.raise_fail ? 1 : 0;
         p.sc_keys = s->sc.keys;
+        p.sc_len = s->sc.len;
         p.sc_qfail = s->sc.qfail;
     }
     const size_t smem = size_t(p.n_pad) * 8 + size_t(s->d) * 4 + 16;
@@ -1700,6 +1702,7 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
     s->sc.key_stride = n->cap_k;
     s->sc.raise_fail = sd;
     s->sc.keys = node_ptrs(n, n->lay.xkeys);
+    s->sc.len = node_ptrs(n, n->lay.xlen);
     s->sc.qfail = node_ptrs(n, n->lay.qfail);
     CountedCut cc;
     cc.planes = reinterpret_cast<const int*>(n->block + n->lay.counts);
@@ -1729,6 +1732,7 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
     if (n_mine > 0) {
         MergeKeysParams m{};
         m.xkeys = reinterpret_cast<const uint64_t*>(n->block + n->lay.xkeys);
+        m.xlen = reinterpret_cast<const int*>(n->block + n->lay.xlen);
         m.parts = world;
         m.slice = slice;
         m.key_stride = n->cap_k;

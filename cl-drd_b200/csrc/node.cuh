@@ -18,6 +18,7 @@ struct NodeLayout {
     size_t topj = 0;     // f32 [world][QB][J]           sample scores, plane p written by rank p
     size_t counts = 0;   // i32 [world][QB][J]           candidates above each level, plane p written by rank p
     size_t xkeys = 0;    // u64 [world][slice][cap_k]    re-scored lists of the queries this rank merges
+    size_t xlen = 0;     // i32 [world][slice]           how many keys of each list are valid (the rest is stale)
     size_t res_d = 0;    // f32 [QB][cap_k]              merged scores (used on the rank that collects the result)
     size_t res_i = 0;    // i64 [QB][cap_k]              merged ids
     size_t qx = 0;       // f32 [QB][d]                  the batch's queries: every rank uploads 1/G and stores it everywhere
@@ -37,6 +38,7 @@ __host__ inline NodeLayout node_layout(int world, int cap_k, int d = 0) {
     l.topj = o;   o = up(o + size_t(world) * QB * J * 4);
     l.counts = o; o = up(o + size_t(world) * QB * J * 4);
     l.xkeys = o;  o = up(o + size_t(world) * size_t(l.slice) * size_t(cap_k) * 8);
+    l.xlen = o;   o = up(o + size_t(world) * size_t(l.slice) * 4);
     l.res_d = o;  o = up(o + QB * size_t(cap_k) * 4);
     l.res_i = o;  o = up(o + QB * size_t(cap_k) * 8);
     l.qx = o;     o = up(o + QB * size_t(d) * 4);
@@ -172,6 +174,7 @@ __global__ void count_levels_peers_kernel(const uint64_t* list, const int* list_
 // page-locked host memory over PCIe).  One CTA per query.  dyn smem: keys[parts*k] u64 | top[k_pad] u64
 struct MergeKeysParams {
     const uint64_t* xkeys;     // [parts][slice][key_stride]
+    const int* xlen;           // [parts][slice] valid keys per list
     int parts;
     long long slice;
     int key_stride;
@@ -204,17 +207,21 @@ __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
     const long long r = blockIdx.x;
     const long long Q = p.q_lo + r;
     const int tid = threadIdx.x;
-    const int n_in = p.parts * p.k;
     if (tid == 0) {
         s_n = 0;
         s_out = 0;
     }
     for (int i = tid; i < p.k_pad; i += blockDim.x) top[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n_in; i += blockDim.x) {
-        const int part = i / p.k, j = i - part * p.k;
-        const uint64_t key = p.xkeys[(size_t(part) * size_t(p.slice) + size_t(r)) * size_t(p.key_stride) + j];
-        if (key != 0) keys[atomicAdd(&s_n, 1)] = key;
+    // only the valid prefix of every shard's list is read (a shard of a G-GPU search sends about k / G keys)
+    for (int part = 0; part < p.parts; ++part) {
+        const size_t row = size_t(part) * size_t(p.slice) + size_t(r);
+        const int len = min(max(p.xlen[row], 0), p.k);
+        const uint64_t* src = p.xkeys + row * size_t(p.key_stride);
+        for (int j = tid; j < len; j += blockDim.x) {
+            const uint64_t key = src[j];
+            if (key != 0) keys[atomicAdd(&s_n, 1)] = key;
+        }
     }
     __syncthreads();
     const int n = s_n;

@@ -311,6 +311,7 @@ struct RescoreParams {
     int sc_key_stride;
     int sc_raise_fail;    // a query this shard could not finish is raised in every rank's qfail (seeded batches)
     PeerPtrs sc_keys;
+    PeerPtrs sc_len;      // i32 [world][slice]: number of valid keys of each list (only those are stored)
     PeerPtrs sc_qfail;
 };
 
@@ -334,9 +335,8 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
             // the merging rank gets an empty list, and every rank learns that the query has to be searched again
             const long long Q = p.q_base + (long long)(p.out_index ? p.out_index[q] : q);
             const int dest = int(Q / p.sc_slice);
-            uint64_t* ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
-                           (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
-            for (int i = tid; i < p.k; i += blockDim.x) ok[i] = 0;
+            if (tid == 0)
+                static_cast<int*>(p.sc_len.p[dest])[size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)] = 0;
             if (tid < p.sc_world) static_cast<int*>(p.sc_qfail.p[tid])[Q] = 1;
         }
         return;
@@ -401,8 +401,9 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     if (p.sc_world > 0) {
         const long long Q = p.q_base + (long long)orow;
         const int dest = int(Q / p.sc_slice);
-        ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) +
-             (size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice)) * size_t(p.sc_key_stride);
+        const size_t at = size_t(p.sc_rank) * size_t(p.sc_slice) + size_t(Q - dest * p.sc_slice);
+        ok = static_cast<uint64_t*>(p.sc_keys.p[dest]) + at * size_t(p.sc_key_stride);
+        if (tid == 0) static_cast<int*>(p.sc_len.p[dest])[at] = min(L, p.k);   // only the valid prefix travels
     } else {
         os = p.out_scores + orow * p.k;
         oi = p.out_ids + orow * p.k;
@@ -435,10 +436,8 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
         block_bitonic_desc(keys, n_pad);
         for (int i = tid; i < min(L, p.k); i += blockDim.x) emit(i, keys[i]);
     }
-    for (int i = L + tid; i < p.k; i += blockDim.x) {   // padding behind the list
-        if (ok) {
-            ok[i] = 0;
-        } else {
+    if (!ok) {
+        for (int i = L + tid; i < p.k; i += blockDim.x) {   // padding behind the list
             os[i] = -FLT_MAX;
             oi[i] = -1;
         }
