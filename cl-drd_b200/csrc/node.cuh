@@ -171,7 +171,7 @@ __global__ void count_levels_peers_kernel(const uint64_t* list, const int* list_
 // u64 key order as the single-shard search, so the result is bit-identical to it; the seed check of the seeded
 // search (k-th merged score >= seed + eps, else the query is raised in every rank's qfail) and the id_map gather are
 // fused in; the rows go wherever the caller's pointers lead (own HBM, the collecting rank's HBM over NVLink, or
-// page-locked host memory over PCIe).  One CTA per query.  dyn smem: keys[parts*k] u64 | top[k_pad] u64
+// page-locked host memory over PCIe).  One CTA per query.  dyn smem: keys[parts*k] u64 | top[k] u64
 struct MergeKeysParams {
     const uint64_t* xkeys;     // [parts][slice][key_stride]
     const int* xlen;           // [parts][slice] valid keys per list
@@ -200,56 +200,28 @@ struct MergeKeysParams {
 __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
-    uint64_t* top = keys + size_t(p.parts) * p.k;
-    __shared__ uint32_t hist[256];
-    __shared__ uint64_t bcast[2];
-    __shared__ int s_n, s_out;
+    uint64_t* top = keys + size_t(p.parts) * p.k;      // [k] the merged order, staged so that the stores go out coalesced
+    __shared__ int s_off[CLDRD_MAX_PEERS + 1];
     const long long r = blockIdx.x;
     const long long Q = p.q_lo + r;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_n = 0;
-        s_out = 0;
-    }
-    for (int i = tid; i < p.k_pad; i += blockDim.x) top[i] = 0;
-    __syncthreads();
     // only the valid prefix of every shard's list is read (a shard of a G-GPU search sends about k / G keys)
-    for (int part = 0; part < p.parts; ++part) {
-        const size_t row = size_t(part) * size_t(p.slice) + size_t(r);
-        const int len = min(max(p.xlen[row], 0), p.k);
-        const uint64_t* src = p.xkeys + row * size_t(p.key_stride);
-        for (int j = tid; j < len; j += blockDim.x) {
-            const uint64_t key = src[j];
-            if (key != 0) keys[atomicAdd(&s_n, 1)] = key;
+    if (tid == 0) {
+        int o = 0;
+        for (int part = 0; part < p.parts; ++part) {
+            s_off[part] = o;
+            o += min(max(p.xlen[size_t(part) * size_t(p.slice) + size_t(r)], 0), p.k);
         }
+        s_off[p.parts] = o;
     }
     __syncthreads();
-    const int n = s_n;
-    int m = n;
-    if (n > p.k) {
-        const uint64_t kth = block_radix_select<64>(keys, n, p.k, hist, bcast);   // keys are distinct
-        for (int i = tid; i < n; i += blockDim.x) {
-            const uint64_t key = keys[i];
-            if (key >= kth) {
-                const int slot = atomicAdd(&s_out, 1);
-                if (slot < p.k) top[slot] = key;
-            }
-        }
-        m = p.k;
-    } else {
-        for (int i = tid; i < n; i += blockDim.x) top[i] = keys[i];
+    const int n = s_off[p.parts];
+    for (int part = 0; part < p.parts; ++part) {
+        const int lo = s_off[part], len = s_off[part + 1] - lo;
+        const uint64_t* src = p.xkeys + (size_t(part) * size_t(p.slice) + size_t(r)) * size_t(p.key_stride);
+        for (int j = tid; j < len; j += blockDim.x) keys[lo + j] = src[j];
     }
-    int n_pad = 2;
-    while (n_pad < m) n_pad <<= 1;
-    block_bitonic_desc(top, n_pad);
-    if (tid == 0 && p.seed) {
-        const float s0 = p.seed[Q];
-        if (s0 != -INFINITY) {
-            const float kth = m >= p.k ? ord2f(key_ord(top[p.k - 1])) : -FLT_MAX;
-            if (!(kth >= s0 + 0.5f * p.band[Q] * 1.0001f))
-                for (int w = 0; w < p.world; ++w) static_cast<int*>(p.qfail.p[w])[Q] = 1;
-        }
-    }
+    __syncthreads();
     size_t orow = p.out_rows ? size_t(p.out_rows[Q]) : size_t(Q);
     float* os = p.out_scores;
     long long* oi = p.out_ids;
@@ -261,13 +233,48 @@ __global__ void __launch_bounds__(512) merge_keys_kernel(MergeKeysParams p) {
     }
     os += orow * p.k;
     oi += orow * p.k;
+    const float s0 = p.seed ? p.seed[Q] : -INFINITY;
+    auto check_seed = [&](float kth) {     // k-th merged score must clear seed + eps, else the query is searched again
+        if (s0 != -INFINITY && !(kth >= s0 + 0.5f * p.band[Q] * 1.0001f))
+            for (int w = 0; w < p.world; ++w) static_cast<int*>(p.qfail.p[w])[Q] = 1;
+    };
+    // Every list arrives sorted (best first), so a key's place in the merged order is its place in its own list plus,
+    // for every other list, the number of keys there that order before it: one binary search per other list instead of
+    // a select and a sort.  Equal keys of different shards (cannot happen: rows are distinct) would go lower shard first.
+    for (int i = tid; i < n; i += blockDim.x) {
+        int part = 0;
+        while (i >= s_off[part + 1]) ++part;
+        const uint64_t key = keys[i];
+        int rank = i - s_off[part];
+        for (int o = 0; o < p.parts; ++o) {
+            if (o == part) continue;
+            int lo = s_off[o], hi = s_off[o + 1];
+            const int base = lo;
+            while (lo < hi) {              // first index whose key does NOT order before `key`
+                const int mid = (lo + hi) >> 1;
+                const uint64_t x = keys[mid];
+                if (x > key || (x == key && o < part)) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo - base;
+        }
+        if (rank < p.k) {
+            top[rank] = key;
+            if (rank == p.k - 1) check_seed(ord2f(key_ord(key)));
+        }
+    }
+    if (n < p.k && tid == 0) check_seed(-FLT_MAX);
+    __syncthreads();
+    // consecutive threads store consecutive entries: the destination may be the collecting rank's HBM over NVLink or
+    // page-locked host memory over PCIe, where scattered 4- and 8-byte stores would each travel as their own packet
+    const int m = min(n, p.k);
     for (int i = tid; i < p.k; i += blockDim.x) {
-        const uint64_t key = i < m ? top[i] : 0ull;
-        if (key != 0) {
+        if (i < m) {
+            const uint64_t key = top[i];
             const uint32_t row = key_row(key);
             os[i] = ord2f(key_ord(key));
             oi[i] = p.id_map ? p.id_map[row] : (long long)row;
-        } else {
+        } else {                                        // fewer than k rows in the whole index
             os[i] = -FLT_MAX;
             oi[i] = -1;
         }

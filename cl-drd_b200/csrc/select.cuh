@@ -348,9 +348,10 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
     const uint64_t* my_list = p.list + size_t(q) * p.keep_cap;
     for (int i = tid; i < L; i += blockDim.x) keys[i] = my_list[i];
     constexpr int kRankSortMax = 512;       // up to here one counting pass beats log^2(n) barrier-separated bitonic passes
+    const bool rank_sort = L <= kRankSortMax && p.n_pad >= 2 * kRankSortMax;
     int n_pad = 2;
     while (n_pad < L) n_pad <<= 1;
-    if (L > kRankSortMax)
+    if (!rank_sort)
         for (int i = L + tid; i < n_pad; i += blockDim.x) keys[i] = 0;  // sorts last
     __shared__ int s_kept;
     __shared__ uint32_t s_cut;
@@ -418,9 +419,11 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
             oi[r] = p.ids ? p.ids[row] : (p.row0 + int64_t(row));
         }
     };
-    if (n_all <= kRankSortMax) {
-        // short list: every thread ranks its entry against all others (keys are distinct: one row, one key) and stores
-        // it at its rank -- one pass over shared memory instead of ~40 barrier-separated compare-exchange passes
+    if (rank_sort) {
+        // short list: every thread ranks its entry against all others (keys are distinct: one row, one key) and puts
+        // it at its rank -- one pass over shared memory instead of ~40 barrier-separated compare-exchange passes.  The
+        // ranked order is staged behind the list (keep_cap >= 2 * kRankSortMax) so that the stores go out coalesced.
+        uint64_t* sorted = keys + kRankSortMax;
         for (int i = tid; i < n_all; i += blockDim.x) {
             const uint64_t key = keys[i];
             if (key == 0) continue;
@@ -430,8 +433,10 @@ __global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
                 const uint64_t x = keys[j];
                 r += (x > key) || (x == key && j < i);
             }
-            if (r < p.k) emit(r, key);
+            sorted[r] = key;
         }
+        __syncthreads();
+        for (int i = tid; i < min(L, p.k); i += blockDim.x) emit(i, sorted[i]);
     } else {
         block_bitonic_desc(keys, n_pad);
         for (int i = tid; i < min(L, p.k); i += blockDim.x) emit(i, keys[i]);
