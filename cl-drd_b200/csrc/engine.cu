@@ -1968,6 +1968,23 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
     // outputs that already live in pinned memory (cldrd_host_alloc) are written by the DMA engine
     // directly; pageable ones go through a pinned staging buffer
     const bool direct_out = is_pinned_host(out_scores_host) && is_pinned_host(out_ids_host);
+    // ... and when the GPU can address them (cldrd_host_alloc maps them), the re-score kernel stores the rows there
+    // itself: the 12 bytes per hit cross PCIe while the kernel is still gathering, instead of in a copy behind it
+    float* map_D = nullptr;
+    int64_t* map_I = nullptr;
+    static const bool host_direct = [] {
+        const char* e = getenv("CLDRD_HOST_DIRECT");
+        return !e || atoi(e) != 0;
+    }();
+    if (direct_out && host_direct) {
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&map_D), out_scores_host, 0) != cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void**>(&map_I), out_ids_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            map_D = nullptr;
+            map_I = nullptr;
+        }
+    }
+    const bool stores_direct = map_D && map_I;
     if (qbytes > s->d_q_bytes) {
         cudaFree(s->d_q);
         s->d_q = nullptr;
@@ -1985,7 +2002,7 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
         CU_TRY(cudaHostAlloc(&s->h_I, oelems * sizeof(int64_t), cudaHostAllocDefault));
         s->h_out_elems = oelems;
     }
-    if (oelems > s->d_out_elems) {
+    if (!stores_direct && oelems > s->d_out_elems) {
         cudaFree(s->d_D);
         cudaFree(s->d_I);
         s->d_D = nullptr;
@@ -1998,6 +2015,10 @@ int cldrd_search_host(cldrd_shard* s, const float* q_host, int64_t nq, int32_t k
     cudaStream_t st = cudaStreamPerThread;
     // pageable or pinned: the runtime stages pageable sources itself
     CU_TRY(cudaMemcpyAsync(s->d_q, q_host, qbytes, cudaMemcpyHostToDevice, st));
+    if (stores_direct) {
+        int rc = cldrd_search_dev(s, s->d_q, nq, k, 1, map_D, map_I, st);   // synchronises the stream before it returns
+        return rc;
+    }
     int rc = cldrd_search_dev(s, s->d_q, nq, k, 1, s->d_D, s->d_I, st);
     if (rc) return rc;
     float* dst_D = direct_out ? out_scores_host : s->h_D;
