@@ -583,7 +583,7 @@ class GpuIndexShards:
         try:
             for r, sh in enumerate(self._shards):
                 h = C.c_void_p()
-                check(lib().cldrd_node_create(C.byref(h), sh.device, G, r, int(k), 0))
+                check(lib().cldrd_node_create(C.byref(h), sh.device, G, r, int(k), self.d if self.d % 4 == 0 else 0))
                 self._nodes.append(h)
             for r, sh in enumerate(self._shards):
                 for p, other in enumerate(self._shards):
@@ -612,13 +612,15 @@ class GpuIndexShards:
         return again
 
     def _run(self, qs, n: int, k: int, seeded: bool, outs, out_rows=None):
-        """qs[i]: the queries on shard i's device; outs[i]: (scores, ids) base addresses as shard i's device sees the
-        output arrays; out_rows[i]: optional int32 device tensor with the output row of every query."""
+        """qs[i]: the queries on shard i's device (a tensor, or a callable (b0, nb) -> device address that may enqueue
+        whatever brings the batch there); outs[i]: (scores, ids) base addresses as shard i's device sees the output
+        arrays; out_rows[i]: optional int32 device tensor with the output row of every query."""
         inflight, again = [], []
         for b0 in range(0, n, _lib.QUERY_BATCH):
             nb = min(_lib.QUERY_BATCH, n - b0)
             if len(inflight) >= self.RING:
                 again += self._end_all(inflight.pop(0))
+            qptr = [qs[i](b0, nb) if callable(qs[i]) else qs[i][b0:b0 + nb].data_ptr() for i in range(len(self._shards))]
             for i, (sh, node) in enumerate(zip(self._shards, self._nodes)):
                 oD, oI = outs[i]
                 if out_rows is None:
@@ -626,7 +628,7 @@ class GpuIndexShards:
                 else:
                     rows = C.c_void_p(out_rows[i][b0:b0 + nb].data_ptr())
                 idm = C.c_void_p(self._id_maps[i].data_ptr()) if self._id_maps[i] is not None else None
-                check(lib().cldrd_node_search_begin(sh.handle, node, C.c_void_p(qs[i][b0:b0 + nb].data_ptr()), nb, k,
+                check(lib().cldrd_node_search_begin(sh.handle, node, C.c_void_p(qptr[i]), nb, k,
                                                     1 if seeded else 0, C.c_void_p(oD), C.c_void_p(oI), rows, idm,
                                                     C.c_void_p(self._streams[i].cuda_stream)))
             inflight.append(b0)
@@ -650,19 +652,47 @@ class GpuIndexShards:
             return D, I
         with self._lock:
             self._ensure_nodes(k)
-            # one upload (none for device-resident embeddings), then NVLink copies to the other shards
-            q0 = x.to(self._devs[0]) if on_dev else torch.from_numpy(x).to(self._devs[0])
-            torch.cuda.current_stream(q0.device).synchronize()
+            G = len(self._shards)
+            spread = (not on_dev) and self.d % 4 == 0 and G > 1
             qs, outs = [], []
+            if spread:
+                # host queries: every device uploads 1/G of the batch over its own PCIe link into its exchange block and
+                # stores it into the other blocks over NVLink (cldrd_node_spread_queries) -- not G uploads of the same bytes
+                row_bytes, src = self.d * 4, x.ctypes.data
+
+                def make_src(i):
+                    sh, node, dv = self._shards[i], self._nodes[i], self._devs[i]
+                    qx = C.c_void_p()
+                    check(lib().cldrd_node_query_ptr(node, C.byref(qx)))
+                    st = C.c_void_p(self._streams[i].cuda_stream)
+
+                    def q_src(b0, nb):
+                        sl = (nb + G - 1) // G
+                        lo = min(nb, i * sl)
+                        hi = min(nb, lo + sl)
+                        if hi > lo:
+                            check(lib().cldrd_peer_copy(dv.index, C.c_void_p(qx.value + lo * row_bytes),
+                                                        C.c_void_p(src + (b0 + lo) * row_bytes), (hi - lo) * row_bytes, st))
+                        check(lib().cldrd_node_spread_queries(sh.handle, node, lo, hi - lo, st))
+                        return qx.value
+                    return q_src
+
+                qs = [make_src(i) for i in range(G)]
+                q0 = None
+            else:
+                # one upload (none for device-resident embeddings), then NVLink copies to the other shards
+                q0 = x.to(self._devs[0]) if on_dev else torch.from_numpy(x).to(self._devs[0])
+                torch.cuda.current_stream(q0.device).synchronize()
             for i, dv in enumerate(self._devs):
-                with torch.cuda.stream(self._streams[i]):
-                    if dv == self._devs[0]:
-                        self._streams[i].wait_stream(torch.cuda.current_stream(dv))
-                        qi = q0
-                    else:
-                        qi = torch.empty_like(q0, device=dv)
-                        qi.copy_(q0, non_blocking=True)
-                    qs.append(qi)
+                if not spread:
+                    with torch.cuda.stream(self._streams[i]):
+                        if dv == self._devs[0]:
+                            self._streams[i].wait_stream(torch.cuda.current_stream(dv))
+                            qi = q0
+                        else:
+                            qi = torch.empty_like(q0, device=dv)
+                            qi.copy_(q0, non_blocking=True)
+                        qs.append(qi)
                 pD, pI = C.c_void_p(), C.c_void_p()
                 check(lib().cldrd_host_device_ptr(dv.index, C.c_void_p(D.ctypes.data), C.byref(pD)))
                 check(lib().cldrd_host_device_ptr(dv.index, C.c_void_p(I.ctypes.data), C.byref(pI)))
@@ -674,7 +704,7 @@ class GpuIndexShards:
                 for i, dv in enumerate(self._devs):
                     with torch.cuda.stream(self._streams[i]):
                         idx = torch.tensor(again, dtype=torch.int64, device=dv)
-                        q2.append(qs[i][idx].contiguous())
+                        q2.append(torch.from_numpy(np.ascontiguousarray(x[again])).to(dv) if spread else qs[i][idx].contiguous())
                         rows.append(idx.to(torch.int32))
                 left = self._run(q2, len(again), k, False, outs, rows)
                 assert not left, "an unseeded batch cannot raise queries"
