@@ -62,39 +62,23 @@ __device__ __forceinline__ float exact_dot_warp(const float* __restrict__ q_s,
         const float4* r4 = reinterpret_cast<const float4*>(row);
         const float4* q4 = reinterpret_cast<const float4*>(q_s);
         const int n4 = d >> 2;
-        // four 16-byte loads in flight per lane (the gather is latency-bound otherwise); the FMA
-        // order is the same as a plain stride-32 loop, so the result does not depend on the unroll
+        // eight 16-byte loads in flight per lane: a 768-dim row is ONE round trip to HBM (the gather is latency-bound
+        // when the lists are short and the clocks are down after the scan); the FMA order is the same as a plain
+        // stride-32 loop, so the result does not depend on the unroll
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = lane; c < n4; c += 128) {
-            const float4 b0 = __ldg(r4 + c);
-            const float4 b1 = (c + 32 < n4) ? __ldg(r4 + c + 32) : zero;
-            const float4 b2 = (c + 64 < n4) ? __ldg(r4 + c + 64) : zero;
-            const float4 b3 = (c + 96 < n4) ? __ldg(r4 + c + 96) : zero;
-            float4 a = q4[c];
-            acc = fmaf(a.x, b0.x, acc);
-            acc = fmaf(a.y, b0.y, acc);
-            acc = fmaf(a.z, b0.z, acc);
-            acc = fmaf(a.w, b0.w, acc);
-            if (c + 32 < n4) {
-                a = q4[c + 32];
-                acc = fmaf(a.x, b1.x, acc);
-                acc = fmaf(a.y, b1.y, acc);
-                acc = fmaf(a.z, b1.z, acc);
-                acc = fmaf(a.w, b1.w, acc);
-            }
-            if (c + 64 < n4) {
-                a = q4[c + 64];
-                acc = fmaf(a.x, b2.x, acc);
-                acc = fmaf(a.y, b2.y, acc);
-                acc = fmaf(a.z, b2.z, acc);
-                acc = fmaf(a.w, b2.w, acc);
-            }
-            if (c + 96 < n4) {
-                a = q4[c + 96];
-                acc = fmaf(a.x, b3.x, acc);
-                acc = fmaf(a.y, b3.y, acc);
-                acc = fmaf(a.z, b3.z, acc);
-                acc = fmaf(a.w, b3.w, acc);
+        for (int c = lane; c < n4; c += 256) {
+            float4 b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b[u] = (c + 32 * u < n4) ? __ldg(r4 + c + 32 * u) : zero;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c + 32 * u < n4) {
+                    const float4 a = q4[c + 32 * u];
+                    acc = fmaf(a.x, b[u].x, acc);
+                    acc = fmaf(a.y, b[u].y, acc);
+                    acc = fmaf(a.z, b[u].z, acc);
+                    acc = fmaf(a.w, b[u].w, acc);
+                }
             }
         }
     } else {

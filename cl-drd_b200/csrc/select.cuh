@@ -317,7 +317,7 @@ struct RescoreParams {
 
 // One CTA per query: exact fp32 score of every listed row, sort, emit the k best.
 // dyn smem: keys[n_pad] u64 | q_s[d] f32
-__global__ void __launch_bounds__(1024) rescore_sort_kernel(RescoreParams p) {
+__global__ void __launch_bounds__(1024, 1) rescore_sort_kernel(RescoreParams p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     float* q_s = reinterpret_cast<float*>(sm_raw + size_t(p.n_pad) * 8);

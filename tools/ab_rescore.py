@@ -24,10 +24,10 @@ for k in (150, 1000):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
+    for _ in range(30):
         D, I = s.local.search_device(q, k, translate_ids=False)
     e1.record()
     torch.cuda.synchronize()
     st = s.shard.stats()
-    print(f"k={k} lib={os.environ.get('CLDRD_LIB_PATH', 'in-tree')} ms/search={e0.elapsed_time(e1) / 10:.3f} "
+    print(f"k={k} lib={os.environ.get('CLDRD_LIB_PATH', 'in-tree')} ms/search={e0.elapsed_time(e1) / 30:.3f} "
           f"rescored/q={st['rescored'] / 6980:.0f} max_list={st['max_list']}", flush=True)
