@@ -495,9 +495,13 @@ class ShardedSearcher:
             if self.id_map is not None:
                 return merge_candidates(D.unsqueeze(0), I.unsqueeze(0), self.id_map)
             return D, I
-        self._setup()
         n, dev = q.shape[0], q.device
-        nx = self._node(k) if n > 0 else None
+        if n == 0:
+            if self.rank != 0:
+                return None, None
+            return (torch.empty((0, k), dtype=torch.float32, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
+        self._setup()
+        nx = self._node(k)
         if nx is None:
             return self._search_nccl(q, k)
         self._id_map_everywhere()
@@ -608,6 +612,12 @@ class ShardedSearcher:
         if self.rank == 0:
             Dv, Iv = host.views(j, n, k, n, lease=j != host.nsets - 1)
         held = []          # batches whose callback waits for the retry of a raised query (rare)
+        scratch = j == host.nsets - 1
+
+        def report(b0, nb):
+            # rows of a leased set stay valid while the consumer holds them; the scratch set is reused by the next search
+            Db, Ib = Dv[b0:b0 + nb], Iv[b0:b0 + nb]
+            on_batch(b0, nb, Db.copy() if scratch else Db, Ib.copy() if scratch else Ib)
 
         def on_end(b0, nb, raised):
             if on_batch is None or self.rank != 0:
@@ -615,7 +625,7 @@ class ShardedSearcher:
             if raised or held:
                 held.append((b0, nb))
             else:
-                on_batch(b0, nb, Dv[b0:b0 + nb], Iv[b0:b0 + nb])
+                report(b0, nb)
 
         if q is None and nx.d == self.d:
             # Host queries: G uploads of the same 21 MB over G PCIe links pulling from one buffer cost more than the
@@ -647,8 +657,8 @@ class ShardedSearcher:
         if self.rank != 0:
             return None, None
         for b0, nb in held:
-            on_batch(b0, nb, Dv[b0:b0 + nb], Iv[b0:b0 + nb])
-        if j == host.nsets - 1:       # every rotating set is still referenced by the caller: scratch + one copy
+            report(b0, nb)
+        if scratch:                   # every rotating set is still referenced by the caller: scratch + one copy
             return Dv.copy(), Iv.copy()
         return Dv, Iv
 
