@@ -1715,12 +1715,8 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
         rc = read_stats(s, st);
         if (!rc && s->h_stats[ST_RANGE_ERR])
             rc = fail(CLDRD_EINVAL, "query values exceed the fp16 range; use the bf16 or tf32 scan");
-        if (!rc && s->h_stats[ST_FAILED] != 0) {
-            const unsigned long long keep_rescored = s->h_stats[ST_RESCORED], keep_surv = s->h_stats[ST_SURVIVORS];
+        if (!rc && s->h_stats[ST_FAILED] != 0)
             rc = run_fallbacks(s, q_dev, int(nq), k, false, nullptr, nullptr, st, false, &totals);
-            (void)keep_rescored;
-            (void)keep_surv;
-        }
     }
     s->sc.world = 0;
     if (rc) return rc;

@@ -108,3 +108,41 @@ def test_levels_are_the_top_j_of_the_union():
     for q in range(5):
         exp = np.sort(np.concatenate([topj[p, q] for p in range(3)]))[::-1][:8]
         assert np.array_equal(lv[q], exp)
+
+
+def test_merge_by_rank_equals_sort_of_the_union():
+    """The merge kernel of the node-wide search (csrc/node.cuh: merge_keys_kernel) does not sort: every shard's list
+    arrives sorted best-first, and a key's place in the merged order is its place in its own list plus, for every other
+    list, the number of keys there that order before it (one binary search per list; equal keys of different shards go
+    lower shard first).  Restated in numpy and compared with a plain sort of the union, on random lists of ragged
+    lengths, empty lists and forced cross-shard ties."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    for trial in range(200):
+        parts = int(rng.integers(1, 9))
+        k = int(rng.integers(1, 40))
+        lists = []
+        for p in range(parts):
+            n = int(rng.integers(0, k + 1))
+            keys = rng.integers(1, 60, size=n).astype(np.uint64)            # small range: ties across shards happen
+            keys = np.unique(keys)[::-1][:n]                                # a shard's own keys are distinct, descending
+            lists.append(keys)
+        merged = np.zeros(k, dtype=np.uint64)
+        filled = np.zeros(k, dtype=bool)
+        for p, mine in enumerate(lists):
+            for j, key in enumerate(mine):
+                rank = j
+                for o, other in enumerate(lists):
+                    if o == p:
+                        continue
+                    before = other > key if o > p else other >= key         # ties: the lower shard goes first
+                    rank += int(before.sum())
+                if rank < k:
+                    assert not filled[rank], "two keys claimed one place"
+                    merged[rank], filled[rank] = key, True
+        union = np.concatenate([np.stack([l, np.full(l.shape, p, dtype=np.uint64)], 1) for p, l in enumerate(lists)] or
+                               [np.zeros((0, 2), dtype=np.uint64)])
+        order = np.lexsort((union[:, 1], -union[:, 0].astype(np.int64)))    # key descending, shard ascending
+        want = union[order][:k, 0]
+        m = want.shape[0]
+        assert filled[:m].all() and not filled[m:].any()
+        assert np.array_equal(merged[:m], want)
