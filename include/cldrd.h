@@ -161,7 +161,7 @@ int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k
  * retriever/retrieval_utils.py:174-182).  One process per GPU (blocks mapped with CUDA IPC) or one
  * process driving several GPUs (blocks addressed directly).
  *
- * Every rank owns an exchange block of cldrd_node_block_bytes(world, max_k) bytes with the same
+ * Every rank owns an exchange block of cldrd_node_block_bytes(world, max_k, d) bytes with the same
  * layout; the peers' kernels store into it.  A batch of at most CLDRD_QUERY_BATCH replicated queries
  * is ONE asynchronous call per rank, cldrd_node_search_begin, which enqueues on the caller's stream:
  *   1. sample scan; the CLDRD_SEED_J best sample scores per query go to plane [rank] of every rank's
@@ -173,9 +173,11 @@ int cldrd_verify_seed(int device, const float* scores_dev, int64_t nq, int32_t k
  *   3. re-score: T = the highest level that >= k rows of the whole index reach (summed counts);
  *      candidates scanning below T - 2*eps are dropped unscored (k rows scanning >= T put the exact
  *      k-th score above T - eps, so a top-k row scans above T - 2*eps); the rest are scored in fp32,
- *      sorted and stored as u64 keys (score, GLOBAL row) straight into the key planes of the rank that
- *      merges the query (query i of the batch belongs to rank i / ceil(nq / world)); barrier;
- *   4. every rank merges its slice (same key order as the single-shard search: bit-identical result),
+ *      sorted and stored as u64 keys (score, GLOBAL row; the valid prefix of the list plus its length)
+ *      straight into the key planes of the rank that merges the query (query i of the batch belongs to
+ *      rank i / ceil(nq / world)); barrier;
+ *   4. every rank merges its slice (a key's merged rank = its place in its own sorted list + one binary
+ *      search per other list; same key order as the single-shard search: bit-identical result),
  *      checks the seed (k-th merged score >= seed + eps), applies id_map and stores the rows through
  *      out_scores / out_ids: any memory this GPU can address -- its own, the collecting rank's result
  *      buffer (cldrd_node_result_ptrs) or page-locked host memory; barrier;

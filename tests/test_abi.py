@@ -88,6 +88,11 @@ def test_sharded_entry_points_validate_arguments(cldrd_lib):
     assert cldrd_lib.cldrd_node_block_bytes(8, 1000, 768) - cldrd_lib.cldrd_node_block_bytes(8, 1000, 0) == 8192 * 768 * 4
     assert cldrd_lib.cldrd_node_spread_queries(None, None, 0, 1, None) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_query_ptr(None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_set_outputs(None, 1, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_search_begin_set(None, None, None, 1, 10, 1, 0, 0, None, None, None) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_node_set_wait_mode(None, 0) == _lib.E_INVAL
+    assert cldrd_lib.cldrd_host_device_ptr(0, None, None) == _lib.E_INVAL
+    assert _lib.MAX_OUT_SETS == 8
     assert cldrd_lib.cldrd_node_search_begin(None, None, None, 1, 10, 1, None, None, None, None, None) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_search_end(None, None, None, None, 0) == _lib.E_INVAL
     assert cldrd_lib.cldrd_node_attach(None, 0, None, None, -1) == _lib.E_INVAL
@@ -106,3 +111,4 @@ def test_header_constants_match_python_side():
     assert int(consts["CLDRD_MAX_PEERS"]) == _lib.MAX_PEERS
     assert int(consts["CLDRD_QUERY_BATCH"]) == _lib.QUERY_BATCH
     assert int(consts["CLDRD_PEER_HANDLE_BYTES"]) == _lib.PEER_HANDLE_BYTES
+    assert int(consts["CLDRD_MAX_OUT_SETS"]) == _lib.MAX_OUT_SETS
