@@ -239,23 +239,43 @@ def writer_rate(np, D, I, nq, k):
     return out
 
 
-def index_load_rate(torch, np, rank, world, dev, barrier, max_over_ranks, n_rows_file=1 << 20):
+def index_load_rate(torch, dist, np, rank, world, dev, barrier, max_over_ranks, n_rows_file=1 << 20):
     """File -> HBM rate of cldrd_shard_load_file (read_index + index_cpu_to_gpu of the reference,
     retriever/retrieve_top_passages.py:85-86): rank 0 writes an IxMp{IxFI} file of n_rows_file x 768 rows through the
-    streaming writer, every rank then loads its row range of it."""
+    streaming writer, every rank then loads its row range of it.  A side measurement: when no directory has room for
+    the file (or writing it fails) every rank learns so and the record says why."""
     from cldrd import dist as CD
     from cldrd._lib import check, lib, ptr
-    where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    path = os.path.join(where, "cldrd_bench_load.index")
+    need = n_rows_file * DIM * 4 + n_rows_file * 8 + (64 << 20)
+    plan = [None, None]        # [path, reason it was skipped]
+    if rank == 0:
+        for where in ("/dev/shm", tempfile.gettempdir()):
+            try:
+                vfs = os.statvfs(where)
+                if os.path.isdir(where) and vfs.f_bavail * vfs.f_frsize > need:
+                    plan[0] = os.path.join(where, f"cldrd_bench_load_{os.getpid()}.index")
+                    break
+            except OSError:
+                continue
+        if plan[0] is None:
+            plan[1] = "no directory with room for the test file"
+        else:
+            try:
+                w = C.c_void_p()
+                check(lib().cldrd_index_writer_begin(C.byref(w), plan[0].encode(), n_rows_file, DIM, 1, 0))
+                block = np.random.Generator(np.random.PCG64(5)).standard_normal((1 << 15, DIM), dtype=np.float32)
+                for r0 in range(0, n_rows_file, 1 << 15):
+                    check(lib().cldrd_index_writer_append(w, ptr(block), min(1 << 15, n_rows_file - r0)))
+                ids = np.arange(n_rows_file, dtype=np.int64)
+                check(lib().cldrd_index_writer_finish(w, ptr(ids)))
+            except Exception as e:
+                plan = [None, f"writing the test file failed: {e}"[:200]]
+    if world > 1:
+        dist.broadcast_object_list(plan, src=0)
+    path = plan[0]
+    if path is None:
+        return {"skipped": plan[1]}
     try:
-        if rank == 0:
-            w = C.c_void_p()
-            check(lib().cldrd_index_writer_begin(C.byref(w), path.encode(), n_rows_file, DIM, 1, 0))
-            block = np.random.Generator(np.random.PCG64(5)).standard_normal((1 << 15, DIM), dtype=np.float32)
-            for r0 in range(0, n_rows_file, 1 << 15):
-                check(lib().cldrd_index_writer_append(w, ptr(block), min(1 << 15, n_rows_file - r0)))
-            ids = np.arange(n_rows_file, dtype=np.int64)
-            check(lib().cldrd_index_writer_finish(w, ptr(ids)))
         barrier()
         t0 = time.perf_counter()
         s = CD.ShardedSearcher.from_file(path, dev.index, scan="f16")
@@ -265,7 +285,7 @@ def index_load_rate(torch, np, rank, world, dev, barrier, max_over_ranks, n_rows
         s.shard.close()
         barrier()
         return {"file_bytes": nbytes, "seconds": dt, "gb_per_s": nbytes / dt / 1e9, "ranks": world,
-                "note": f"{where} (page cache) -> pread -> pinned ring -> HBM, incl. the fp16 scan copy and the norm pass"}
+                "note": f"{os.path.dirname(path)} (page cache) -> pread -> pinned ring -> HBM, incl. the fp16 scan copy and the norm pass"}
     finally:
         if rank == 0 and os.path.exists(path):
             os.unlink(path)
@@ -490,8 +510,11 @@ def main():
                                                      "calls": (nq + 127) // 128,
                                                      "note": "one index pass per 128 queries: HBM-bound"}
         if rank == 0:
-            extras["writer"] = writer_rate(np, D_host, I_host, nq, k)
-        extras["index_load"] = index_load_rate(torch, np, rank, world, dev, barrier, max_over_ranks)
+            try:
+                extras["writer"] = writer_rate(np, D_host, I_host, nq, k)
+            except Exception as e:          # a side measurement must not take the line down
+                extras["writer"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        extras["index_load"] = index_load_rate(torch, dist, np, rank, world, dev, barrier, max_over_ranks)
         if world > 1:
             # The faiss-shaped multi-GPU call of the reference, retrieval_utils.py:165-182: ONE process drives all N GPUs
             # (index_cpu_to_gpu_multiple(..., shard=True) -> index.search(numpy)).  Rank 0 builds it next to the ranks'
@@ -508,7 +531,15 @@ def main():
     if not args.no_extras and args.workload == "curriculum":
         # the curriculum step end to end: host queries in, run file out, the file growing batch by batch behind the
         # search (retriever/retrieve_top_passages.py:88-109 on the 502 939 training queries)
-        where = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        where = tempfile.gettempdir()
+        for cand in ("/dev/shm", tempfile.gettempdir()):       # ~37 bytes per line
+            try:
+                vfs = os.statvfs(cand)
+                if vfs.f_bavail * vfs.f_frsize > nq * k * 40 + (256 << 20):
+                    where = cand
+                    break
+            except OSError:
+                continue
         path = os.path.join(where, f"cldrd_bench_c5_{os.getpid()}.tsv")
         qids = np.arange(nq, dtype=np.int64) * 3 + 7
         D_host = I_host = None
@@ -522,14 +553,19 @@ def main():
                 stream.put(qids[c0:c0 + chunk], Ic, Dc)
         else:
             searcher.search_host(q_host, k, on_batch=(lambda b0, nb, Db, Ib: stream.put(qids[b0:b0 + nb], Ib, Db)) if rank == 0 else None)
+        werr = None
         if rank == 0:
-            stream.close()
+            try:
+                stream.close()
+            except Exception as e:          # a side measurement must not take the line down (disk full, ...)
+                werr = f"{type(e).__name__}: {e}"[:300]
         dt = max_over_ranks(time.perf_counter() - t0)
         if rank == 0:
-            extras["e2e_with_run_file"] = {"value": nq / dt, "unit": "queries/s", "seconds": dt, "lines": nq * k,
-                                           "bytes": os.path.getsize(path), "where": where,
-                                           "note": "search_host + RunFileStream: batch i is formatted and written while batch i+1 is searched"}
-            os.unlink(path)
+            extras["e2e_with_run_file"] = {"error": werr} if werr else {
+                "value": nq / dt, "unit": "queries/s", "seconds": dt, "lines": nq * k, "bytes": os.path.getsize(path), "where": where,
+                "note": "search_host + RunFileStream: batch i is formatted and written while batch i+1 is searched"}
+            if os.path.exists(path):
+                os.unlink(path)
 
     # ---- roofline of the scan kernel ----------------------------------------------------------------
     peaks = load_peaks()
