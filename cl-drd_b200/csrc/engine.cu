@@ -365,6 +365,7 @@ struct BatchCtx {
     // survivor-buffer plan of the current chunk (scan writes it, select reads it)
     int q_stride = 0, seg_cap = 0, pool_cap = 0, groups = 1, run_len = 1, grid = 0, seg_by_group = 0;
     double seed_rank = 0.0;   // expected rank (in the whole index) of the seed threshold
+    double expected_surv = 0.0;  // survivors per query this shard expects from a one-launch seeded pass (0 = unknown)
     bool tc2 = false;         // this launch uses the CTA-pair kernel
     // Workspace view.  A batch normally owns the whole workspace (qoff = 0, region = 0, 1 region);
     // a pipelined batch is cut in two halves that use disjoint query ranges of every per-query
@@ -533,8 +534,16 @@ int launch_scan(BatchCtx& c, int mode, int64_t row_begin, int nrows, int tile_st
 size_t select_smem(const cldrd_shard* s) { return size_t(s->ws_keep_cap + kSurvCap) * 8 + size_t(s->d) * 4 + 16; }
 
 // k_sel: how many best rows the list must keep (the search's k, or the sample's j)
-int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_sel, int tile_stride = 1) {
+int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_sel, int tile_stride = 1,
+                  bool one_launch_pass = false) {
     cldrd_shard* s = c.s;
+    // Shared memory decides how many select CTAs share an SM (2 at the full 8192-survivor capacity), and the kernel is a
+    // chain of barrier-separated passes: latency, not work.  A one-launch seeded pass knows how many survivors to expect
+    // (the seed's rank, split over the shards), so it takes 5x that (at least 2048) and lets 4 CTAs share the SM; a query
+    // that still overflows is flagged and searched again like any other overflow.
+    int surv_cap = kSurvCap;
+    if (!dense && one_launch_pass && c.expected_surv > 0.0)
+        surv_cap = int(std::min<double>(kSurvCap, std::max(2048.0, 5.0 * c.expected_surv)));
     SelectParams p{};
     p.list = s->w_list + size_t(c.qoff) * s->ws_keep_cap;
     p.list_len = s->w_list_len + c.qoff;
@@ -545,7 +554,7 @@ int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_s
     p.seg_cap = c.seg_cap;
     p.pool_cap = c.pool_cap;
     p.groups = c.groups;
-    p.surv_cap = kSurvCap;
+    p.surv_cap = surv_cap;
     p.dense = dense ? s->w_dense + size_t(c.qoff) * kDensePiece : nullptr;
     p.dense_ld = kDensePiece;
     p.dense_n = nrows;
@@ -561,7 +570,7 @@ int launch_select(BatchCtx& c, bool dense, int64_t row_begin, int nrows, int k_s
     p.q = c.q;
     p.d = s->d;
     p.vec4 = s->vec4 && (reinterpret_cast<uintptr_t>(c.q) % 16 == 0);
-    select_merge_kernel<<<c.nq, 512, select_smem(s), c.st>>>(p);
+    select_merge_kernel<<<c.nq, 512, size_t(s->ws_keep_cap + surv_cap) * 8 + size_t(s->d) * 4 + 16, c.st>>>(p);
     CU_TRY(cudaGetLastError());
     c.launches++;
     return CLDRD_OK;
@@ -758,7 +767,7 @@ int run_chunks(BatchCtx& c, PassKind kind) {
             if (i + 1 < nchunks) m = (m / TC_BN) * TC_BN;
             if (m <= 0) continue;
             if ((rc = launch_scan(c, TC_FILTER, done, int(m)))) return rc;
-            if ((rc = launch_select(c, false, done, int(m), c.k))) return rc;
+            if ((rc = launch_select(c, false, done, int(m), c.k, 1, nchunks == 1))) return rc;
             done += m;
         }
         return CLDRD_OK;
@@ -865,6 +874,7 @@ int search_batch(cldrd_shard* s, const float* q_dev, int nq, int k, bool transla
         const SamplePlan sp = sample_plan(s, k);
         const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
         c.seed_rank = double(CLDRD_SEED_J) / frac;
+        if (seed_mode == 1) c.expected_surv = c.seed_rank;   // own sample: the seed's rank in this shard
     }
     if (seed_mode == 1) {
         if ((rc = run_sample(c, s->w_topj))) return rc;
@@ -1671,6 +1681,7 @@ static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_
         const SamplePlan sp = sample_plan(s, k);
         const double frac = sp.tiles > 0 ? double(sp.tiles) * TC_BN / double(std::max<int64_t>(s->nrows, 1)) : 1.0;
         c.seed_rank = double(CLDRD_SEED_J) / frac;
+        c.expected_surv = c.seed_rank / world;               // the seed is the J-th best of the union of all samples
         if ((rc = run_sample(c, node_ptrs(n, n->lay.topj), world, size_t(rank) * plane))) return rc;
         if ((rc = node_barrier(s, n, st))) return rc;
         levels_seed_kernel<<<unsigned(nq), 128, size_t(world) * CLDRD_SEED_J * sizeof(float), st>>>(
