@@ -160,3 +160,19 @@ def test_second_cpu_implementation_agrees_with_the_oracle():
     D64, R64 = O.search_rows(xb, xq, k, dtype=np.float64)
     r = O.compare_topk(D64.astype(np.float32), R64.astype(np.int64), D, R.astype(np.int64), *ext)
     assert r["ok"], r
+
+
+def test_bench_checker_agrees_with_the_oracle():
+    """The brute-force checker behind bench.py's `parity` block and the full-size GPU test (fp64 torch matmul over a
+    shard's rows, stable sort: score descending, row ascending) is pinned here, on the CPU, to the oracle's fp64 search:
+    same rows in the same order, including exact duplicates (ties -> lower row) and fewer rows than asked for."""
+    import torch
+    import bench
+    xb, xq = O.synth(7000, 48, 50), O.synth(9, 48, 51)
+    xb[100:110] = xb[5]                                   # exact duplicates: ties
+    s, r = bench.brute_force_shard(torch, torch.from_numpy(xb), 1000, torch.from_numpy(xq), 64)
+    D64, R64 = O.search_rows(xb, xq, 64, dtype=np.float64)
+    assert np.array_equal(r.numpy() - 1000, R64)
+    assert np.allclose(s.numpy(), D64, rtol=1e-12, atol=0)
+    s, r = bench.brute_force_shard(torch, torch.from_numpy(xb[:5]), 0, torch.from_numpy(xq), 8)
+    assert (r.numpy()[:, 5:] == -1).all() and np.isinf(s.numpy()[:, 5:]).all()
