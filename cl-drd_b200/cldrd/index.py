@@ -600,6 +600,12 @@ class GpuIndexShards:
         for s in self._shards:
             s.close()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def _end_all(self, b0: int):
         again = None
         for sh, node in zip(self._shards, self._nodes):
