@@ -1620,6 +1620,10 @@ int cldrd_node_result_ptrs(const cldrd_node* n, int32_t owner_rank, void** score
 
 }  // extern "C"
 
+// Everything below is validated BEFORE the first launch: once a batch has started to enqueue, every rank must enqueue the
+// same sequence of barriers.  A CUDA failure in the middle (it would be a launch failure: nothing here allocates)
+// returns the error and leaves this rank's barrier count behind its peers'; their next barrier then ends in the
+// watchdog's CLDRD_ECUDA on every rank instead of a result -- the node has to be rebuilt.
 static int node_search_begin_impl(cldrd_shard* s, cldrd_node* n, const float* q_dev, int64_t nq, int32_t k, int32_t seeded,
                                   float* out_scores, int64_t* out_ids, bool use_sets, int32_t out_select, int64_t out_row0,
                                   const int32_t* out_rows_dev, const int64_t* id_map_dev, void* cuda_stream) {
