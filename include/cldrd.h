@@ -295,7 +295,7 @@ int cldrd_merge_w(int device, const float* scores_dev, const int64_t* rows_dev, 
                   float* out_scores_dev, int64_t* out_ids_dev, void* cuda_stream);
 
 /* Same with planes that hold more rows than are merged: input [parts][plane_rows][w], the first
- * nq <= plane_rows rows of every plane are merged (the exchange buffers of cldrd_search_dev_scatter:
+ * nq <= plane_rows rows of every plane are merged (lists received slice-wise from an all-to-all:
  * plane_rows = slice, nq = the queries this rank owns). */
 int cldrd_merge_planes(int device, const float* scores_dev, const int64_t* rows_dev, int32_t parts,
                        int64_t plane_rows, int64_t nq, int32_t w, int32_t k,

@@ -4,11 +4,11 @@ Not a restatement of the reference (which has no sharded search that works: the 
 retriever/retrieval_utils.py:165-182 raises NameError): this models what OUR kernels decide, so that the
 exactness argument of DESIGN.md sections 4, 5 and 7 can be attacked on the CPU with adversarial scan errors:
 
-  levels_from_samples   cl-drd_b200/csrc/select.cuh  levels_from_samples_kernel
+  levels_from_samples   cl-drd_b200/csrc/node.cuh    levels_seed_kernel
   shard_candidates      scan filter (score >= seed) + select_merge_kernel's band cut max(v_k - band, seed)
-  count_levels          count_levels_kernel
-  cut_from_counts       cut_from_counts_kernel
-  verify                verify_seed_kernel
+  count_levels          node.cuh  count_levels_peers_kernel
+  cut_from_counts       select.cuh  rescore_sort_kernel (the counted cut, computed from the summed count planes)
+  verify                node.cuh  merge_keys_kernel's seed check (verify_seed_kernel on the NCCL transport)
 
 The one property everything rests on: a scan score differs from the exact fp32 score by at most eps
 (band = 2 * eps).  `run` plays the whole protocol on exact scores S and scan scores S_hat and reports, per
