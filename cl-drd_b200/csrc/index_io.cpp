@@ -180,6 +180,9 @@ struct cldrd_index_writer {
     int32_t with_ids = 0;
     int64_t rows_written = 0;
     int64_t data_off = 0;
+    int64_t row0 = 0;        // this writer covers rows [row0, row0 + nrows) of the n the file declares
+    int64_t nrows = 0;
+    bool creator = true;     // wrote the headers; writes the id array in finish
     std::string path;
 };
 
@@ -203,11 +206,13 @@ int cldrd_index_probe(const char* path, int64_t* ntotal, int32_t* d, int32_t* me
     return CLDRD_OK;
 }
 
-int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t n, int32_t d,
-                             int32_t with_ids, int32_t idmap2) {
-    if (!out || !path || n < 0 || d <= 0) return fail(CLDRD_EINVAL, "writer_begin: bad argument");
-    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) return fail(CLDRD_EIO, "cannot create '%s': %s", path, strerror(errno));
+int cldrd_index_writer_open_range(cldrd_index_writer** out, const char* path, int64_t n, int32_t d, int32_t with_ids,
+                                  int32_t idmap2, int64_t row0, int64_t nrows, int32_t create) {
+    if (!out || !path || n < 0 || d <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > n)
+        return fail(CLDRD_EINVAL, "writer_open_range: bad argument (rows [%lld, +%lld) of %lld)", (long long)row0,
+                    (long long)nrows, (long long)n);
+    int fd = open(path, create ? (O_WRONLY | O_CREAT | O_TRUNC) : O_WRONLY, 0644);
+    if (fd < 0) return fail(CLDRD_EIO, "cannot %s '%s': %s", create ? "create" : "open", path, strerror(errno));
     unsigned char hdr[2 * kHeaderBytes + 8];
     size_t len = 0;
     if (with_ids) {
@@ -219,7 +224,7 @@ int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t
     uint64_t cnt = uint64_t(n) * uint64_t(d);
     memcpy(hdr + len, &cnt, 8);
     len += 8;
-    if (!pwrite_all(fd, hdr, len, 0)) {
+    if (create && !pwrite_all(fd, hdr, len, 0)) {
         close(fd);
         return fail(CLDRD_EIO, "write to '%s' failed: %s", path, strerror(errno));
     }
@@ -229,17 +234,26 @@ int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t
     w->d = d;
     w->with_ids = with_ids;
     w->data_off = int64_t(len);
+    w->row0 = row0;
+    w->nrows = nrows;
+    w->creator = create != 0;
     w->path = path;
     *out = w;
     return CLDRD_OK;
 }
 
+int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t n, int32_t d,
+                             int32_t with_ids, int32_t idmap2) {
+    if (n < 0) return fail(CLDRD_EINVAL, "writer_begin: bad argument");
+    return cldrd_index_writer_open_range(out, path, n, d, with_ids, idmap2, 0, n, 1);
+}
+
 int cldrd_index_writer_append(cldrd_index_writer* w, const float* rows_host, int64_t nrows) {
     if (!w || (!rows_host && nrows) || nrows < 0) return fail(CLDRD_EINVAL, "writer_append: bad argument");
-    if (w->rows_written + nrows > w->n)
-        return fail(CLDRD_EINVAL, "writer_append: %lld rows exceed the %lld declared",
-                    (long long)(w->rows_written + nrows), (long long)w->n);
-    off_t off = w->data_off + off_t(w->rows_written) * w->d * 4;
+    if (w->rows_written + nrows > w->nrows)
+        return fail(CLDRD_EINVAL, "writer_append: %lld rows exceed the %lld of this writer's range",
+                    (long long)(w->rows_written + nrows), (long long)w->nrows);
+    off_t off = w->data_off + off_t(w->row0 + w->rows_written) * w->d * 4;
     if (!pwrite_all(w->fd, rows_host, size_t(nrows) * w->d * 4, off))
         return fail(CLDRD_EIO, "write to '%s' failed: %s", w->path.c_str(), strerror(errno));
     w->rows_written += nrows;
@@ -249,10 +263,10 @@ int cldrd_index_writer_append(cldrd_index_writer* w, const float* rows_host, int
 int cldrd_index_writer_finish(cldrd_index_writer* w, const int64_t* ids_host) {
     if (!w) return fail(CLDRD_EINVAL, "writer_finish: NULL");
     int rc = CLDRD_OK;
-    if (w->rows_written != w->n)
+    if (w->rows_written != w->nrows)
         rc = fail(CLDRD_ESTATE, "writer_finish: %lld of %lld rows written", (long long)w->rows_written,
-                  (long long)w->n);
-    if (!rc && w->with_ids) {
+                  (long long)w->nrows);
+    if (!rc && w->with_ids && w->creator) {     // the creator writes the id array of ALL n rows
         if (!ids_host && w->n)
             rc = fail(CLDRD_EINVAL, "writer_finish: ids required");
         else {

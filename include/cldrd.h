@@ -71,6 +71,14 @@ int cldrd_index_write(const char* path, const float* xb_host, const int64_t* ids
 typedef struct cldrd_index_writer cldrd_index_writer;
 int cldrd_index_writer_begin(cldrd_index_writer** out, const char* path, int64_t n, int32_t d,
                              int32_t with_ids, int32_t idmap2);
+/* Sharded build (one process per GPU encodes its slice of the collection, all write ONE file): the writer covers
+ * rows [row0, row0 + nrows) of the n rows the file declares.  create != 0 (exactly one process, before the others
+ * open the file) creates the file and writes the headers; that writer's finish also writes the id array of all n
+ * rows.  The others pass create = 0 and NULL ids.  Rows land at their final offsets, so the file is byte-identical to a
+ * single-process build whatever the order of the writes. */
+int cldrd_index_writer_open_range(cldrd_index_writer** out, const char* path, int64_t n, int32_t d,
+                                  int32_t with_ids, int32_t idmap2, int64_t row0, int64_t nrows,
+                                  int32_t create);
 int cldrd_index_writer_append(cldrd_index_writer* w, const float* rows_host, int64_t nrows);
 int cldrd_index_writer_finish(cldrd_index_writer* w, const int64_t* ids_host /* n or NULL */);
 
