@@ -9,6 +9,7 @@
 #include <cerrno>
 #include <charconv>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
@@ -24,7 +25,62 @@
 
 namespace {
 
-// Python's repr(float(x)) into buf; returns length.
+// Where CPython's format_float_short ('r') puts the point / the exponent: `digits` are the nd <= 24 shortest
+// round-trip digits, decpt the position of the decimal point relative to them.  Exponent form iff decpt <= -4 or
+// decpt > 16.  The digits are moved with fixed 24-byte copies (three register moves instead of a memcpy call per
+// piece): `digits` must be readable for 48 bytes and `p` writable for 48 bytes; the bytes behind the returned
+// pointer are scratch.
+inline void copy24(char* d, const char* s) { memcpy(d, s, 24); }
+
+inline char* layout_digits(char* p, const char* digits, int nd, int decpt) {
+    if (decpt <= -4 || decpt > 16) {
+        p[0] = digits[0];
+        if (nd > 1) {
+            p[1] = '.';
+            copy24(p + 2, digits + 1);
+            p += nd + 1;
+        } else {
+            ++p;
+        }
+        *p++ = 'e';
+        int e = decpt - 1;
+        if (e < 0) {
+            *p++ = '-';
+            e = -e;
+        } else {
+            *p++ = '+';
+        }
+        char eb[8];
+        int ne = 0;
+        do {
+            eb[ne++] = char('0' + e % 10);
+            e /= 10;
+        } while (e);
+        if (ne < 2) eb[ne++] = '0';  // at least two exponent digits
+        while (ne) *p++ = eb[--ne];
+    } else if (decpt <= 0) {
+        *p++ = '0';
+        *p++ = '.';
+        for (int i = 0; i < -decpt; ++i) *p++ = '0';
+        copy24(p, digits);
+        p += nd;
+    } else if (decpt >= nd) {
+        copy24(p, digits);
+        p += nd;
+        for (int i = 0; i < decpt - nd; ++i) *p++ = '0';
+        *p++ = '.';
+        *p++ = '0';
+    } else {
+        copy24(p, digits);
+        copy24(p + decpt + 1, digits + decpt);
+        p[decpt] = '.';
+        p += nd + 1;
+    }
+    return p;
+}
+
+// Python's repr(float(x)) into buf; returns length.  General path: any double, digits from std::to_chars
+// (shortest round-trip, closest to the value among the shortest: the same contract as CPython's repr).
 int py_repr_double(double v, char* buf) {
     if (std::isnan(v)) {
         memcpy(buf, "nan", 3);
@@ -53,7 +109,7 @@ int py_repr_double(double v, char* buf) {
     int len = int(res.ptr - sci);
     int epos = 0;
     while (epos < len && sci[epos] != 'e') ++epos;
-    char digits[32];
+    char digits[48] = {0};
     int nd = 0;
     for (int i = 0; i < epos; ++i)
         if (sci[i] != '.') digits[nd++] = sci[i];
@@ -68,56 +124,198 @@ int py_repr_double(double v, char* buf) {
         for (; i < len; ++i) exp10 = exp10 * 10 + (sci[i] - '0');
         if (neg) exp10 = -exp10;
     }
-    int decpt = exp10 + 1;  // position of the decimal point relative to the digit string
-    // CPython format_float_short, 'r': exponent form iff decpt <= -4 or decpt > 16
-    if (decpt <= -4 || decpt > 16) {
-        *p++ = digits[0];
-        if (nd > 1) {
-            *p++ = '.';
-            memcpy(p, digits + 1, nd - 1);
-            p += nd - 1;
+    return int(layout_digits(p, digits, nd, exp10 + 1) - buf);
+}
+
+// "00" "01" ... "99"
+struct Pairs {
+    char c[200];
+    constexpr Pairs() : c() {
+        for (int i = 0; i < 100; ++i) {
+            c[2 * i] = char('0' + i / 10);
+            c[2 * i + 1] = char('0' + i % 10);
         }
-        *p++ = 'e';
-        int e = decpt - 1;
-        if (e < 0) {
-            *p++ = '-';
-            e = -e;
-        } else {
-            *p++ = '+';
-        }
-        char eb[8];
-        int ne = 0;
-        do {
-            eb[ne++] = char('0' + e % 10);
-            e /= 10;
-        } while (e);
-        if (ne < 2) eb[ne++] = '0';  // at least two exponent digits
-        while (ne) *p++ = eb[--ne];
-    } else if (decpt <= 0) {
-        *p++ = '0';
-        *p++ = '.';
-        for (int i = 0; i < -decpt; ++i) *p++ = '0';
-        memcpy(p, digits, nd);
-        p += nd;
-    } else if (decpt >= nd) {
-        memcpy(p, digits, nd);
-        p += nd;
-        for (int i = 0; i < decpt - nd; ++i) *p++ = '0';
-        *p++ = '.';
-        *p++ = '0';
-    } else {
-        memcpy(p, digits, decpt);
-        p += decpt;
-        *p++ = '.';
-        memcpy(p, digits + decpt, nd - decpt);
-        p += nd - decpt;
     }
-    return int(p - buf);
+};
+constexpr Pairs kPairs;
+
+// v < 10^8, no leading zeros
+inline char* put_u32_short(char* p, uint32_t v) {
+    const int n = v < 10000u ? (v < 100u ? (v < 10u ? 1 : 2) : (v < 1000u ? 3 : 4))
+                             : (v < 1000000u ? (v < 100000u ? 5 : 6) : (v < 10000000u ? 7 : 8));
+    char* q = p + n;
+    while (v >= 100u) {
+        const uint32_t t = v / 100u;
+        memcpy(q -= 2, kPairs.c + 2 * (v - t * 100u), 2);
+        v = t;
+    }
+    if (v >= 10u)
+        memcpy(q - 2, kPairs.c + 2 * v, 2);
+    else
+        q[-1] = char('0' + v);
+    return p + n;
+}
+
+// exactly eight digits of v < 10^8, leading zeros included: two independent chains of two pairs
+inline char* put_8digits(char* p, uint32_t v) {
+    const uint32_t hi = v / 10000u, lo = v - hi * 10000u;
+    const uint32_t a = hi / 100u, b = hi - a * 100u, c = lo / 100u, d = lo - c * 100u;
+    memcpy(p, kPairs.c + 2 * a, 2);
+    memcpy(p + 2, kPairs.c + 2 * b, 2);
+    memcpy(p + 4, kPairs.c + 2 * c, 2);
+    memcpy(p + 6, kPairs.c + 2 * d, 2);
+    return p + 8;
+}
+
+inline char* put_u64(char* p, uint64_t v) {
+    if (v < 100000000ull) return put_u32_short(p, uint32_t(v));
+    const uint64_t hi = v / 100000000ull;
+    const uint32_t lo = uint32_t(v - hi * 100000000ull);
+    if (hi < 100000000ull) return put_8digits(put_u32_short(p, uint32_t(hi)), lo);
+    const uint64_t top = hi / 100000000ull;          // < 1845 for any 64-bit v
+    const uint32_t mid = uint32_t(hi - top * 100000000ull);
+    return put_8digits(put_8digits(put_u32_short(p, uint32_t(top)), mid), lo);
 }
 
 inline char* put_i64(char* p, int64_t v) {
-    auto r = std::to_chars(p, p + 24, v);
-    return r.ptr;
+    if (v < 0) {
+        *p++ = '-';
+        return put_u64(p, uint64_t(0) - uint64_t(v));
+    }
+    return put_u64(p, uint64_t(v));
+}
+
+typedef unsigned __int128 u128;
+
+constexpr uint64_t kPow5[27] = {1ull,
+                                5ull,
+                                25ull,
+                                125ull,
+                                625ull,
+                                3125ull,
+                                15625ull,
+                                78125ull,
+                                390625ull,
+                                1953125ull,
+                                9765625ull,
+                                48828125ull,
+                                244140625ull,
+                                1220703125ull,
+                                6103515625ull,
+                                30517578125ull,
+                                152587890625ull,
+                                762939453125ull,
+                                3814697265625ull,
+                                19073486328125ull,
+                                95367431640625ull,
+                                476837158203125ull,
+                                2384185791015625ull,
+                                11920928955078125ull,
+                                59604644775390625ull,
+                                298023223876953125ull,
+                                1490116119384765625ull};
+
+constexpr int kFastEmin = -33, kFastEmax = 52;   // binary exponents floor(log2 v) the fast path takes
+
+// P(E) = 16 - floor(E * log10 2): v * 10^P lies in [1e16, 2e17) for every v in [2^E, 2^(E+1))
+struct ScaleTable {
+    int8_t p[kFastEmax - kFastEmin + 1];
+    constexpr ScaleTable() : p() {
+        // floor(E * log10(2)), log10(2) = 0.30102999566398...; 14 decimals decide the floor for every |E| < 64
+        for (int E = kFastEmin; E <= kFastEmax; ++E) {
+            const long long num = (long long)E * 30102999566398LL;   // E * log10(2) * 1e14
+            long long fl = num / 100000000000000LL;
+            if (num < 0 && fl * 100000000000000LL != num) --fl;
+            p[E - kFastEmin] = int8_t(16 - fl);
+        }
+    }
+};
+constexpr ScaleTable kScale;
+
+// Shortest round-trip digits of double(s) for an fp32 s: the only values the writer ever prints.
+//
+// s = m * 2^e with m < 2^24, so s * 10^P = m * 5^P * 2^(P+e) is ONE 64x64 -> 128-bit product and a shift, exactly:
+// W = its integer part (17-18 digits), r / 2^sh its fraction.  The decimals that parse back to double(s) are those
+// within h = 2^(E-53) of it (E = floor(log2 s); both ends included: the double's mantissa has 29 trailing zero
+// bits, so it is even; below a power of two the lower half is h / 2).  In the unit of W, h = 5^P * 2^(-30-t) with
+// t = -P-e, so the integers inside the interval are [a, b] = [W + ceil((r*2^31 - 2 hd) / 2^(31+sh)),
+// W + floor((r*2^31 + 2 hu) / 2^(31+sh))], exact in 64-bit arithmetic (hu = 5^P * 2^max(0,-t) < 2^60.4, hd = hu, or
+// hu / 2 below a power of two).  The shortest text is the largest j for which a multiple of 10^j lies in [a, b]
+// (monotone in j), and of the multiples just below and just above s at that j the closer one that is inside, the even
+// one on an exact tie: the contract of CPython's repr (David Gay's mode 0) and of std::to_chars, against which
+// cldrd_format_score_selfcheck sweeps all 2^32 bit patterns (tools/check_score_text.py).
+// Returns false outside the fast range (zero, denormals, |s| < 2^-33, |s| >= 2^53, inf, nan): those go through
+// py_repr_double.
+inline bool shortest_f32(uint32_t abs_bits, char* digits, int* nd, int* decpt) {
+    const int E = int(abs_bits >> 23) - 127;
+    if (E < kFastEmin || E > kFastEmax) return false;
+    const uint32_t frac = abs_bits & 0x7fffffu;
+    const uint64_t m = frac | 0x800000u;
+    const int e = E - 23;
+    const int P = kScale.p[E - kFastEmin];
+    const int t = -P - e;
+    const u128 prod = u128(m) * kPow5[P];
+    uint64_t W, r, hnum;
+    int sh;
+    if (t >= 0) {
+        W = uint64_t(prod >> t);
+        r = uint64_t(prod) & ((uint64_t(1) << t) - 1);
+        sh = t;
+        hnum = kPow5[P];
+    } else {
+        W = uint64_t(prod) << (-t);
+        r = 0;
+        sh = 0;
+        hnum = kPow5[P] << (-t);
+    }
+    const int s31 = 31 + sh;
+    const int64_t r31 = int64_t(r << 31);
+    const uint64_t b = W + (uint64_t(r31 + int64_t(2 * hnum)) >> s31);
+    const int64_t num_lo = r31 - int64_t(frac ? 2 * hnum : hnum);
+    const uint64_t a = W + uint64_t((num_lo + ((int64_t(1) << s31) - 1)) >> s31);   // arithmetic shift: floor
+    // largest j with a multiple of 10^j in [a, b]; qb = b / 10^j, qw = W / 10^j
+    uint64_t qb = b, qw = W, p10 = 1;
+    int j = 0;
+    for (;;) {
+        const uint64_t qb1 = qb / 10, p10n = p10 * 10;
+        if (qb1 * p10n < a) break;
+        qb = qb1;
+        qw /= 10;
+        p10 = p10n;
+        ++j;
+    }
+    const uint64_t cd = qw * p10;             // the multiple at or below s ...
+    const bool in_d = cd >= a, in_u = cd + p10 <= b;   // ... and the one above it
+    bool up;
+    if (in_d && in_u) {
+        const uint64_t rm = W - cd;            // s - cd = rm + r / 2^sh
+        if (j == 0) {
+            const uint64_t half = sh ? uint64_t(1) << (sh - 1) : 0;      // r > 0 only when sh >= 1
+            up = r > half || (r == half && r && (qw & 1));
+        } else {
+            const uint64_t half = p10 / 2;
+            up = rm > half || (rm == half && (r || (qw & 1)));
+        }
+    } else {
+        up = in_u;
+    }
+    const uint64_t D = qw + (up ? 1 : 0);
+    const int n = int(put_u64(digits, D) - digits);
+    *nd = n;
+    *decpt = n + j - P;
+    return true;
+}
+
+inline char* put_score(char* p, float s) {
+    uint32_t bits;
+    memcpy(&bits, &s, 4);
+    char digits[48] = {0};
+    int nd, decpt;
+    if (shortest_f32(bits & 0x7fffffffu, digits, &nd, &decpt)) {
+        if (bits >> 31) *p++ = '-';
+        return layout_digits(p, digits, nd, decpt);
+    }
+    return p + py_repr_double(double(s), p);
 }
 
 }  // namespace
@@ -126,28 +324,73 @@ extern "C" {
 
 int cldrd_format_score(float s, char* buf) {
     if (!buf) return cldrd::fail(CLDRD_EINVAL, "format_score: NULL buffer");
-    return py_repr_double(double(s), buf);
+    char tmp[96];                       // put_score uses the bytes behind its result as scratch
+    const int n = int(put_score(tmp, s) - tmp);
+    memcpy(buf, tmp, size_t(n));
+    return n;
+}
+
+// The writer's fast path against the general one (std::to_chars digits) on `count` fp32 bit patterns
+// first, first + stride, ... (wrapping mod 2^32).  Returns the number of patterns whose text differs and the first
+// such pattern; how many of them the fast path took itself goes to *fast_taken.
+int64_t cldrd_format_score_selfcheck(uint32_t first, uint32_t stride, int64_t count, uint32_t* first_bad,
+                                     int64_t* fast_taken) {
+    int64_t bad = 0, fast = 0;
+    uint32_t bits = first;
+    char a[96], b[96];
+    for (int64_t i = 0; i < count; ++i, bits += stride) {
+        float s;
+        memcpy(&s, &bits, 4);
+        const int la = int(put_score(a, s) - a);
+        const int lb = py_repr_double(double(s), b);
+        char dg[48];
+        int nd, dp;
+        fast += shortest_f32(bits & 0x7fffffffu, dg, &nd, &dp) ? 1 : 0;
+        if (la != lb || memcmp(a, b, size_t(la)) != 0) {
+            if (!bad && first_bad) *first_bad = bits;
+            ++bad;
+        }
+    }
+    if (fast_taken) *fast_taken = fast;
+    return bad;
 }
 
 // One formatted line per hit.  `rank` is the 1-based rank of the first hit of this row.
 static inline char* format_row(char* p, int64_t qid, const float* s, const int64_t* d, int32_t k, int64_t rank) {
-    char qbuf[24];
-    const int qlen = int(put_i64(qbuf, qid) - qbuf);
+    // qid + tab and the rank column are kept as text and moved with fixed 24-byte copies (the bytes behind the
+    // field are overwritten by the next field); the rank counts up by one per line and is incremented in place
+    char qbuf[48] = {0}, rbuf[48] = {0};
+    const int qlen = int(put_i64(qbuf, qid) - qbuf) + 1;
+    qbuf[qlen - 1] = '\t';
+    int rlen = int(put_i64(rbuf, rank) - rbuf);
+    const bool counting = rank >= 0 && rank <= INT64_MAX - k;
     for (int32_t j = 0; j < k; ++j) {
-        memcpy(p, qbuf, qlen);
-        p += qlen;
+        copy24(p, qbuf);
+        p = put_i64(p + qlen, d[j]);
         *p++ = '\t';
-        p = put_i64(p, d[j]);
+        if (counting) {
+            copy24(p, rbuf);
+            p += rlen;
+            char* c = rbuf + rlen - 1;
+            while (c >= rbuf && *c == '9') *c-- = '0';
+            if (c >= rbuf) {
+                ++*c;
+            } else {                      // 99...9 -> 100...0
+                rbuf[0] = '1';
+                rbuf[rlen++] = '0';
+            }
+        } else {
+            p = put_i64(p, rank + j);
+        }
         *p++ = '\t';
-        p = put_i64(p, rank + j);
-        *p++ = '\t';
-        p += py_repr_double(double(s[j]), p);
+        p = put_score(p, s[j]);
         *p++ = '\n';
     }
     return p;
 }
 
-// longest line: 20 (qid) + 20 (docid) + 20 (rank) + 24 (score) + 4 separators
+// longest line: 20 (qid) + 20 (docid) + 20 (rank) + 24 (score) + 4 separators = 88; the fixed-size copies of
+// format_row / layout_digits touch up to 48 bytes behind the field they write, which the piece buffers' tail covers
 static constexpr size_t kMaxLine = 96;
 
 static int pwrite_all(int fd, const char* q, size_t n, off_t off, const char* path) {
@@ -205,7 +448,7 @@ int cldrd_write_run_mt(const char* path, const int64_t* qids, const float* score
     std::vector<int> rcs(size_t(T), CLDRD_OK);
     std::vector<std::string> errs{size_t(T)};
     auto worker = [&](int t) {
-        std::vector<char> buf(size_t(piece) * size_t(std::max(k, 1)) * kMaxLine + 64);
+        std::vector<char> buf(size_t(piece) * size_t(std::max(k, 1)) * kMaxLine + 128);
         for (;;) {
             const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
             if (i >= npieces) break;

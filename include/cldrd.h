@@ -351,7 +351,7 @@ int cldrd_write_run(const char* path, const int64_t* qids, const float* scores,
  * cores): rows are cut into ~4 MiB pieces, formatted in parallel and written with pwrite at
  * prefix-summed offsets, so the file is byte-identical to the single-threaded one.  At config 5
  * (502 939 x 200 = 100 M lines) the reference's Python loop (retrieve_top_passages.py:99-109) would
- * take minutes; one thread of this writer ~20 s. */
+ * take minutes; one thread of this writer a few seconds. */
 int cldrd_write_run_mt(const char* path, const int64_t* qids, const float* scores,
                        const int64_t* ids, int64_t nq, int32_t k, int32_t append, int32_t threads,
                        int64_t* lines_written);
@@ -359,6 +359,14 @@ int cldrd_write_run_mt(const char* path, const int64_t* qids, const float* score
 /* Format one float exactly as the reference's f-string does; returns the length written
  * (buf must hold >= 32 bytes). */
 int cldrd_format_score(float s, char* buf);
+
+/* Self-check of the score formatter: the writer prints fp32 scores through a specialised exact routine (one
+ * 64x64-bit product per score instead of a general double -> text conversion); this entry compares its text with
+ * the general routine's on `count` fp32 bit patterns first, first + stride, ... (mod 2^32).  Returns the number of
+ * patterns that differ (0 = identical; < 0 never), the first such pattern in *first_bad and how many patterns the
+ * specialised routine handled itself in *fast_taken (both optional).  tools/check_score_text.py sweeps all 2^32. */
+int64_t cldrd_format_score_selfcheck(uint32_t first, uint32_t stride, int64_t count, uint32_t* first_bad,
+                                     int64_t* fast_taken);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,56 @@ def test_score_text_matches_python_repr(cldrd_lib):
         assert cldrd.format_score(v) == repr(float(v)), float(v)
 
 
+def test_score_text_fast_path_equals_general_routine(cldrd_lib):
+    """The writer prints fp32 scores through a specialised exact routine (csrc/runfile.cpp: shortest_f32); the library
+    compares it with the general std::to_chars routine itself.  Here: 2^22 consecutive patterns around typical scores,
+    a stride that visits every exponent of both signs, and the exact-tie / power-of-two cases against Python's repr.
+    All 2^32 patterns: tools/check_score_text.py (profiles/r02_score_text_sweep.json: 0 differences)."""
+    import ctypes as C
+    import cldrd
+    bad, fast = C.c_uint32(0), C.c_int64(0)
+    first = int(np.array([100.0], dtype=np.float32).view(np.uint32)[0])
+    assert cldrd_lib.cldrd_format_score_selfcheck(first, 1, 1 << 22, C.byref(bad), C.byref(fast)) == 0, hex(bad.value)
+    assert fast.value == 1 << 22                       # these scores never leave the fast path
+    assert cldrd_lib.cldrd_format_score_selfcheck(12345, 1021, 1 << 22, C.byref(bad), C.byref(fast)) == 0, hex(bad.value)
+    assert 0 < fast.value < 1 << 22                    # zero / denormals / huge / inf / nan take the general one
+    ties = [512 + 1 / 2**14, 512 + 3 / 2**14, 1024 + 5 / 2**14, 2.0**-33, 2.0**-34, 2.0**52, 2.0**53, 2.0**24 - 1,
+            0.1, 1e-4, 9.9999e-5, 1e16, 9.9999998e15, 8388608.5, 0.0078125, 3.0e-10, 1.17549435e-38]
+    for v in ties + [-t for t in ties]:
+        v32 = np.float32(v)
+        assert cldrd.format_score(v32) == repr(float(v32)), float(v32)
+    for e in range(1, 255):                            # every power of two and its two neighbours
+        for frac in (0, 1, 0x7fffff):
+            v32 = np.array([(e << 23) | frac], dtype=np.uint32).view(np.float32)[0]
+            assert cldrd.format_score(v32) == repr(float(v32)), float(v32)
+
+
+def test_run_writer_extreme_ids_and_rank_carries(cldrd_lib, tmp_path):
+    """int64 extremes in every integer column, -1 pads, rank sequences that cross 9 -> 10 -> 100 -> 1000 and a
+    duplicate qid whose sequence continues past 99 999 -> 100 000: same bytes as the reference's loop."""
+    import cldrd
+    import oracle.flat_ip as O
+    k = 1200
+    rng = np.random.default_rng(5)
+    D = -np.sort(-rng.standard_normal((4, k)).astype(np.float32) * 1e3, axis=1)
+    I = rng.integers(-2**63, 2**63 - 1, (4, k), dtype=np.int64)
+    I[0, :3] = [-1, 2**63 - 1, -2**63]
+    D[1, -2:] = np.float32(-3.4028235e38)
+    qids = np.array([-2**63, 2**63 - 1, 7, 7], dtype=np.int64)
+    a, b = tmp_path / "a.tsv", tmp_path / "b.tsv"
+    cldrd.write_run_file(str(a), qids, I, D, threads=2)
+    O.write_run(str(b), qids.tolist(), I, D)
+    assert a.read_bytes() == b.read_bytes()
+    # 84 rows of one qid: its rank column runs from 1 to 100 800
+    qd = np.full(84, 3, dtype=np.int64)
+    D2 = np.tile(D[:1], (84, 1))
+    I2 = np.tile(I[1:2], (84, 1))
+    cldrd.write_run_file(str(a), qd, I2, D2, threads=3)
+    O.write_run(str(b), qd.tolist(), I2, D2)
+    assert a.read_bytes() == b.read_bytes()
+    assert a.read_bytes().splitlines()[-1].split(b"\t")[2] == b"100800"
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
 def test_reference_evaluator_consumes_our_run_file(cldrd_lib, tmp_path):
     """evaluation/retrieval_evaluator.py:42-76 reads cols 0,1 in file order: feed it our writer's output."""
