@@ -35,6 +35,7 @@ def load_checkpoint(model: torch.nn.Module, path: str, is_parallel: bool = True)
     checkpoint = torch.load(path, map_location="cpu")
     state_dict = checkpoint["state_dict"]
     if is_parallel:
+        print("load parallel wrapped model.")
         state_dict = OrderedDict((k[7:], v) for k, v in state_dict.items())  # remove `module.`
     model.load_state_dict(state_dict)
 
