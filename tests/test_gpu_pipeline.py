@@ -139,3 +139,37 @@ def test_retrieve_top_passages_under_torchrun_equals_single_process(cldrd_lib, t
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
     assert run2.read_bytes() == run1.read_bytes()
 
+
+
+def test_index_text_under_torchrun_on_two_gpus_is_byte_identical(cldrd_lib, tmp_path):
+    """The sharded index build on real GPUs (needs 2; NCCL group, fp16 autocast encoder on each rank's own device):
+    rank r encodes and writes its row range of the one file; same bytes and meta.pkl as the single-process build."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model_dir = _tiny_model_dir(tmp_path)
+    rng = np.random.default_rng(9)
+    coll = tmp_path / "collection.tsv"
+    pids = rng.permutation(100_000)[:512] + 7_000_000
+    with open(coll, "w") as f:
+        for pid in pids:
+            f.write(f"{pid}\t{' '.join(rng.choice(WORDS, size=rng.integers(5, 30)))}\n")
+    script = os.path.join(root, "cl-drd_b200", "retriever", "index_text.py")
+    # 512 rows, batches of 128: rank r's batches are exactly batches 2r, 2r+1 of the single-process run (same padding)
+    common = ["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir, "--passages_path", str(coll),
+              "--index_name", "ckpt", "--share_weights", "--batch_size", "128", "--max_length", "40"]
+    one, two = str(tmp_path / "one") + "/", str(tmp_path / "two") + "/"
+    r = subprocess.run([sys.executable, script] + common + ["--index_dir", one], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29557", script] + common + ["--index_dir", two], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    a, b = open(os.path.join(one, "ckpt.index"), "rb").read(), open(os.path.join(two, "ckpt.index"), "rb").read()
+    assert len(a) == len(b) == 82 + 512 * 64 * 4 + 8 + 512 * 8
+    assert a == b
+    xb, ids, info = O.read_index(os.path.join(two, "ckpt.index"))
+    assert info["fourcc"] == "IxMp" and ids.tolist() == pids.tolist() and np.isfinite(xb).all() and np.abs(xb).sum() > 0
+    ma, mb = (pickle.load(open(os.path.join(d, "meta.pkl"), "rb")) for d in (one, two))
+    assert ma["text_ids"].tolist() == mb["text_ids"].tolist() == pids.tolist() and ma["text_id_to_idx"] == mb["text_id_to_idx"]
