@@ -41,6 +41,7 @@ SIGNATURES = {
     "cldrd_index_writer_begin": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "cldrd_index_writer_open_range": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                                 C.c_int64, C.c_int32]),
+    "cldrd_index_writer_sync": (C.c_int, [C.c_void_p]),
     "cldrd_index_writer_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "cldrd_index_writer_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cldrd_index_read_rows": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),

@@ -228,6 +228,17 @@ int cldrd_index_writer_open_range(cldrd_index_writer** out, const char* path, in
         close(fd);
         return fail(CLDRD_EIO, "write to '%s' failed: %s", path, strerror(errno));
     }
+    if (!create) {      // joining a file somebody else created (or a build that is being continued): same layout?
+        unsigned char have[sizeof(hdr)];
+        int rfd = open(path, O_RDONLY);
+        const bool got = rfd >= 0 && pread_all(rfd, have, len, 0);
+        if (rfd >= 0) close(rfd);
+        if (!got || memcmp(have, hdr, len) != 0) {
+            close(fd);
+            return fail(CLDRD_EFORMAT, "'%s' does not declare %lld rows of dimension %d in this layout", path,
+                        (long long)n, (int)d);
+        }
+    }
     auto* w = new cldrd_index_writer();
     w->fd = fd;
     w->n = n;
@@ -260,13 +271,21 @@ int cldrd_index_writer_append(cldrd_index_writer* w, const float* rows_host, int
     return CLDRD_OK;
 }
 
+int cldrd_index_writer_sync(cldrd_index_writer* w) {
+    if (!w) return fail(CLDRD_EINVAL, "writer_sync: NULL");
+    if (fdatasync(w->fd) != 0) return fail(CLDRD_EIO, "fdatasync '%s' failed: %s", w->path.c_str(), strerror(errno));
+    return CLDRD_OK;
+}
+
 int cldrd_index_writer_finish(cldrd_index_writer* w, const int64_t* ids_host) {
     if (!w) return fail(CLDRD_EINVAL, "writer_finish: NULL");
     int rc = CLDRD_OK;
     if (w->rows_written != w->nrows)
         rc = fail(CLDRD_ESTATE, "writer_finish: %lld of %lld rows written", (long long)w->rows_written,
                   (long long)w->nrows);
-    if (!rc && w->with_ids && w->creator) {     // the creator writes the id array of ALL n rows
+    // the id array of ALL n rows: required from the writer that created the file, accepted from any other (the
+    // process that continues an interrupted build did not create the file)
+    if (!rc && w->with_ids && (w->creator || ids_host)) {
         if (!ids_host && w->n)
             rc = fail(CLDRD_EINVAL, "writer_finish: ids required");
         else {

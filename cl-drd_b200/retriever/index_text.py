@@ -7,9 +7,16 @@ Launched under torchrun (`torchrun --nproc-per-node G index_text.py ...`) the bu
 shard_ranges(N, G)[r] of the collection on its own GPU and writes them at their final offsets of the ONE index file
 (cldrd_index_writer_open_range); rank 0 creates the file, gathers the ids and writes the id array and meta.pkl.  The
 file is byte-identical to a single-process build (the 2.5 h the reference reports for 8.8 M passages on one GPU,
-README.md:20, are encoder time: it divides by G)."""
+README.md:20, are encoder time: it divides by G).
+
+An interrupted build can be continued (`--continue_build`): every rank records, in `<index file>.progress.<rank>of<G>`,
+how many of its rows are on stable storage (fdatasync first, then the record, every CLDRD_BUILD_SYNC_ROWS rows); a
+continued build skips those rows, encodes the rest in the same batches and ends with the same bytes as an
+uninterrupted one.  The reference's build holds everything in RAM until the end and starts over."""
 import argparse
 import ctypes as C
+import glob
+import json
 import os
 import pickle
 import sys
@@ -39,11 +46,29 @@ def get_args(argv=None):
     parser.add_argument("--share_weights", action="store_true", default=False)
     parser.add_argument("--batch_size", default=512, type=int)
     parser.add_argument("--index_name", default="", help="index file stem when --resume is empty")
+    parser.add_argument("--continue_build", action="store_true", default=False,
+                        help="continue an interrupted build of the same index file instead of starting over")
     args = parser.parse_args(argv)
     if args.resume:
         assert args.index_dir[:-7] in args.resume     # same guard as the reference (:50)
     os.makedirs(args.index_dir, exist_ok=True)     # (several ranks may get here at once)
     return args
+
+
+def _read_progress(path, expect):
+    """(rows of this rank's range already on stable storage, NaNs counted in them) from a progress record that belongs
+    to the same build (same collection size, dimension, row range and batch size); (0, 0) otherwise."""
+    try:
+        with open(path) as f:
+            p = json.load(f)
+    except (OSError, ValueError):
+        return 0, 0
+    if not isinstance(p, dict) or any(p.get(k) != v for k, v in expect.items()):
+        return 0, 0
+    done = p.get("done", 0)
+    if not isinstance(done, int) or not 0 <= done <= expect["nrows"]:
+        return 0, 0
+    return done, int(p.get("n_nan", 0))
 
 
 def main(args):
@@ -75,25 +100,65 @@ def main(args):
     dataset = SequenceDataset.create_from_seqs_file(path, tokenizer, args.max_length, is_query=args.is_query)
     n = len(dataset)
     rr = shard_ranges(n, world)[rank]               # this rank's rows of the collection, in file order
-    part = Subset(dataset, rr) if world > 1 else dataset
-    # the reference tokenises with 4 worker processes (retriever/index_text.py:84)
-    workers = int(os.environ.get("CLDRD_LOADER_WORKERS", "4"))
-    loader = DataLoader(part, batch_size=args.batch_size, shuffle=False, num_workers=workers, collate_fn=dataset.collate_fn)
     stem = (Path(args.resume).stem.split(".")[0] if args.resume else args.index_name) + ".index"
     index_path = os.path.join(args.index_dir, stem)
     hidden = model.query_encoder.config.hidden_size
-    w = C.c_void_p()
+    # Continue or start over: rank 0 looks at the file, everybody follows its decision.
+    fresh = True
+    if rank == 0:
+        if args.continue_build and os.path.exists(index_path):
+            # an interrupted build left headers + some rows and no id array yet: joining it as a writer of zero rows
+            # succeeds exactly when the file declares this collection size, dimension and layout
+            probe = C.c_void_p()
+            if lib().cldrd_index_writer_open_range(C.byref(probe), index_path.encode(), n, hidden, 1, 0, 0, 0, 0) == 0:
+                lib().cldrd_index_writer_finish(probe, None)
+                fresh = False
+        if fresh:
+            for stale in glob.glob(glob.escape(index_path) + ".progress.*"):
+                os.remove(stale)
     if world > 1:
         import torch.distributed as dist
-        if rank == 0:      # creates the file and its headers; the others open it once it exists
-            check(lib().cldrd_index_writer_open_range(C.byref(w), index_path.encode(), n, hidden, 1, 0, rr.start, len(rr), 1))
+        box = [fresh]
+        dist.broadcast_object_list(box, src=0)
+        fresh = bool(box[0])
+    progress_path = f"{index_path}.progress.{rank}of{world}"
+    expect = {"n": n, "d": hidden, "row0": rr.start, "nrows": len(rr), "batch_size": args.batch_size}
+    done, n_nan = (0, 0) if fresh else _read_progress(progress_path, expect)
+    if done:
+        print(f"[rank {rank}] continuing the build at row {rr.start + done} ({done} of {len(rr)} rows already in the file)")
+    todo = range(rr.start + done, rr.stop)
+    part = Subset(dataset, todo) if (world > 1 or done) else dataset
+    # the reference tokenises with 4 worker processes (retriever/index_text.py:84)
+    workers = int(os.environ.get("CLDRD_LOADER_WORKERS", "4"))
+    loader = DataLoader(part, batch_size=args.batch_size, shuffle=False, num_workers=workers, collate_fn=dataset.collate_fn)
+    w = C.c_void_p()
+    creator = fresh and rank == 0      # creates the file and its headers; the others open it once it exists
+    if creator:
+        check(lib().cldrd_index_writer_open_range(C.byref(w), index_path.encode(), n, hidden, 1, 0, todo.start, len(todo), 1))
+    if world > 1:
+        import torch.distributed as dist
         dist.barrier()
-        if rank != 0:
-            check(lib().cldrd_index_writer_open_range(C.byref(w), index_path.encode(), n, hidden, 1, 0, rr.start, len(rr), 0))
-    else:
-        check(lib().cldrd_index_writer_begin(C.byref(w), index_path.encode(), n, hidden, 1, 0))
-    text_ids = []
-    n_nan = 0
+    if not creator:
+        check(lib().cldrd_index_writer_open_range(C.byref(w), index_path.encode(), n, hidden, 1, 0, todo.start, len(todo), 0))
+    sync_rows = int(os.environ.get("CLDRD_BUILD_SYNC_ROWS", "65536"))        # 0: no progress records
+    fault_after = int(os.environ.get("CLDRD_FAULT_BUILD_AFTER_ROWS", "0"))   # fault injection (tests): die after that many rows
+    flushed = done                       # rows of this rank's range handed to the file
+    recorded = done                      # ... of which on stable storage and in the progress record
+
+    def record_progress():
+        nonlocal recorded
+        if sync_rows <= 0 or flushed == recorded:
+            return
+        check(lib().cldrd_index_writer_sync(w))          # the record never runs ahead of the data
+        tmp = progress_path + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(dict(expect, done=flushed, n_nan=n_nan), f)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, progress_path)
+        recorded = flushed
+
+    text_ids = [dataset.id_seq_pair[i][0] for i in range(rr.start, rr.start + done)]      # ids follow the file order
     # Two page-locked slots: batch i's rows travel device -> host and are appended to the file while the encoder
     # already works on batch i+1 (the reference blocks on `.cpu().numpy()` after every batch, retrieval_utils.py:47).
     on_gpu = dev.type == "cuda"
@@ -102,13 +167,18 @@ def main(args):
     pending = []      # (slot, rows) copied but not yet written
 
     def flush_one():
-        nonlocal n_nan
+        nonlocal n_nan, flushed
         slot, m = pending.pop(0)
         if on_gpu:
             ready[slot].synchronize()
         rows = slots[slot][:m].numpy()
         n_nan += int(np.isnan(rows).sum())
         check(lib().cldrd_index_writer_append(w, ptr(rows), m))
+        flushed += m
+        if sync_rows > 0 and flushed - recorded >= sync_rows:
+            record_progress()
+        if fault_after and flushed - done >= fault_after:
+            raise RuntimeError(f"CLDRD_FAULT_BUILD_AFTER_ROWS: injected failure after {flushed - done} rows")
 
     finished = False
     try:
@@ -130,6 +200,7 @@ def main(args):
                 flush_one()
         while pending:
             flush_one()
+        record_progress()      # this rank's range is complete: a continued build has nothing left to encode here
         if world > 1:      # ids of all ranks, in row order, on every rank (rank 0 writes them)
             import torch.distributed as dist
             parts = [None] * world
@@ -144,7 +215,7 @@ def main(args):
         finished = True
     finally:
         if not finished:      # encoder or I/O error mid-way: release the writer (handle, fd); the file stays incomplete
-            lib().cldrd_index_writer_finish(w, None)
+            lib().cldrd_index_writer_finish(w, None)      # (and can be completed with --continue_build)
     if rank == 0:
         meta = {"text_ids": text_ids_arr, "text_id_to_idx": {tid: idx for idx, tid in enumerate(text_ids)}}
         with open(os.path.join(args.index_dir, "meta.pkl"), "wb") as f:
@@ -154,6 +225,8 @@ def main(args):
         dist.barrier()       # every rank's rows are in the file when anybody returns
         if own_group:
             dist.destroy_process_group()
+    if os.path.exists(progress_path):      # the file is complete (ids and meta.pkl included): nothing to continue
+        os.remove(progress_path)
     return index_path
 
 
