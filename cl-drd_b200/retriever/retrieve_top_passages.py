@@ -73,8 +73,9 @@ def _encode(args, is_query_side):
                                        show_progress_bar=True, to_device=True)
 
 
-def main(args, is_query_side=True, header="# unique query"):
-    check_paths(args.queries_path, args.output_path)
+def main(args, is_query_side=True, header="# unique query", guards=True):
+    if guards:
+        check_paths(args.queries_path, args.output_path)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     os.environ.setdefault("CLDRD_SCAN", args.precision)

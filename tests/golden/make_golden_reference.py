@@ -6,6 +6,7 @@ What runs unmodified, from /root/reference, through its own entry points:
 
     retriever/index_text.py            get_args() + main()     -> <index_dir>/checkpoint_120000.index, meta.pkl
     retriever/retrieve_top_passages.py get_args() + main()     -> dev.run
+    retriever/retrieve_top_queries.py  get_args() + main()     -> passages.run   (k = 200, 40 passages against the same index)
     (and through them dataset/sequence_dataset.py, models/nway_dual_encoder.py,
      retriever/retrieval_utils.py: get_embeddings_from_scratch, convert_index_to_gpu, index_retrieve)
 
@@ -22,6 +23,9 @@ What is stubbed so that they run here, and nothing else:
                          torch.cuda.amp.autocast(enabled=True) is a no-op without CUDA.
     transformers.AdamW   removed from transformers 5.x; models/nway_dual_encoder.py:3 imports it (never uses it here).
     ujson                absent; dataset/nway_dataset.py:9 imports it (never used on this path) -> json.
+    models.dual_encoder  retrieve_top_queries.py:23 imports `DualEncoder` from a module the reference does not ship: aliased
+                         to the reference's own models/nway_dual_encoder.py:NwayDualEncoder (same constructor arguments,
+                         same passage_embs).
 
 Inputs are generated here from seeds and committed with the outputs (all small): a random-init DistilBERT-shaped
 two-tower model (dim 64, 1 layer, 29-word vocabulary) as an HF model directory + a DataParallel-style checkpoint
@@ -116,6 +120,19 @@ sys.argv = ["retrieve_top_passages.py", "--resume", work + "/experiment/models/c
 print("=== retrieve_top_passages ===")
 rp.main(rp.get_args())
 np.save(work + "/query_embs.npy", np.concatenate(SEARCH_LOG))
+del SEARCH_LOG[:]
+import models.nway_dual_encoder as nde
+alias = types.ModuleType("models.dual_encoder")
+alias.DualEncoder = nde.NwayDualEncoder
+sys.modules["models.dual_encoder"] = alias
+import retriever.retrieve_top_queries as rq
+assert rq.__file__.startswith(%(ref)r)
+sys.argv = ["retrieve_top_queries.py", "--model_name_or_path", work + "/tiny-distilbert",
+            "--tokenizer_name_or_path", work + "/tiny-distilbert", "--passages_path", work + "/passages.small.tsv",
+            "--index_path", work + "/experiment/index/checkpoint_120000.index", "--output_path", work + "/runs/passages.run"]
+print("=== retrieve_top_queries ===")
+rq.main(rq.get_args())
+np.save(work + "/passage_embs.npy", np.concatenate(SEARCH_LOG))
 '''
 
 
@@ -150,6 +167,9 @@ def build_inputs(work):
     with open(os.path.join(work, "queries.dev.tsv"), "w") as f:
         for qid in qids:
             f.write(f"{qid}\t{' '.join(rng.choice(WORDS, size=rng.integers(2, 8)))}\n")
+    with open(os.path.join(work, "passages.small.tsv"), "w") as f:
+        for pid in rng.permutation(9000)[:40] + 8_000_000:
+            f.write(f"{pid}\t{' '.join(rng.choice(WORDS, size=rng.integers(5, 30)))}\n")
 
 
 def main():
@@ -163,22 +183,24 @@ def main():
         raise SystemExit("the reference scripts failed")
     shutil.rmtree(OUT, ignore_errors=True)
     os.makedirs(OUT)
-    for name in ("tiny-distilbert", "collection.tsv", "queries.dev.tsv", "query_embs.npy"):
+    for name in ("tiny-distilbert", "collection.tsv", "queries.dev.tsv", "query_embs.npy", "passages.small.tsv", "passage_embs.npy"):
         src = os.path.join(work, name)
         (shutil.copytree if os.path.isdir(src) else shutil.copy)(src, os.path.join(OUT, name))
     shutil.copy(os.path.join(work, "experiment", "models", "checkpoint_120000.pth.tar"), OUT)
     shutil.copy(os.path.join(work, "experiment", "index", "checkpoint_120000.index"), OUT)
     shutil.copy(os.path.join(work, "experiment", "index", "meta.pkl"), OUT)
-    with open(os.path.join(work, "runs", "dev.run"), "rb") as f, gzip.GzipFile(os.path.join(OUT, "dev.run.gz"), "wb", mtime=0) as g:
-        g.write(f.read())
+    for run in ("dev.run", "passages.run"):
+        with open(os.path.join(work, "runs", run), "rb") as f, gzip.GzipFile(os.path.join(OUT, run + ".gz"), "wb", mtime=0) as g:
+            g.write(f.read())
     # the lines the scripts print that the mirrors must print too (progress bars and torch warnings dropped)
     keep = [ln for ln in r.stdout.splitlines()
             if ln.startswith(("===", "****", "load ", "# nan", "embs dtype", "retrieve ", "# unique", "average ranks", "Query Num"))]
     with open(os.path.join(OUT, "stdout.txt"), "w") as f:
         f.write("\n".join(ln.replace(work, "<work>") for ln in keep) + "\n")
     meta = pickle.load(open(os.path.join(OUT, "meta.pkl"), "rb"))
-    info = {"made_by": "tests/golden/make_golden_reference.py", "reference_scripts_run": ["retriever/index_text.py", "retriever/retrieve_top_passages.py"],
-            "stubs": ["faiss (oracle-backed)", "Tensor.cuda/Module.cuda -> self", "transformers.AdamW", "ujson -> json"],
+    info = {"made_by": "tests/golden/make_golden_reference.py", "reference_scripts_run": ["retriever/index_text.py", "retriever/retrieve_top_passages.py", "retriever/retrieve_top_queries.py"],
+            "stubs": ["faiss (oracle-backed)", "Tensor.cuda/Module.cuda -> self", "transformers.AdamW", "ujson -> json",
+                      "models.dual_encoder.DualEncoder -> models.nway_dual_encoder.NwayDualEncoder"],
             "passages": int(len(meta["text_ids"])), "queries": 24, "k": 1000, "dim": 64,
             "sizes": {n: os.path.getsize(os.path.join(OUT, n)) for n in sorted(os.listdir(OUT)) if os.path.isfile(os.path.join(OUT, n))}}
     with open(os.path.join(OUT, "README.json"), "w") as f:

@@ -33,8 +33,8 @@ def _ref_stdout(section):
     return lines[a + 1:b]
 
 
-def _golden_run():
-    return gzip.open(os.path.join(FIX, "dev.run.gz"), "rb").read()
+def _golden_run(name="dev.run.gz"):
+    return gzip.open(os.path.join(FIX, name), "rb").read()
 
 
 def _parse_run(text: bytes, k: int):
@@ -57,7 +57,8 @@ def _experiment(tmp_path):
 
 def test_fixture_is_what_the_generator_describes():
     info = __import__("json").load(open(os.path.join(FIX, "README.json")))
-    assert info["reference_scripts_run"] == ["retriever/index_text.py", "retriever/retrieve_top_passages.py"]
+    assert info["reference_scripts_run"] == ["retriever/index_text.py", "retriever/retrieve_top_passages.py",
+                                             "retriever/retrieve_top_queries.py"]
     for name, size in info["sizes"].items():
         if name != "README.json":
             assert os.path.getsize(os.path.join(FIX, name)) == size, name
@@ -166,6 +167,41 @@ def test_retrieve_loop_and_writer_reproduce_the_reference_run_file(cldrd_lib, tm
     for lo in range(0, 24, 7):
         st.put(np.asarray(qids[lo:lo + 7], dtype=np.int64), I[lo:lo + 7], D[lo:lo + 7])
     assert st.close() == avg and b.read_bytes() == gold
+
+
+def test_transposed_script_passages_to_top_queries(cldrd_lib, tmp_path):
+    """retriever/retrieve_top_queries.py as the reference ran it (k = 200, shared-weight encoder without a checkpoint,
+    max_length 256, no path guards): our encoder mirror reproduces its passage embeddings, our retrieve loop + writer its
+    `pid \\t qid \\t rank \\t score` file byte for byte, and the mirrored CLI is wired with the same roles and the
+    same summary line."""
+    import cldrd
+    from torch.utils.data import DataLoader
+    from transformers import AutoTokenizer
+    from cldrd.encoder import DualEncoder, SequenceDataset
+    from cldrd.retrieval_utils import get_embeddings_from_scratch, index_retrieve_arrays
+    from retriever import retrieve_top_queries
+    model_dir = os.path.join(FIX, "tiny-distilbert")
+    model = DualEncoder(model_dir, share_weights=True)
+    ds = SequenceDataset.create_from_seqs_file(os.path.join(FIX, "passages.small.tsv"), AutoTokenizer.from_pretrained(model_dir), 256, False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        embs, pids = get_embeddings_from_scratch(model, DataLoader(ds, batch_size=512, collate_fn=ds.collate_fn), True, False)
+    gold_embs = np.load(os.path.join(FIX, "passage_embs.npy"))
+    assert embs.shape == gold_embs.shape == (40, 64) and np.allclose(embs, gold_embs, rtol=1e-5, atol=1e-6)
+    gold = _golden_run("passages.run.gz")
+    p_ref, D_ref, I_ref = _parse_run(gold, 200)
+    assert pids == p_ref.tolist() == [int(ln.split("\t")[0]) for ln in open(os.path.join(FIX, "passages.small.tsv"))]
+    with contextlib.redirect_stdout(io.StringIO()):
+        D, I = index_retrieve_arrays(_OracleIndex(os.path.join(FIX, "checkpoint_120000.index")), gold_embs, 200)
+    out = tmp_path / "passages.run"
+    avg = cldrd.write_run_file(str(out), pids, I, D)
+    assert out.read_bytes() == gold
+    ref_lines = _ref_stdout("retrieve_top_queries")
+    assert ref_lines[-2:] == ["# unique passages = 40", f"average ranks per query = {avg}"]
+    # the mirrored CLI: same defaults, roles swapped, the reference's summary line, no path guards
+    a = retrieve_top_queries.get_args(["--passages_path", "x.tsv", "--index_path", "y", "--output_path", "z"])
+    assert a.top_k == 200 and a.max_length == 256 and a.share_weights and not a.is_parallel and a.queries_path == "x.tsv"
+    src = open(retrieve_top_queries.__file__).read()
+    assert 'header="# unique passages"' in src and "is_query_side=False" in src and "guards=False" in src
 
 
 def test_reader_takes_the_reference_built_index_file(cldrd_lib):
