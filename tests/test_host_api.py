@@ -270,3 +270,27 @@ def test_reference_retrieval_utils_imports_against_our_faiss(cldrd_lib):
     ) % (os.path.join(root, "cl-drd_b200", "compat"), REF, REF)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REF, timeout=300)
     assert r.returncode == 0 and "ok 0" in r.stdout, r.stderr[-2000:]
+
+
+def test_run_writer_random_shapes_equal_reference_loop(cldrd_lib, tmp_path):
+    """Random (nq, k, thread count, duplicate-qid runs, score scales from 1e-12 to 1e12, append splits): always the bytes
+    of the reference's regroup + f-string loops (retrieve_top_passages.py:90-109)."""
+    import cldrd
+    import oracle.flat_ip as O
+    rng = np.random.default_rng(11)
+    for case in range(12):
+        nq, k = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        scale = 10.0 ** rng.uniform(-12, 12)
+        D = (rng.standard_normal((nq, k)) * scale).astype(np.float32)
+        if case % 3 == 0:
+            D = np.round(D, 2)                         # short decimals: the formatter drops many digits
+        I = rng.integers(-1, 2**40, (nq, k), dtype=np.int64)
+        qids = np.sort(rng.integers(0, max(2, nq // 2), nq)).astype(np.int64) if case % 2 else rng.permutation(nq).astype(np.int64) + 5
+        a, b = tmp_path / f"a{case}.tsv", tmp_path / f"b{case}.tsv"
+        cut = int(rng.integers(0, nq + 1))
+        while 0 < cut < nq and qids[cut] == qids[cut - 1]:      # an append continues at a qid boundary, like RunFileStream's blocks
+            cut += 1
+        cldrd.write_run_file(str(a), qids[:cut], I[:cut], D[:cut], threads=int(rng.integers(1, 9)))
+        cldrd.write_run_file(str(a), qids[cut:], I[cut:], D[cut:], append=True, threads=int(rng.integers(1, 9)))
+        O.write_run(str(b), qids.tolist(), I, D)
+        assert a.read_bytes() == b.read_bytes(), (case, nq, k, scale)
