@@ -20,6 +20,7 @@ import json
 import os
 import pickle
 import sys
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -122,7 +123,11 @@ def main(args):
         dist.broadcast_object_list(box, src=0)
         fresh = bool(box[0])
     progress_path = f"{index_path}.progress.{rank}of{world}"
-    expect = {"n": n, "d": hidden, "row0": rr.start, "nrows": len(rr), "batch_size": args.batch_size}
+    # what a progress record must agree on to be continued: same collection size and dimension, same row range, same
+    # batches, and the same ids in the same order in this rank's range (a collection file that was edited in between)
+    ids_crc = zlib.crc32(np.fromiter((dataset.id_seq_pair[i][0] for i in rr), dtype=np.int64, count=len(rr)).tobytes())
+    expect = {"n": n, "d": hidden, "row0": rr.start, "nrows": len(rr), "batch_size": args.batch_size, "ids_crc": ids_crc,
+              "is_query": bool(args.is_query), "max_length": int(args.max_length)}
     done, n_nan = (0, 0) if fresh else _read_progress(progress_path, expect)
     if done:
         print(f"[rank {rank}] continuing the build at row {rr.start + done} ({done} of {len(rr)} rows already in the file)")
