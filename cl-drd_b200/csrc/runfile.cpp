@@ -491,3 +491,202 @@ int cldrd_write_run(const char* path, const int64_t* qids, const float* scores, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Run-file reader: "qid\tpid[\trank[\tscore]]" lines back into arrays (what evaluation/retrieval_evaluator.py:46-63
+// and the curriculum post-processing read; at config 5 the file has 100 M lines).  Same acceptance rule as the
+// reference's reader: a line is `line.strip().split("\t")`, must have 2 to 4 fields, fields 0 and 1 are integers.
+// The file is cut into byte ranges, one per thread; a line belongs to the range that holds its '\n'.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline bool is_py_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// int(field) for the canonical spellings: optional blanks, optional sign, decimal digits.  false otherwise
+// (including values outside int64, which no id of the retriever reaches).
+inline bool parse_i64_field(const char* b, const char* e, int64_t* out) {
+    while (b < e && is_py_space(*b)) ++b;
+    while (e > b && is_py_space(e[-1])) --e;
+    bool neg = false;
+    if (b < e && (*b == '+' || *b == '-')) neg = *b++ == '-';
+    if (b == e) return false;
+    uint64_t v = 0;
+    for (; b < e; ++b) {
+        const unsigned dgt = unsigned(*b) - unsigned('0');
+        if (dgt > 9) return false;
+        if (v > (UINT64_MAX - dgt) / 10) return false;
+        v = v * 10 + dgt;
+    }
+    if (v > uint64_t(INT64_MAX) + (neg ? 1u : 0u)) return false;
+    *out = neg ? int64_t(uint64_t(0) - v) : int64_t(v);
+    return true;
+}
+
+// 0 ok, 1 = field count outside 2..4, 2 = field 0 or 1 is not an integer
+inline int parse_run_line(const char* b, const char* e, int64_t* qid, int64_t* pid) {
+    while (b < e && is_py_space(*b)) ++b;
+    while (e > b && is_py_space(e[-1])) --e;
+    const char* t1 = static_cast<const char*>(memchr(b, '\t', size_t(e - b)));
+    if (!t1) return 1;
+    const char* t2 = static_cast<const char*>(memchr(t1 + 1, '\t', size_t(e - t1 - 1)));
+    const char* f1_end = t2 ? t2 : e;
+    if (t2) {
+        const char* t3 = static_cast<const char*>(memchr(t2 + 1, '\t', size_t(e - t2 - 1)));
+        if (t3 && memchr(t3 + 1, '\t', size_t(e - t3 - 1))) return 1;      // five fields or more
+    }
+    if (!parse_i64_field(b, t1, qid) || !parse_i64_field(t1 + 1, f1_end, pid)) return 2;
+    return 0;
+}
+
+struct RunSpan {
+    int64_t r0 = 0, r1 = 0;       // byte range scanned for '\n'
+    int64_t lines = 0;            // lines owned
+    int64_t last_nl = -1;         // position of the last '\n' in the range
+    int64_t begin = 0, end = 0;   // bytes of the owned lines
+    int64_t first_line = 0;       // index of the first owned line
+};
+
+}  // namespace
+
+extern "C" {
+
+int cldrd_read_run(const char* path, int64_t* qids, int64_t* pids, int64_t capacity, int32_t threads,
+                   int64_t* nlines, int64_t* bad_line) {
+    if (!path || !nlines || (qids == nullptr) != (pids == nullptr) || capacity < 0)
+        return cldrd::fail(CLDRD_EINVAL, "read_run: bad argument");
+    if (bad_line) *bad_line = -1;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return cldrd::fail(CLDRD_EIO, "cannot open run file '%s': %s", path, strerror(errno));
+    const int64_t size = int64_t(lseek(fd, 0, SEEK_END));
+    if (size < 0) {
+        close(fd);
+        return cldrd::fail(CLDRD_EIO, "cannot seek '%s': %s", path, strerror(errno));
+    }
+    int T = threads;
+    if (T <= 0) {
+        if (const char* e = getenv("CLDRD_WRITER_THREADS")) T = atoi(e);
+        if (T <= 0) T = int(std::thread::hardware_concurrency());
+    }
+    T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(T, 256), (size + (int64_t(4) << 20) - 1) / (int64_t(4) << 20))));
+    std::vector<RunSpan> sp{size_t(T)};
+    std::atomic<int> io_failed{0};
+    constexpr size_t kBlock = size_t(4) << 20;
+    auto in_threads = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto& x : th) x.join();
+    };
+    // pass 1: '\n' per byte range
+    in_threads([&](int t) {
+        RunSpan& s = sp[size_t(t)];
+        s.r0 = size * t / T;
+        s.r1 = size * (t + 1) / T;
+        std::vector<char> buf(kBlock);
+        for (int64_t pos = s.r0; pos < s.r1;) {
+            const size_t want = size_t(std::min<int64_t>(int64_t(kBlock), s.r1 - pos));
+            const ssize_t got = pread(fd, buf.data(), want, off_t(pos));
+            if (got <= 0) {
+                if (got < 0 && errno == EINTR) continue;
+                io_failed.store(1);
+                return;
+            }
+            const char* p = buf.data();
+            const char* lim = p + got;
+            while (const char* nl = static_cast<const char*>(memchr(p, '\n', size_t(lim - p)))) {
+                ++s.lines;
+                s.last_nl = pos + (nl - buf.data());
+                p = nl + 1;
+            }
+            pos += got;
+        }
+    });
+    if (io_failed.load()) {
+        close(fd);
+        return cldrd::fail(CLDRD_EIO, "read from '%s' failed", path);
+    }
+    int64_t total = 0, owned_to = 0;
+    for (int t = 0; t < T; ++t) {
+        RunSpan& s = sp[size_t(t)];
+        s.begin = owned_to;
+        s.end = s.last_nl >= 0 ? s.last_nl + 1 : owned_to;
+        owned_to = s.end;
+        s.first_line = total;
+        total += s.lines;
+    }
+    if (owned_to < size) {            // the last line has no '\n': it belongs to the last range
+        sp[size_t(T - 1)].end = size;
+        sp[size_t(T - 1)].lines += 1;
+        total += 1;
+    }
+    *nlines = total;
+    if (!qids) {
+        close(fd);
+        return CLDRD_OK;
+    }
+    if (capacity < total) {
+        close(fd);
+        return cldrd::fail(CLDRD_EINVAL, "read_run: %lld lines, room for %lld", (long long)total, (long long)capacity);
+    }
+    // pass 2: parse the owned lines
+    std::vector<int64_t> bad_at(size_t(T), -1);
+    std::vector<int> bad_kind(size_t(T), 0);
+    in_threads([&](int t) {
+        const RunSpan& s = sp[size_t(t)];
+        std::vector<char> buf(kBlock + (size_t(1) << 16));
+        size_t have = 0;
+        int64_t line = s.first_line;
+        auto take = [&](const char* b, const char* e) {
+            const int k = parse_run_line(b, e, qids + line, pids + line);
+            if (k && bad_at[size_t(t)] < 0) {
+                bad_at[size_t(t)] = line;
+                bad_kind[size_t(t)] = k;
+            }
+            ++line;
+        };
+        for (int64_t pos = s.begin; pos < s.end || have;) {
+            const size_t want = size_t(std::min<int64_t>(int64_t(buf.size() - have), s.end - pos));
+            size_t got = 0;
+            while (got < want) {
+                const ssize_t r = pread(fd, buf.data() + have + got, want - got, off_t(pos + int64_t(got)));
+                if (r <= 0) {
+                    if (r < 0 && errno == EINTR) continue;
+                    io_failed.store(1);
+                    return;
+                }
+                got += size_t(r);
+            }
+            pos += int64_t(got);
+            have += got;
+            const char* p = buf.data();
+            const char* lim = p + have;
+            while (const char* nl = static_cast<const char*>(memchr(p, '\n', size_t(lim - p)))) {
+                take(p, nl);
+                p = nl + 1;
+            }
+            if (pos >= s.end) {
+                if (p < lim) take(p, lim);          // the unterminated last line of the file
+                break;
+            }
+            have = size_t(lim - p);
+            if (have == buf.size()) {               // a "line" longer than the buffer: not a run file
+                bad_at[size_t(t)] = line;
+                bad_kind[size_t(t)] = 1;
+                return;
+            }
+            memmove(buf.data(), p, have);
+        }
+    });
+    close(fd);
+    if (io_failed.load()) return cldrd::fail(CLDRD_EIO, "read from '%s' failed", path);
+    for (int t = 0; t < T; ++t)
+        if (bad_at[size_t(t)] >= 0) {
+            if (bad_line) *bad_line = bad_at[size_t(t)];
+            return cldrd::fail(CLDRD_EFORMAT, "%s: line %lld of '%s'",
+                               bad_kind[size_t(t)] == 1 ? "array length is not legal" : "not an integer id",
+                               (long long)(bad_at[size_t(t)] + 1), path);
+        }
+    return CLDRD_OK;
+}
+
+}  // extern "C"

@@ -361,6 +361,15 @@ int cldrd_write_run_mt(const char* path, const int64_t* qids, const float* score
                        const int64_t* ids, int64_t nq, int32_t k, int32_t append, int32_t threads,
                        int64_t* lines_written);
 
+/* Run-file reader (the other direction: what evaluation/retrieval_evaluator.py:46-63 and the curriculum
+ * post-processing of the top-200 runs do line by line in Python; 100 M lines at config 5).  Every line is
+ * `line.strip().split("\t")` as in the reference: 2 to 4 fields, fields 0 and 1 integers (qid, pid); rank and score are
+ * not needed by either consumer (file order IS rank order) and are skipped.  Call with qids = pids = NULL to learn
+ * *nlines, then with arrays of that capacity: line i's ids land in qids[i], pids[i].  threads: as cldrd_write_run_mt.
+ * CLDRD_EFORMAT + *bad_line (0-based, optional) on the first line the reference's reader would reject. */
+int cldrd_read_run(const char* path, int64_t* qids, int64_t* pids, int64_t capacity, int32_t threads,
+                   int64_t* nlines, int64_t* bad_line);
+
 /* Format one float exactly as the reference's f-string does; returns the length written
  * (buf must hold >= 32 bytes). */
 int cldrd_format_score(float s, char* buf);

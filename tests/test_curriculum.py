@@ -222,3 +222,73 @@ def test_teacher_rerank_orders_the_candidates_before_the_cut(tmp_path):
                          "--label_mode", "9"]))
     got = [json.loads(ln) for ln in out.read_text().splitlines()]
     assert got == ex
+
+
+def _py_read_run(path):
+    """The reference's reader loop (evaluation/retrieval_evaluator.py:46-63), lists per qid in first-seen order."""
+    order, lists = {}, []
+    with open(path, "r") as f:
+        for line in f:
+            a = line.strip().split("\t")
+            if not 2 <= len(a) <= 4:
+                raise ValueError("array length is not legal.")
+            q, p = int(a[0]), int(a[1])
+            if q not in order:
+                order[q] = len(lists)
+                lists.append([])
+            lists[order[q]].append(p)
+    return list(order), lists
+
+
+def _same(native, ref):
+    q, lists = native
+    return q.tolist() == ref[0] and len(lists) == len(ref[1]) and all(a.tolist() == b for a, b in zip(lists, ref[1]))
+
+
+def test_native_run_reader_equals_the_reference_reader_loop(tmp_path):
+    """cldrd_read_run (parallel, two passes) against the line loop of the reference's reader: column variants, CRLF,
+    blanks around fields, an unterminated last line, qids that come back later, int64 extremes, the empty file."""
+    p = tmp_path / "a.run"
+    p.write_bytes(b"7\t100\n7\t101\t2\n  8\t200\t1\t3.5\r\n9\t-1\t1\t-3.4028234663852886e+38\n7\t102\t3\t1.0  \n"
+                  b"+10\t 300 \t1\n-9223372036854775808\t9223372036854775807\t1\t0.5\n8\t201")
+    assert _same(CU.read_run(p), _py_read_run(p))
+    q, lists = CU.read_run(p)
+    assert q.tolist() == [7, 8, 9, 10, -2**63] and lists[0].tolist() == [100, 101, 102] and lists[1].tolist() == [200, 201]
+    (tmp_path / "empty.run").write_bytes(b"")
+    q, lists = CU.read_run(tmp_path / "empty.run")
+    assert q.shape == (0,) and lists == []
+    for bad, what in ((b"1\t2\n3\n", "array length"), (b"1\t2\t3\t4\t5\n", "array length"), (b"1\t2\n\n3\t4\n", "array length"),
+                      (b"1\tx\n", "integer"), (b"1.5\t2\n", "integer"), (b"1\t2\n \n", "array length")):
+        (tmp_path / "bad.run").write_bytes(bad)
+        with pytest.raises(ValueError, match=what):
+            CU.read_run(tmp_path / "bad.run")
+        with pytest.raises(ValueError):
+            _py_read_run(tmp_path / "bad.run")
+    (tmp_path / "bad.run").write_bytes(b"1\t2\n3\t99999999999999999999\n")       # an id no int64 array can hold
+    with pytest.raises(ValueError, match="integer"):
+        CU.read_run(tmp_path / "bad.run")
+    with pytest.raises(Exception):
+        CU.read_run(tmp_path / "missing.run")
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_native_run_reader_across_thread_ranges(tmp_path, threads):
+    """A file of several 4 MiB ranges (the unit a reader thread gets), lines of uneven length so that range borders fall
+    inside lines, with and without a final newline: same arrays for every thread count, equal to the reference loop."""
+    import cldrd
+    rng = np.random.default_rng(threads)
+    nq, k = 1500, 200
+    D = (rng.standard_normal((nq, k)) * 10.0 ** rng.integers(-3, 6, (nq, 1))).astype(np.float32)
+    I = rng.integers(0, 2**40, (nq, k), dtype=np.int64) // rng.integers(1, 2**30, (nq, k))
+    qids = rng.permutation(nq).astype(np.int64) * 977 + 3
+    run = tmp_path / "big.run"
+    cldrd.write_run_file(str(run), qids, I, D)
+    assert os.path.getsize(run) > 9 << 20
+    q, p = CU.read_run_arrays(run, threads)
+    assert np.array_equal(q, np.repeat(qids, k)) and np.array_equal(p, I.reshape(-1))
+    raw = run.read_bytes()
+    run.write_bytes(raw[:-1])                               # no newline at the end of the file
+    q2, p2 = CU.read_run_arrays(run, threads)
+    assert np.array_equal(q2, q) and np.array_equal(p2, p)
+    if threads == 3:
+        assert _same(CU.read_run(run, threads), _py_read_run(run))
