@@ -186,3 +186,13 @@ def ranklists_for_evaluator(query_ids, nn_ids) -> Dict[int, List[int]]:
     for q, row in zip(np.asarray(query_ids, dtype=np.int64).tolist(), nn_ids):
         out.setdefault(q, []).extend(row[row >= 0].tolist())
     return out
+
+
+def ranklists_from_run_file(path, threads: int = 0) -> Dict[int, List[int]]:
+    """The `qid_to_ranklist` dict that `RankingEvaluator.compute_metrics` builds from a run file line by line
+    (evaluation/retrieval_evaluator.py:46-63), built by the native reader instead: same keys in the same order, same
+    lists (padding ids included, exactly what the reference's loop would hold).  Pass it to
+    `_calculate_metrics_plain(ranklists, evaluator.qid_to_relevant_data, binarization_point=...)` (:64-76)."""
+    qids, lists = read_run(path, threads)
+    return {int(q): l.tolist() for q, l in zip(qids.tolist(), lists)}
+

@@ -173,6 +173,12 @@ def test_in_memory_hand_off_matches_run_file_metrics(tmp_path):
     in_mem = in_mem[0] if isinstance(in_mem, tuple) else in_mem
     for key, v in from_file.items():
         assert in_mem[key] == v, key
+    # and the dict built from the run file by the native reader: the very dict compute_metrics builds for itself
+    from_native = CU.ranklists_from_run_file(run)
+    assert list(from_native) == qids.tolist() and from_native == {int(q): row.tolist() for q, row in zip(qids, I)}
+    m2 = ev._calculate_metrics_plain(from_native, ev.qid_to_relevant_data, binarization_point=1.)
+    m2 = m2[0] if isinstance(m2, tuple) else m2
+    assert m2 == from_file
 
 
 def _teacher_file(path, qids, lists, seed=11, drop_every=7):
