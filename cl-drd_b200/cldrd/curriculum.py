@@ -110,6 +110,18 @@ def _window(ranked: np.ndarray, lo: int, hi: int) -> np.ndarray:
     return ranked[min(lo, ranked.shape[0]):min(hi, ranked.shape[0])]
 
 
+def _draw(pool: np.ndarray, keys: np.ndarray, n: int) -> np.ndarray:
+    """n members of pool without replacement, in pool (= rank) order: those with the n smallest keys."""
+    if n == 0:
+        return pool[:0]
+    m = pool.shape[0]
+    pick = np.argpartition(keys[:m], n - 1)[:n] if n < m else np.arange(m)
+    return pool[np.sort(pick)]
+
+
+GROUP_BLOCK = 8192      # queries per block of random keys (part of what `seed` means: do not change)
+
+
 def build_groups(qids: Sequence[int], ranked_pids: Sequence[np.ndarray], n_rel: int = 10, n_most: int = 10,
                  n_semi: int = 10, most_window: Optional[Tuple[int, int]] = None,
                  semi_window: Optional[Tuple[int, int]] = None, qrels: Optional[Dict[int, Iterable[int]]] = None,
@@ -120,19 +132,27 @@ def build_groups(qids: Sequence[int], ranked_pids: Sequence[np.ndarray], n_rel: 
     top_k) are dropped first.  `qrels` (qid -> judged-relevant pids), when given, are moved to the front of the
     relevant group - the human positive is always a member, like `rel_pid` in the reference's other loaders
     (dataset/nway_dataset.py:204-209) - and never sampled as a negative.
-    strict: a query whose lists cannot be filled raises (the dataset would assert later); else it is skipped."""
+    strict: a query whose lists cannot be filled raises (the dataset would assert later); else it is skipped.
+
+    The draw: every query gets one uniform key per window position (PCG64(seed), blocks of GROUP_BLOCK queries) and
+    takes the positions with the smallest keys.  Queries whose list needs no clean-up (no padding, no repeated pid, no
+    judged positive, the block's common length) are cut as one matrix per block; the others one by one, by the same
+    rule and with the same keys, so the result does not depend on which way a query went (config 5: 502 939 queries)."""
     assert n_rel >= 1 and n_most >= 0 and n_semi >= 0
     most_window = most_window or (n_rel, max(50, n_rel + n_most))
     semi_window = semi_window or (most_window[1], max(200, most_window[1] + n_semi))
     assert most_window[0] >= n_rel and semi_window[0] >= most_window[1], "windows must not overlap"
     rng = np.random.Generator(np.random.PCG64(seed))
-    out = []
-    for qid, ranked in zip(qids, ranked_pids):
+    wm, ws = most_window[1] - most_window[0], semi_window[1] - semi_window[0]
+    qids = [int(q) for q in (qids.tolist() if isinstance(qids, np.ndarray) else qids)]
+    out: List[Optional[dict]] = []
+
+    def one(qid: int, ranked: np.ndarray, km: np.ndarray, ks: np.ndarray) -> Optional[dict]:
         ranked = np.asarray(ranked, dtype=np.int64)
         ranked = ranked[ranked >= 0]
         _, first = np.unique(ranked, return_index=True)          # a reranked list may repeat a pid
         ranked = ranked[np.sort(first)]
-        pos = [int(p) for p in qrels.get(int(qid), ())] if qrels else []
+        pos = [int(p) for p in qrels.get(qid, ())] if qrels else []
         if pos:
             ranked = ranked[~np.isin(ranked, pos)]
             take = max(n_rel - len(pos), 0)
@@ -145,13 +165,46 @@ def build_groups(qids: Sequence[int], ranked_pids: Sequence[np.ndarray], n_rel: 
         semi_pool = _window(ranked, *semi_window)
         if len(rel) < n_rel or most_pool.shape[0] < n_most or semi_pool.shape[0] < n_semi:
             if strict:
-                raise ValueError(f"qid {int(qid)}: {ranked.shape[0]} ranked passages cannot fill "
+                raise ValueError(f"qid {qid}: {ranked.shape[0]} ranked passages cannot fill "
                                  f"{n_rel}+{n_most}+{n_semi} from windows {most_window}, {semi_window}")
-            continue
-        most = most_pool[np.sort(rng.choice(most_pool.shape[0], n_most, replace=False))] if n_most else most_pool[:0]
-        semi = semi_pool[np.sort(rng.choice(semi_pool.shape[0], n_semi, replace=False))] if n_semi else semi_pool[:0]
-        out.append({"qid": int(qid), "relT_pids": [int(p) for p in rel],
-                    "most_hard_pids": most.tolist(), "semi_hard_pids": semi.tolist()})
+            return None
+        return {"qid": qid, "relT_pids": [int(p) for p in rel], "most_hard_pids": _draw(most_pool, km, n_most).tolist(),
+                "semi_hard_pids": _draw(semi_pool, ks, n_semi).tolist()}
+
+    for b0 in range(0, len(qids), GROUP_BLOCK):
+        bq = qids[b0:b0 + GROUP_BLOCK]
+        bl = [np.asarray(l, dtype=np.int64) for l in ranked_pids[b0:b0 + GROUP_BLOCK]]
+        m = len(bq)
+        km, ks = rng.random((m, wm)), rng.random((m, ws))
+        res: List[Optional[dict]] = [None] * m
+        done = np.zeros(m, dtype=bool)
+        lens = np.fromiter((l.shape[0] for l in bl), dtype=np.int64, count=m)
+        L = int(np.bincount(lens).argmax()) if m else 0
+        plain = np.flatnonzero(lens == L)
+        if qrels:
+            plain = plain[[bq[i] not in qrels or not list(qrels[bq[i]]) for i in plain.tolist()]] if plain.size else plain
+        if plain.size and L >= n_rel:
+            R = np.stack([bl[i] for i in plain.tolist()])
+            srt = np.sort(R, axis=1)
+            ok = (R >= 0).all(axis=1) & ~(srt[:, 1:] == srt[:, :-1]).any(axis=1)
+            plain, R = plain[ok], R[ok]
+            mp, spl = R[:, most_window[0]:most_window[1]], R[:, semi_window[0]:semi_window[1]]
+            if plain.size and mp.shape[1] >= n_most and spl.shape[1] >= n_semi:
+                def draw(pool, keys, n):
+                    if n == 0:
+                        return pool[:, :0]
+                    w = pool.shape[1]
+                    pick = np.argpartition(keys[:, :w], n - 1, axis=1)[:, :n] if n < w else np.tile(np.arange(w), (pool.shape[0], 1))
+                    return np.take_along_axis(pool, np.sort(pick, axis=1), axis=1)
+                rel_l = R[:, :n_rel].tolist()
+                most_l = draw(mp, km[plain], n_most).tolist()
+                semi_l = draw(spl, ks[plain], n_semi).tolist()
+                for j, i in enumerate(plain.tolist()):
+                    res[i] = {"qid": bq[i], "relT_pids": rel_l[j], "most_hard_pids": most_l[j], "semi_hard_pids": semi_l[j]}
+                done[plain] = True
+        for i in np.flatnonzero(~done).tolist():
+            res[i] = one(bq[i], bl[i], km[i], ks[i])
+        out.extend(r for r in res if r is not None)
     return out
 
 

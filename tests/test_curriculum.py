@@ -298,3 +298,24 @@ def test_native_run_reader_across_thread_ranges(tmp_path, threads):
     assert np.array_equal(q2, q) and np.array_equal(p2, p)
     if threads == 3:
         assert _same(CU.read_run(run, threads), _py_read_run(run))
+
+
+def test_matrix_path_and_one_by_one_path_cut_the_same_groups():
+    """build_groups cuts plain queries (no padding, no repeats, no positive, common length) as one matrix per block and
+    the rest one by one; both follow the same rule with the same keys.  Ranks beyond every window, appended in varying
+    numbers, push queries onto the one-by-one path without changing what they should get."""
+    qids, lists = _ranked(nq=300, depth=200, seed=9)
+    fast = CU.build_groups(qids, lists, seed=4)
+    longer = [np.concatenate([l, np.arange(10**6, 10**6 + 1 + (i % 7))]) if i % 3 else l for i, l in enumerate(lists)]
+    assert fast == CU.build_groups(qids, longer, seed=4)
+    # padding behind rank 200 and a repeated pid behind rank 200 change nothing either
+    messy = [np.concatenate([l, [-1, -1, l[0]]]) if i % 2 else l for i, l in enumerate(lists)]
+    assert fast == CU.build_groups(qids, messy, seed=4)
+    # qrels for a few queries: the others keep their draws
+    qrels = {int(qids[5]): [int(lists[5][77])], int(qids[6]): []}
+    with_q = CU.build_groups(qids, lists, seed=4, qrels=qrels)
+    assert [e for i, e in enumerate(with_q) if i != 5] == [e for i, e in enumerate(fast) if i != 5]
+    assert with_q[5]["relT_pids"][0] == int(lists[5][77])
+    # all sizes at their limits: windows exactly as wide as the draw
+    e = CU.build_groups(qids[:3], lists[:3], n_rel=5, n_most=5, n_semi=190, most_window=(5, 10), semi_window=(10, 200))
+    assert all(x["most_hard_pids"] == l[5:10].tolist() and x["semi_hard_pids"] == l[10:200].tolist() for x, l in zip(e, lists))
