@@ -14,6 +14,12 @@ and anchors on the reference's own call sites:
   * regroup + run-file formatting     retriever/retrieve_top_passages.py:90-109
   * ``meta.pkl``                      retriever/index_text.py:107-109
 
+What IS pinned: the restatements of the reference's own Python on this path -- ``index_retrieve``, ``regroup``,
+``write_run``, ``write_meta`` -- reproduce, byte for byte, the files the reference's unmodified scripts wrote when they
+were run in this container (tests/golden/make_golden_reference.py -> tests/golden/ref_pipeline/;
+tests/test_oracle.py::test_oracle_restatements_reproduce_the_reference_run_here).  What stays unpinned: ``search`` and
+the index-file bytes (faiss' own code), for which only the published semantics and the literal offsets exist.
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import this module.  The product path (``cl-drd_b200/``) never does:
 it has no CPU search at all and fails loudly when the CUDA library is missing.

@@ -176,3 +176,29 @@ def test_bench_checker_agrees_with_the_oracle():
     assert np.allclose(s.numpy(), D64, rtol=1e-12, atol=0)
     s, r = bench.brute_force_shard(torch, torch.from_numpy(xb[:5]), 0, torch.from_numpy(xq), 8)
     assert (r.numpy()[:, 5:] == -1).all() and np.isinf(s.numpy()[:, 5:]).all()
+
+
+def test_oracle_restatements_reproduce_the_reference_run_here(tmp_path):
+    """The oracle's restatements of the reference's OWN code (index_retrieve loop, regroup, f-string writer, meta.pkl)
+    against files the reference's scripts produced in this container (tests/golden/ref_pipeline/, generator:
+    tests/golden/make_golden_reference.py): byte for byte.  This pins those restatements to the reference itself; the
+    search arithmetic and the index-file bytes inside the fixture are the oracle's (faiss is absent) and stay unpinned."""
+    import gzip
+    import pickle
+    fix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pipeline")
+    xb, ids, _ = O.read_index(os.path.join(fix, "checkpoint_120000.index"))
+    for run, embs, tsv, k in (("dev.run.gz", "query_embs.npy", "queries.dev.tsv", 1000),
+                              ("passages.run.gz", "passage_embs.npy", "passages.small.tsv", 200)):
+        xq = np.load(os.path.join(fix, embs))
+        text_ids = [int(ln.split("\t")[0]) for ln in open(os.path.join(fix, tsv))]
+        nn_scores, nn_ids = O.index_retrieve(xb, ids, xq, k, batch=128)
+        assert isinstance(nn_scores, list) and isinstance(nn_scores[0][0], float)
+        out = tmp_path / run[:-3]
+        avg = O.write_run(str(out), text_ids, nn_ids, nn_scores)
+        assert out.read_bytes() == gzip.open(os.path.join(fix, run), "rb").read()
+        assert avg == float(k)
+    O.write_meta(str(tmp_path), ids.tolist())
+    ours, gold = (pickle.load(open(os.path.join(d, "meta.pkl"), "rb")) for d in (str(tmp_path), fix))
+    assert ours["text_ids"].dtype == gold["text_ids"].dtype and ours["text_ids"].tolist() == gold["text_ids"].tolist()
+    assert ours["text_id_to_idx"] == gold["text_id_to_idx"] and list(ours["text_id_to_idx"]) == list(gold["text_id_to_idx"])
+    assert open(os.path.join(str(tmp_path), "meta.pkl"), "rb").read() == open(os.path.join(fix, "meta.pkl"), "rb").read()
