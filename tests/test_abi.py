@@ -112,3 +112,33 @@ def test_header_constants_match_python_side():
     assert int(consts["CLDRD_QUERY_BATCH"]) == _lib.QUERY_BATCH
     assert int(consts["CLDRD_PEER_HANDLE_BYTES"]) == _lib.PEER_HANDLE_BYTES
     assert int(consts["CLDRD_MAX_OUT_SETS"]) == _lib.MAX_OUT_SETS
+
+
+def test_integration_md_ctypes_stub_is_live(cldrd_lib, tmp_path):
+    """The binding INTEGRATION.md §2 tells a maintainer to add next to retrieval_utils.py is executed as written
+    (library path substituted): it must load the library, probe an index file with the documented argument list and
+    reach cldrd_shard_create -- which, on this GPU-less box, must refuse loudly instead of falling back to anything."""
+    import re
+    import numpy as np
+    from oracle import flat_ip as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    sec = md[md.index("## 2. The ctypes stub"):md.index("## 3.")]
+    code = re.search(r"```python\n(.*?)```", sec, re.S).group(1)
+    assert "class B200FlatIP" in code and "/path/to/cl-drd_b200/cldrd/libcldrd.so" in code
+    code = code.replace("/path/to/cl-drd_b200/cldrd/libcldrd.so", os.path.join(root, "cl-drd_b200", "cldrd", "libcldrd.so"))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md#2", "exec"), ns)
+    path = str(tmp_path / "t.index")
+    O.write_index(path, O.synth(64, 64, 0), O.synth_ids(64))
+    import torch
+    if torch.cuda.is_available():
+        idx = ns["B200FlatIP"](path)
+        D, I = idx.search(O.synth(3, 64, 1), 5)
+        assert D.shape == (3, 5) and I.shape == (3, 5)
+    else:
+        ns["B200FlatIP"].__del__ = lambda self: None          # nothing was created
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns["B200FlatIP"](path)
+    with pytest.raises(RuntimeError, match="cannot open"):
+        ns["_ck"](ns["_lib"].cldrd_index_probe(b"/nonexistent.index", None, None, None, None, None, None, None))
