@@ -15,6 +15,7 @@ continued build skips those rows, encodes the rest in the same batches and ends 
 uninterrupted one.  The reference's build holds everything in RAM until the end and starts over."""
 import argparse
 import ctypes as C
+import errno
 import glob
 import json
 import os
@@ -54,6 +55,11 @@ def get_args(argv=None):
         assert args.index_dir[:-7] in args.resume     # same guard as the reference (:50)
     os.makedirs(args.index_dir, exist_ok=True)     # (several ranks may get here at once)
     return args
+
+
+def _free_bytes(directory) -> int:
+    vfs = os.statvfs(directory)
+    return vfs.f_bavail * vfs.f_frsize
 
 
 def _read_progress(path, expect):
@@ -117,11 +123,19 @@ def main(args):
         if fresh:
             for stale in glob.glob(glob.escape(index_path) + ".progress.*"):
                 os.remove(stale)
+            # fail now, not after hours of encoding: the whole file (headers + rows + id array) must fit
+            need = 82 + n * hidden * 4 + 8 + n * 8
+            have = _free_bytes(args.index_dir) + (os.path.getsize(index_path) if os.path.exists(index_path) else 0)
+            if have < need:
+                fresh = None
     if world > 1:
         import torch.distributed as dist
         box = [fresh]
         dist.broadcast_object_list(box, src=0)
-        fresh = bool(box[0])
+        fresh = box[0]
+    if fresh is None:      # every rank raises (nobody is left waiting in a collective)
+        raise OSError(errno.ENOSPC, f"not enough room in {args.index_dir!r} for an index of {n} x {hidden} rows "
+                                    f"({82 + n * hidden * 4 + 8 + n * 8} bytes)")
     progress_path = f"{index_path}.progress.{rank}of{world}"
     # what a progress record must agree on to be continued: same collection size and dimension, same row range, same
     # batches, and the same ids in the same order in this rank's range (a collection file that was edited in between)

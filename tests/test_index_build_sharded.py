@@ -181,3 +181,27 @@ def test_interrupted_sharded_build_continues_to_the_same_bytes(cldrd_lib, tmp_pa
     assert open(os.path.join(one, "ckpt.index"), "rb").read() == open(os.path.join(two, "ckpt.index"), "rb").read()
     assert open(os.path.join(one, "meta.pkl"), "rb").read() == open(os.path.join(two, "meta.pkl"), "rb").read()
     assert not [f for f in os.listdir(two) if "progress" in f]
+
+
+def test_build_refuses_a_full_disk_before_encoding(cldrd_lib, tmp_path, monkeypatch):
+    """The room for the whole index file is checked before the first batch is encoded (the reference finds out in
+    faiss.write_index, after the 2.5 h of encoding); a continued build only needs what is still missing."""
+    import pytest
+    sys.path.insert(0, os.path.join(ROOT, "cl-drd_b200"))
+    from retriever import index_text
+    model_dir = _tiny_model_dir(tmp_path)
+    coll, pids = _collection(tmp_path, n=64)
+    common = ["--model_name_or_path", model_dir, "--tokenizer_name_or_path", model_dir, "--passages_path", str(coll),
+              "--index_name", "ckpt", "--share_weights", "--batch_size", "32", "--max_length", "32"]
+    need = 82 + 64 * 32 * 4 + 8 + 64 * 8
+    monkeypatch.setattr(index_text, "_free_bytes", lambda d: need - 1)
+    out = str(tmp_path / "full") + "/"
+    with pytest.raises(OSError, match="not enough room"):
+        _build_in_process(common + ["--index_dir", out], monkeypatch)
+    assert not os.path.exists(os.path.join(out, "ckpt.index"))
+    monkeypatch.setattr(index_text, "_free_bytes", lambda d: need)
+    _build_in_process(common + ["--index_dir", out], monkeypatch)
+    assert os.path.getsize(os.path.join(out, "ckpt.index")) == need
+    # rebuilding over an existing file of the same size needs no extra room
+    monkeypatch.setattr(index_text, "_free_bytes", lambda d: 0)
+    _build_in_process(common + ["--index_dir", out], monkeypatch)
