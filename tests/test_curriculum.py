@@ -319,3 +319,17 @@ def test_matrix_path_and_one_by_one_path_cut_the_same_groups():
     # all sizes at their limits: windows exactly as wide as the draw
     e = CU.build_groups(qids[:3], lists[:3], n_rel=5, n_most=5, n_semi=190, most_window=(5, 10), semi_window=(10, 200))
     assert all(x["most_hard_pids"] == l[5:10].tolist() and x["semi_hard_pids"] == l[10:200].tolist() for x, l in zip(e, lists))
+
+
+def test_write_groups_text_is_json_dumps_text(tmp_path):
+    qids, lists = _ranked(nq=40)
+    ex = CU.groups_for_label_mode(qids, lists, "7", seed=3)
+    ex.append({"qid": -5, "relT_pids": [], "most_hard_pids": [2**62], "semi_hard_pids": [-1, 0]})
+    ex.append({"qid": 7, "relT_pids": [1], "most_hard_pids": [2], "semi_hard_pids": [3], "extra": "x"})      # not the plain shape
+    ex.append({"qid": np.int64(8), "relT_pids": [1], "most_hard_pids": [2], "semi_hard_pids": [3]})           # numpy scalar
+    out = tmp_path / "g.json"
+    ok = [e for e in ex if not isinstance(e["qid"], np.integer)]
+    assert CU.write_groups(out, ok) == len(ok)
+    assert out.read_text() == "".join(json.dumps(e) + "\n" for e in ok)
+    with pytest.raises(TypeError):
+        CU.write_groups(out, ex[-1:])          # json.dumps refuses numpy scalars: no silent change of behaviour
