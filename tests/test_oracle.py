@@ -202,3 +202,53 @@ def test_oracle_restatements_reproduce_the_reference_run_here(tmp_path):
     assert ours["text_ids"].dtype == gold["text_ids"].dtype and ours["text_ids"].tolist() == gold["text_ids"].tolist()
     assert ours["text_id_to_idx"] == gold["text_id_to_idx"] and list(ours["text_id_to_idx"]) == list(gold["text_id_to_idx"])
     assert open(os.path.join(str(tmp_path), "meta.pkl"), "rb").read() == open(os.path.join(fix, "meta.pkl"), "rb").read()
+
+
+def test_compare_topk_cannot_be_fooled_by_plausible_lists():
+    """The parity checker is what every GPU result is judged by: lists that look right but are not must fail --
+    a repeated id, a foreign id carrying the right score, a swap across the k boundary outside the near-tie band,
+    wrong padding -- and the allowances must stay as narrow as the rule says (ties as sets, boundary band only)."""
+    xb, xq = O.synth(400, 16, 8), O.synth(4, 16, 9)
+    xb[7] = xb[3]                                            # rows 3 and 7 tie exactly for every query
+    k = 30
+    D, R = O.search_rows(xb, xq, k)
+    De, Re = O.search_rows(xb, xq, k + 8, dtype=np.float64)
+    assert O.compare_topk(D, R, D, R, De, Re)["ok"]
+    # a tie pair may come in either order ...
+    for i in range(4):
+        pos = {int(r): j for j, r in enumerate(R[i])}
+        if 3 in pos and 7 in pos:
+            R2 = R.copy()
+            R2[i, pos[3]], R2[i, pos[7]] = 7, 3
+            assert O.compare_topk(D, R2, D, R, De, Re)["ok"]
+            # ... but not twice the same member
+            R3 = R.copy()
+            R3[i, pos[7]] = 3
+            assert not O.compare_topk(D, R3, D, R, De, Re)["ok"]
+    # a foreign row with the right score in its place
+    R4 = R.copy()
+    R4[0, 4] = int(Re[0, k + 5])
+    r = O.compare_topk(D, R4, D, R, De, Re)
+    assert not r["ok"] and r["bad_ids"] >= 1 and r["overlap"] < 1.0
+    # the k-th row exchanged for the (k+1)-th: excused only when fp64 says they are within the tolerance (they are not here)
+    R5, D5 = R.copy(), D.copy()
+    R5[1, k - 1] = int(Re[1, k])
+    D5[1, k - 1] = np.float32(De[1, k])
+    assert abs(De[1, k] - De[1, k - 1]) > 1e-5 * abs(De[1, k - 1])
+    assert not O.compare_topk(D5, R5, D, R, De, Re)["ok"]
+    # padding must match to the bit
+    Dp, Rp = O.search_rows(xb[:20], xq, k)
+    assert (Rp[:, 20:] == -1).all() and O.compare_topk(Dp, Rp, Dp, Rp)["ok"]
+    Rq = Rp.copy()
+    Rq[0, 25] = 0
+    assert not O.compare_topk(Dp, Rq, Dp, Rp)["ok"]
+    Dq = Dp.copy()
+    Dq[0, 25] = 0.0
+    assert not O.compare_topk(Dq, Rp, Dp, Rp)["ok"]
+    # scores: 1e-5 relative is the limit, on every position
+    D6 = D.copy()
+    D6[2, 11] = D6[2, 11] * np.float32(1 + 3e-5)
+    assert not O.compare_topk(D6, R, D, R, De, Re)["ok"]
+    D7 = D.copy()
+    D7[2, 11] = np.nextafter(D7[2, 11], np.float32(np.inf))
+    assert O.compare_topk(D7, R, D, R, De, Re)["ok"]
