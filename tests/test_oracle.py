@@ -209,12 +209,14 @@ def test_compare_topk_cannot_be_fooled_by_plausible_lists():
     a repeated id, a foreign id carrying the right score, a swap across the k boundary outside the near-tie band,
     wrong padding -- and the allowances must stay as narrow as the rule says (ties as sets, boundary band only)."""
     xb, xq = O.synth(400, 16, 8), O.synth(4, 16, 9)
-    xb[7] = xb[3]                                            # rows 3 and 7 tie exactly for every query
+    xb[3] = xq[0] * 0.5                                      # near the top for query 0 ...
+    xb[7] = xb[3]                                            # ... and rows 3 and 7 tie exactly for every query
     k = 30
     D, R = O.search_rows(xb, xq, k)
     De, Re = O.search_rows(xb, xq, k + 8, dtype=np.float64)
     assert O.compare_topk(D, R, D, R, De, Re)["ok"]
     # a tie pair may come in either order ...
+    assert {3, 7} <= set(R[0].tolist())
     for i in range(4):
         pos = {int(r): j for j, r in enumerate(R[i])}
         if 3 in pos and 7 in pos:
