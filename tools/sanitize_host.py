@@ -6,7 +6,7 @@ UndefinedBehaviorSanitizer.  CPU only:
     LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 \
         python tools/sanitize_host.py
 """
-import ctypes as C, numpy as np, os, sys, tempfile
+import ctypes as C, numpy as np, os, tempfile
 L = C.CDLL("/tmp/libhost_asan.so")
 L.cldrd_last_error.restype = C.c_char_p
 L.cldrd_format_score_selfcheck.restype = C.c_int64
